@@ -1,0 +1,152 @@
+"""Generate golden vectors by running THE REFERENCE ITSELF in the build container.
+
+    python tests/golden/make_golden.py          (needs /root/reference; not run on the GPU box)
+
+Two reference implementations are exercised, both unmodified:
+
+* the live path ``annealing_sign_problem/common.py:make_ising_model`` (:131-208), imported
+  by file path with stub modules for its absent third-party imports (h5py,
+  lattice_symmetries, ising_glass_annealer) -- the stubs provide only a container class
+  ``Hamiltonian(exchange, field)`` and a ``signs_to_bits`` following
+  cbits/build_matrix.c:67-76; the operator is the oracle's duck-typed ``OperatorNP``
+  (the reference only calls ``.basis.number_spins`` and ``.batched_apply``);
+* the legacy C path ``cbits/build_matrix.c`` compiled where it lies (oracle/_ref).
+
+Outputs ``tests/golden/*.npz`` (inputs + outputs, small) which the CPU tests use to pin
+the oracle and the GPU tests use to check the CUDA path.
+"""
+import importlib.util
+import json
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
+sys.path.insert(0, ROOT)
+
+from oracle import capi  # noqa: E402
+from oracle.live_path import signs_to_bits  # noqa: E402
+from oracle.operator_np import OperatorNP, ground_state, system_path  # noqa: E402
+
+
+def import_reference_common():
+    class Hamiltonian:
+        def __init__(self, exchange, field):
+            self.exchange, self.field = exchange, field
+            self.shape = exchange.shape
+
+    sa = types.ModuleType("ising_glass_annealer")
+    sa.Hamiltonian = Hamiltonian
+    sa.signs_to_bits = signs_to_bits
+    ls = types.ModuleType("lattice_symmetries")
+    ls.Operator = object
+    ls.SpinBasis = object
+    sys.modules.setdefault("h5py", types.ModuleType("h5py"))
+    sys.modules["ising_glass_annealer"] = sa
+    sys.modules["lattice_symmetries"] = ls
+    spec = importlib.util.spec_from_file_location(
+        "reference_common", "/root/reference/annealing_sign_problem/common.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def cluster_closed_subset(op, n_target, rng):
+    """Seeds + one batched_apply shell, truncated (mirrors make_hamiltonian_extension,
+    common.py:516-522): gives hit rates of tens of percent."""
+    states = op.basis.states
+    seeds = rng.choice(states, size=max(4, n_target // 8), replace=False)
+    shell, _, _ = op.apply_u64(np.sort(seeds))
+    pool = np.unique(np.concatenate([seeds, shell]))
+    if pool.shape[0] > n_target:
+        pool = np.sort(rng.choice(pool, size=n_target, replace=False))
+    return pool
+
+
+def synthetic_log_psi(n, rng, sigma=2.0):
+    """psi_i = +-exp(sigma z_i), as log|psi| + i*pi*[psi<0] (common.py:791-803 format)."""
+    z = rng.standard_normal(n)
+    neg = rng.random(n) < 0.5
+    return sigma * z + 1j * np.pi * neg
+
+
+def one_case(ref_common, name, n_target, seed, out):
+    rng = np.random.default_rng(seed)
+    op = OperatorNP.load(system_path(name))
+    spins = cluster_closed_subset(op, n_target, rng)
+    log_psi = synthetic_log_psi(spins.shape[0], rng)
+
+    model = ref_common.make_ising_model(spins, op, log_psi=log_psi)
+    coo = model.ising_hamiltonian.exchange
+    assert np.array_equal(model.spins, spins)
+
+    # legacy C path on the same candidates, amplitudes known for ALL candidates
+    psi = np.exp(log_psi).real
+    psi = psi / np.linalg.norm(psi)
+    other_spins, other_coeffs, other_counts = op.apply_u64(spins)
+    # amplitudes outside the set: deterministic pseudo-amplitudes keyed on the state
+    idx = np.clip(np.searchsorted(spins, other_spins), 0, spins.shape[0] - 1)
+    inside = spins[idx] == other_spins
+    h = (other_spins * np.uint64(0x9E3779B97F4A7C15)) >> np.uint64(40)
+    outside_psi = (h.astype(np.float64) / 2.0 ** 24 - 0.5) * 1e-2
+    other_psi = np.where(inside, psi[idx], outside_psi)
+    counts = np.ones(spins.shape[0], dtype=np.int64)
+    rows, cols, vals, field = capi.build_matrix(
+        spins, counts, psi, other_spins, other_coeffs, other_counts, other_psi, impl="ref")
+    signs = capi.extract_signs(psi, impl="ref")
+
+    np.savez_compressed(
+        out,
+        system=name,
+        spins=spins,
+        log_psi=log_psi,
+        live_row=coo.row.astype(np.int32),
+        live_col=coo.col.astype(np.int32),
+        live_data=coo.data,
+        live_x0=model.initial_signs,
+        other_spins=other_spins,
+        other_coeffs=other_coeffs,
+        other_counts=other_counts,
+        other_psi=other_psi,
+        c_rows=rows,
+        c_cols=cols,
+        c_vals=vals,
+        c_field=field,
+        c_signs=signs,
+    )
+    print("%-28s n=%d T=%d hits=%d live_nnz=%d -> %s (%d bytes)" % (
+        name, spins.shape[0], other_spins.shape[0], rows.shape[0], coo.nnz,
+        os.path.basename(out), os.path.getsize(out)))
+
+
+def known_answers(out):
+    """Full-basis known-answer table, recomputed by the oracle's ED."""
+    table = {}
+    for name in ["j1j2_square_4x4", "heisenberg_kagome_16", "heisenberg_kagome_18",
+                 "sk_16_1", "sk_16_2", "sk_16_3"]:
+        op = OperatorNP.load(system_path(name))
+        n = op.basis.number_states
+        s, c, k = op.apply_u64(op.basis.states)
+        e0, psi, e1 = ground_state(op)
+        table[name] = {"n": n, "T": int(s.shape[0]), "E0": e0, "gap": e1 - e0}
+        print(name, table[name])
+    with open(out, "w") as f:
+        json.dump(table, f, indent=1)
+
+
+def main():
+    if not os.path.isdir("/root/reference"):
+        sys.exit("needs /root/reference (build container only)")
+    capi.build()
+    ref_common = import_reference_common()
+    one_case(ref_common, "j1j2_square_4x4", 700, 1, os.path.join(HERE, "live_j1j2_square_4x4.npz"))
+    one_case(ref_common, "heisenberg_kagome_18", 900, 2, os.path.join(HERE, "live_heisenberg_kagome_18.npz"))
+    one_case(ref_common, "sk_16_1", 300, 3, os.path.join(HERE, "live_sk_16_1.npz"))
+    known_answers(os.path.join(HERE, "known_answers.json"))
+
+
+if __name__ == "__main__":
+    main()

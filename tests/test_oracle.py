@@ -1,0 +1,237 @@
+"""Pins the CPU oracle: against the reference's own compiled C (oracle/_ref), against golden
+vectors produced by the reference's live path (tests/golden/make_golden.py), and against
+known-answer values."""
+import itertools
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse
+
+from oracle import live_path
+from oracle.operator_np import OperatorNP, SpinBasisNP, ground_state, system_path
+
+GOLDEN = ["live_j1j2_square_4x4.npz", "live_heisenberg_kagome_18.npz", "live_sk_16_1.npz"]
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_port_matches_reference_c_golden(oracle_capi, golden_dir, name):
+    g = _load(golden_dir, name)
+    spins = g["spins"]
+    psi = np.exp(g["log_psi"]).real
+    psi = psi / np.linalg.norm(psi)
+    counts = np.ones(spins.shape[0], dtype=np.int64)
+    impls = ["port", "port64"] + (["ref"] if oracle_capi.have_ref() else [])
+    for impl in impls:
+        rows, cols, vals, field = oracle_capi.build_matrix(
+            spins, counts, psi, g["other_spins"], g["other_coeffs"], g["other_counts"], g["other_psi"], impl=impl)
+        assert np.array_equal(rows, g["c_rows"]), impl
+        assert np.array_equal(cols, g["c_cols"]), impl
+        assert np.array_equal(vals, g["c_vals"]), impl  # same association -> bitwise
+        assert np.array_equal(field, g["c_field"]), impl
+        assert np.array_equal(oracle_capi.extract_signs(psi, impl="port" if impl != "ref" else "ref"), g["c_signs"])
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_operator_restatement_reproduces_golden_candidates(golden_dir, name):
+    g = _load(golden_dir, name)
+    op = OperatorNP.load(system_path(str(g["system"])))
+    s, c, k = op.apply_u64(g["spins"])
+    assert np.array_equal(s, g["other_spins"])
+    assert np.array_equal(c, g["other_coeffs"])
+    assert np.array_equal(k, g["other_counts"])
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_canonical_csr_of_c_path_equals_live_path(oracle_capi, golden_dir, name):
+    """KAT-4: merged+sorted build_matrix.c output has the live path's indices; values agree to
+    1e-12 relative (the two reference paths associate the product differently)."""
+    g = _load(golden_dir, name)
+    n = g["spins"].shape[0]
+    indptr, indices, data = oracle_capi.canonical_csr(n, g["c_rows"], g["c_cols"], g["c_vals"])
+    live = scipy.sparse.coo_matrix((g["live_data"], (g["live_row"], g["live_col"])), shape=(n, n)).tocsr()
+    live.sort_indices()
+    keep = data != 0.0  # scipy's binop drops explicit zeros (common.py:194)
+    rows = np.repeat(np.arange(n), np.diff(indptr))[keep]
+    ours = scipy.sparse.csr_matrix((data[keep], (rows, indices[keep])), shape=(n, n))
+    ours.sort_indices()
+    assert np.array_equal(ours.indptr, live.indptr)
+    assert np.array_equal(ours.indices, live.indices)
+    # the C path is not symmetrised; the live one is: compare with 0.5 (M + M^T)
+    sym = (0.5 * (ours + ours.T)).tocsr()
+    sym.sort_indices()
+    assert np.array_equal(sym.indices, live.indices)
+    np.testing.assert_allclose(sym.data, live.data, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_live_path_restatement_is_bitwise_the_reference(golden_dir, name):
+    g = _load(golden_dir, name)
+    op = OperatorNP.load(system_path(str(g["system"])))
+    m = live_path.make_ising_model(g["spins"], op, log_psi=g["log_psi"])
+    assert np.array_equal(m.exchange.row, g["live_row"])
+    assert np.array_equal(m.exchange.col, g["live_col"])
+    assert np.array_equal(m.exchange.data, g["live_data"])
+    assert np.array_equal(m.initial_signs, g["live_x0"])
+    assert not m.field.any()
+
+
+def test_extract_signs_edge_cases(oracle_capi):
+    """KAT-5: strict >0, zeros/-0/NaN -> bit 0, n not a multiple of 64, tail bits zero."""
+    rng = np.random.default_rng(0)
+    for n in [0, 1, 63, 64, 65, 130, 1000]:
+        psi = rng.standard_normal(n)
+        if n > 4:
+            psi[1], psi[2], psi[3] = 0.0, -0.0, np.nan
+        bits = oracle_capi.extract_signs(psi)
+        assert bits.shape[0] == (n + 63) // 64
+        expect = live_path.signs_to_bits(np.where(psi > 0, 1.0, -1.0))
+        assert np.array_equal(bits, expect)
+        back = live_path.bits_to_signs(bits, n)
+        assert np.array_equal(back > 0, psi > 0)
+        if oracle_capi.have_ref():
+            assert np.array_equal(oracle_capi.extract_signs(psi, impl="ref"), bits)
+
+
+def test_known_answer_energy_of_exact_signs(oracle_capi, golden_dir):
+    """KAT-1/3/6 on the full basis of j1j2_square_4x4 and heisenberg_kagome_16."""
+    table = json.load(open(os.path.join(golden_dir, "known_answers.json")))
+    for name in ["j1j2_square_4x4", "heisenberg_kagome_16"]:
+        op = OperatorNP.load(system_path(name))
+        e0, psi, _ = ground_state(op)
+        assert abs(e0 - table[name]["E0"]) < 1e-9
+        spins = op.basis.states
+        assert spins.shape[0] == table[name]["n"]
+        m = live_path.make_ising_model(spins, op, log_psi=np.log(psi.astype(np.complex128)))
+        assert m.exchange.nnz == table[name]["T"] or name != "j1j2_square_4x4"
+        csr = m.exchange.tocsr()
+        assert abs(csr - csr.T).max() == 0.0
+        e = oracle_capi.energy(csr.indptr, csr.indices, csr.data, None, m.initial_signs)
+        assert abs(e - e0) < 1e-10
+        # variational bound: a random configuration is never below E0
+        rnd = np.random.default_rng(1).integers(0, 2 ** 63, size=m.initial_signs.shape[0], dtype=np.uint64)
+        assert oracle_capi.energy(csr.indptr, csr.indices, csr.data, None, rnd) >= e0 - 1e-10
+
+
+def test_inversion_basis_kagome_18_counts(golden_dir):
+    table = json.load(open(os.path.join(golden_dir, "known_answers.json")))
+    op = OperatorNP.load(system_path("heisenberg_kagome_18"))
+    assert op.basis.number_states == table["heisenberg_kagome_18"]["n"] == 24310
+    s, c, k = op.apply_u64(op.basis.states)
+    assert s.shape[0] == table["heisenberg_kagome_18"]["T"] == 487630
+
+
+def test_permutation_group_closure_orders():
+    from oracle.operator_np import load_config
+
+    for name, order in [("heisenberg_kagome_36", 144 * 2), ("heisenberg_pyrochlore_2x2x2", 384 * 2)]:
+        basis = SpinBasisNP.from_config(load_config(system_path(name))["basis"])
+        assert basis.group_order == order
+
+
+def test_symmetrised_operator_is_hermitian_small():
+    """A 12-site ring with translations + inversion: H in the symmetrised basis is symmetric and
+    its spectrum is a subset of the unsymmetrised one."""
+    n = 12
+    cfg = {
+        "basis": {"number_spins": n, "hamming_weight": n // 2, "spin_inversion": 1,
+                  "symmetries": [{"permutation": [(i + 1) % n for i in range(n)], "sector": 0}]},
+        "hamiltonian": {"terms": [{"matrix": [[1, 0, 0, 0], [0, -1, 2, 0], [0, 2, -1, 0], [0, 0, 0, 1]],
+                                   "sites": [[i, (i + 1) % n] for i in range(n)]}]},
+    }
+    sym = OperatorNP.from_config(cfg)
+    hs = sym.to_sparse().toarray()
+    np.testing.assert_allclose(hs, hs.T, atol=1e-12)
+    cfg_full = json.loads(json.dumps(cfg))
+    cfg_full["basis"]["spin_inversion"] = None
+    cfg_full["basis"]["symmetries"] = []
+    hf = OperatorNP.from_config(cfg_full).to_sparse().toarray()
+    ws, wf = np.linalg.eigvalsh(hs), np.linalg.eigvalsh(hf)
+    assert abs(ws[0] - wf[0]) < 1e-10  # ground state lives in the trivial sector
+    for w in ws:
+        assert np.min(np.abs(wf - w)) < 1e-9
+
+
+def test_philox_known_answers(oracle_capi):
+    """Random123 kat_vectors for philox4x32-10."""
+    kat = [
+        ([0, 0, 0, 0], [0, 0], [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]),
+        ([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2, [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]),
+        ([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0],
+         [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]),
+    ]
+    for ctr, key, out in kat:
+        assert [int(v) for v in oracle_capi.philox(ctr, key)] == out
+
+
+def test_exp_neg_accuracy(oracle_capi):
+    for x in np.concatenate([np.linspace(1e-9, 22.99, 4001), [1e-300, 0.5, 1.0, 22.999999]]):
+        assert abs(oracle_capi.exp_neg(x) / math.exp(-x) - 1.0) < 4e-15  # x*log2(e) rounds once: error grows like x * 2^-53
+
+
+def _random_model(n, density, rng):
+    a = scipy.sparse.random(n, n, density=density, random_state=rng, data_rvs=rng.standard_normal).tocsr()
+    a = (a + a.T).tocsr()
+    a.setdiag(rng.standard_normal(n))
+    a.sort_indices()
+    return a
+
+
+def test_anneal_finds_brute_force_minimum(oracle_capi):
+    rng = np.random.default_rng(5)
+    n = 14
+    j = _random_model(n, 0.4, rng)
+    h = rng.standard_normal(n) * 0.3
+    dense = j.toarray()
+    best = min(
+        float(np.dot(s, dense @ s) + np.dot(h, s))
+        for s in (np.array(b) * 2.0 - 1.0 for b in itertools.product([0, 1], repeat=n)))
+    betas = live_path.default_betas(j.indptr, j.indices, j.data, h, 200)
+    bits, best_rel, final_rel = oracle_capi.anneal(j.indptr, j.indices, j.data, h, 16, betas, seed=7)
+    energies = [oracle_capi.energy(j.indptr, j.indices, j.data, h, b) for b in bits]
+    assert abs(min(energies) - best) < 1e-10
+    assert np.all(best_rel <= final_rel) and np.all(best_rel <= 0)
+    # determinism + thread-count independence
+    bits2, rel2, _ = oracle_capi.anneal(j.indptr, j.indices, j.data, h, 16, betas, seed=7, threads=1)
+    assert np.array_equal(bits, bits2) and np.array_equal(best_rel, rel2)
+    bits3, _, _ = oracle_capi.anneal(j.indptr, j.indices, j.data, h, 16, betas, seed=8)
+    assert not np.array_equal(bits, bits3)
+
+
+def test_anneal_respects_x0_and_running_energy(oracle_capi):
+    rng = np.random.default_rng(6)
+    n = 70
+    j = _random_model(n, 0.1, rng)
+    x0 = rng.integers(0, 2 ** 63, size=2, dtype=np.uint64)
+    x0[1] &= np.uint64((1 << (n - 64)) - 1)
+    escale = 2.0 ** 40
+    betas = live_path.default_betas(j.indptr, j.indices, j.data, None, 50)
+    bits, best_rel, _ = oracle_capi.anneal(j.indptr, j.indices, j.data, None, 4, betas, seed=1, x0=x0, escale=escale)
+    e_start = oracle_capi.energy(j.indptr, j.indices, j.data, None, x0)
+    for r in range(4):
+        e = oracle_capi.energy(j.indptr, j.indices, j.data, None, bits[r])
+        assert abs((e - e_start) - best_rel[r] / escale) < 1e-8
+    # zero sweeps at infinite beta from a local minimum stays put
+    betas_inf = np.full(3, np.inf)
+    b2, rel2, _ = oracle_capi.anneal(j.indptr, j.indices, j.data, None, 1, betas_inf, seed=1, x0=bits[0])
+    assert rel2[0] <= 0
+
+
+def test_accuracy_and_overlap_restatement():
+    rng = np.random.default_rng(2)
+    n = 200
+    a = rng.choice([-1.0, 1.0], size=n)
+    b = a.copy()
+    b[:17] *= -1
+    w = rng.random(n)
+    acc, ov = live_path.compute_accuracy_and_overlap(live_path.signs_to_bits(b), live_path.signs_to_bits(a), w)
+    assert abs(acc - (n - 17) / n) < 1e-15
+    assert abs(ov - abs(np.dot(a * b, w / w.sum()))) < 1e-15
+    acc2, ov2 = live_path.compute_accuracy_and_overlap(live_path.signs_to_bits(-b), live_path.signs_to_bits(a), w)
+    assert abs(acc2 - acc) < 1e-15 and abs(ov2 - ov) < 1e-15  # global-flip invariant
