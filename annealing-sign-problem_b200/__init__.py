@@ -1,0 +1,16 @@
+"""B200-native drop-in for the hot path of twesterhout/annealing-sign-problem:
+Ising-model extraction (``make_ising_model``) and replica simulated annealing
+(``solve_ising_model``), behind the reference's own Python entry points
+(annealing_sign_problem/common.py:131-261)."""
+__version__ = "0.1.0"
+
+from .common import (  # noqa: F401
+    IsingModel,
+    binary_search,
+    compute_accuracy_and_overlap,
+    load_hamiltonian,
+    make_ising_model,
+    solve_ising_model,
+)
+from . import annealer as sa  # noqa: F401  (plays the role of `import ising_glass_annealer as sa`)
+from . import symmetries as ls  # noqa: F401  (plays the role of `import lattice_symmetries as ls`)

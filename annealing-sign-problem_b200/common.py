@@ -1,0 +1,313 @@
+"""The reference's hot-path entry points (annealing_sign_problem/common.py:46-261, 544-548,
+782-787) with the same names, arguments and error behaviour, running on the B200 through
+libasp_b200.so.  ``import annealing_sign_problem_b200.common as common`` is the drop-in for
+``import annealing_sign_problem.common as common`` as far as this path is concerned.
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass
+from typing import Callable, Optional, Tuple
+
+import numpy as np
+import scipy.sparse
+import torch
+
+from . import annealer as sa
+from . import symmetries as ls
+from ._lib import AspError, check, ffi, lib, ptr, require_cuda, stream
+
+try:  # the reference logs through loguru (common.py:15); stay quiet if it is absent
+    from loguru import logger
+except Exception:  # pragma: no cover
+    import logging
+
+    logger = logging.getLogger("annealing_sign_problem_b200")
+
+_SIGN_BIT = -0x8000000000000000
+
+
+@dataclass
+class IsingModel:  # common.py:46-55
+    spins: np.ndarray
+    quantum_hamiltonian: object
+    ising_hamiltonian: sa.Hamiltonian
+    initial_signs: np.ndarray
+
+    @property
+    def size(self):
+        return self.spins.shape[0]
+
+
+def load_hamiltonian(filename: str) -> ls.Operator:  # common.py:782-787
+    config = ls.load_config(filename)
+    basis = ls.SpinBasis.load_from_yaml(config["basis"])
+    return ls.Operator.load_from_yaml(config["hamiltonian"], basis)
+
+
+def _normalize_spins_1d(spins) -> np.ndarray:
+    """common.py:58-68 accepts [n] or [n,8]; every caller keeps only column 0 (:100)."""
+    spins = np.asarray(spins, dtype=np.uint64, order="C")
+    if spins.ndim <= 1:
+        return np.ascontiguousarray(spins.reshape(-1))
+    if spins.ndim == 2:
+        if spins.shape[1] != 8:
+            raise ValueError("'spins' has wrong shape: {}; expected (?, 8)".format(spins.shape))
+        if spins[:, 1:].any():
+            raise ValueError("only works with up to 64 bits")
+        return np.ascontiguousarray(spins[:, 0])
+    raise ValueError("'spins' has wrong shape: {}; expected a 2D array".format(spins.shape))
+
+
+def _sort_unique_device(x: torch.Tensor):
+    """Ascending UNSIGNED order of int64 bit patterns; -> (unique sorted, index of first
+    occurrence, counts), i.e. np.unique(..., return_index=True, return_counts=True)."""
+    keys = x ^ _SIGN_BIT
+    sorted_keys, perm = torch.sort(keys, stable=True)
+    n = sorted_keys.shape[0]
+    if n == 0:
+        return x, perm, torch.zeros(0, dtype=torch.int64, device=x.device)
+    head = torch.ones(n, dtype=torch.bool, device=x.device)
+    head[1:] = sorted_keys[1:] != sorted_keys[:-1]
+    starts = torch.nonzero(head).reshape(-1)
+    counts = torch.diff(starts, append=torch.tensor([n], device=x.device))
+    return sorted_keys[starts] ^ _SIGN_BIT, perm[starts], counts
+
+
+# ---------------------------------------------------------------------------------------
+# Device-resident extraction (what bench.py times as `value`; host wrappers below add I/O)
+# ---------------------------------------------------------------------------------------
+def extract_csr_device(operator: ls.Operator, spins: torch.Tensor, psi: torch.Tensor,
+                       row_begin: int = 0, num_rows: Optional[int] = None, workspace: Optional[torch.Tensor] = None):
+    """Rows [row_begin, row_begin+num_rows) of J against the full sorted basis ``spins``.
+
+    spins: int64 bit patterns, ascending (unsigned), unique, CUDA.  psi: f64 CUDA, same length.
+    -> (indptr int64 [num_rows+1], indices int32 [nnz] global columns, data f64 [nnz]).
+    """
+    dev = require_cuda()
+    n_total = int(spins.shape[0])
+    if num_rows is None:
+        num_rows = n_total - row_begin
+    if operator.is_sorted_emitter:
+        need = int(lib().asp_extract_workspace_bytes(operator.handle, n_total, num_rows))
+        if workspace is None or workspace.numel() < need:
+            workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+        nnz = ffi.new("uint64_t *")
+        check(lib().asp_extract_count(operator.handle, n_total, ptr(spins, "uint64_t *"), row_begin, num_rows,
+                                      ptr(workspace, "void *"), workspace.numel(), nnz, stream()))
+        indptr = torch.empty(num_rows + 1, dtype=torch.int64, device=dev)
+        indices = torch.empty(int(nnz[0]), dtype=torch.int32, device=dev)
+        data = torch.empty(int(nnz[0]), dtype=torch.float64, device=dev)
+        check(lib().asp_extract_fill(operator.handle, n_total, ptr(spins, "uint64_t *"), ptr(psi, "double *"),
+                                     row_begin, num_rows, ptr(workspace, "void *"), workspace.numel(),
+                                     ptr(indptr, "int64_t *"), ptr(indices, "int32_t *"), ptr(data, "double *"), stream()))
+        return indptr, indices, data
+    # symmetrised / non-sorted operators: neighbour lists on the device, then the
+    # explicit-candidate kernel, then canonicalisation
+    rows = spins[row_begin:row_begin + num_rows]
+    other_spins, other_coeffs, other_counts = operator.batched_apply_device(rows)
+    return build_csr_from_candidates_device(spins, psi, row_begin, other_spins, other_coeffs, other_counts,
+                                            max_row_len=operator.max_candidates)
+
+
+def build_csr_from_candidates_device(spins, psi, row_begin, other_spins, other_coeffs, other_counts, max_row_len=0):
+    """Explicit-candidate path (what cbits/build_matrix.c does) + canonical CSR."""
+    dev = require_cuda()
+    n_total = int(spins.shape[0])
+    num_rows = int(other_counts.shape[0])
+    T = int(other_spins.shape[0])
+    other_counts = other_counts.contiguous()
+    offsets = torch.empty(num_rows + 1, dtype=torch.int64, device=dev)
+    tmp = torch.empty(int(lib().asp_scan_tmp_bytes(num_rows)), dtype=torch.uint8, device=dev)
+    check(lib().asp_exclusive_scan_i64(ptr(other_counts, "int64_t *"), ptr(offsets, "int64_t *"),
+                                       num_rows, ptr(tmp, "void *"), stream()))
+    row_offsets = torch.empty(num_rows + 1, dtype=torch.int64, device=dev)
+    rows = torch.empty(max(T, 1), dtype=torch.int32, device=dev)
+    cols = torch.empty(max(T, 1), dtype=torch.int32, device=dev)
+    vals = torch.empty(max(T, 1), dtype=torch.float64, device=dev)
+    nnz = ffi.new("uint64_t *")
+    # other_psi = NULL: a hit takes |psi[column]| (live-path semantics, common.py:71-82)
+    check(lib().asp_build_matrix_dev(
+        n_total, ptr(spins, "uint64_t *"), row_begin, num_rows, ffi.NULL, ptr(psi, "double *"),
+        ptr(other_spins.contiguous(), "uint64_t *"), ptr(other_coeffs.contiguous(), "double *"),
+        ptr(offsets, "int64_t *"), ffi.NULL, ptr(row_offsets, "int64_t *"), ptr(rows, "uint32_t *"),
+        ptr(cols, "uint32_t *"), ptr(vals, "double *"), ffi.NULL, T, nnz, stream()))
+    m = int(nnz[0])
+    if max_row_len == 0:
+        max_row_len = int(other_counts.max()) if num_rows else 1
+    return canonicalize_csr_device(num_rows, row_offsets, cols, vals, m, max_row_len)
+
+
+def canonicalize_csr_device(num_rows, row_offsets, cols, vals, nnz_in, max_row_len):
+    """Stable column sort inside each row + duplicates summed in generation order
+    (asp_csr_canonicalize)."""
+    dev = cols.device
+    indptr = torch.empty(num_rows + 1, dtype=torch.int64, device=dev)
+    indices = torch.empty(max(nnz_in, 1), dtype=torch.int32, device=dev)
+    data = torch.empty(max(nnz_in, 1), dtype=torch.float64, device=dev)
+    nnz = ffi.new("uint64_t *")
+    check(lib().asp_csr_canonicalize(num_rows, max_row_len, ptr(row_offsets, "int64_t *"), ptr(cols, "uint32_t *"),
+                                     ptr(vals, "double *"), nnz_in, ptr(indptr, "int64_t *"),
+                                     ptr(indices, "int32_t *"), ptr(data, "double *"), nnz, stream()))
+    m = int(nnz[0])
+    return indptr, indices[:m].contiguous(), data[:m].contiguous()
+
+
+def symmetrize_csr_device(n: int, indptr, indices, data) -> None:
+    """In place 0.5 (J + J^T) (common.py:194) for a structurally symmetric J."""
+    missing = ffi.new("uint64_t *")
+    check(lib().asp_csr_symmetrize(n, ptr(indptr, "int64_t *"), ptr(indices, "int32_t *"), ptr(data, "double *"),
+                                   missing, stream()))
+    if missing[0]:
+        raise AspError("the extracted matrix is not structurally symmetric ({} unmatched entries): "
+                       "a non-Hermitian operator is outside the hot path".format(int(missing[0])))
+
+
+# ---------------------------------------------------------------------------------------
+# make_ising_model -- common.py:131-208
+# ---------------------------------------------------------------------------------------
+def make_ising_model(
+    spins,
+    quantum_hamiltonian,
+    log_psi=None,
+    log_psi_fn: Optional[Callable] = None,
+    external_field: bool = False,
+    debug: bool = False,
+):
+    start_time = time.time()
+    if log_psi is None and log_psi_fn is None:
+        raise ValueError("at least one of log_psi or log_psi_fn should be specified")
+    if external_field and log_psi_fn is None:
+        raise ValueError("log_psi_fn should be specified when external_field=True")
+    if external_field:
+        assert False  # common.py:199-200: the reference's branch is `assert False`
+    assert quantum_hamiltonian.basis.number_spins <= 64, "TODO: only works with up to 64 bits"
+    dev = require_cuda()
+
+    spins = _normalize_spins_1d(spins)
+    d_spins_in = torch.from_numpy(spins.view(np.int64)).to(dev)
+    d_spins, first, counts = _sort_unique_device(d_spins_in)
+    if bool((counts != 1).any()):
+        logger.warning("'spins' were not unique, are you sure this is what you want?")
+    if log_psi is not None:
+        log_psi = np.asarray(log_psi)[first.cpu().numpy()]  # first occurrence, sorted order (common.py:149-151)
+    spins = d_spins.cpu().numpy().view(np.uint64)
+    if log_psi is None:
+        log_psi = log_psi_fn(spins)
+    n = spins.shape[0]
+
+    d_log_psi = torch.from_numpy(np.ascontiguousarray(log_psi, dtype=np.complex128)).to(dev)
+    psi = torch.exp(d_log_psi)
+    if not bool(torch.all(psi.imag.abs() <= 1e-6)):
+        raise ValueError("expected all wavefunction coefficients to be real")
+    psi = psi.real.contiguous()
+    psi = psi / torch.linalg.norm(psi)
+
+    tick = time.time()
+    if isinstance(quantum_hamiltonian, ls.Operator):
+        indptr, indices, data = extract_csr_device(quantum_hamiltonian, d_spins, psi)
+    else:
+        # a foreign ls.Operator-like object: its own batched_apply generates the neighbours
+        # (chunked exactly as common.py:85-106), the search/coupling/CSR still run on the GPU
+        out_s, out_c, out_k = [], [], []
+        for start in range(0, n, 10000):
+            x = np.zeros((min(start + 10000, n) - start, 8), dtype=np.uint64)
+            x[:, 0] = spins[start:start + 10000]
+            s, c, k = quantum_hamiltonian.batched_apply(x)
+            if not np.allclose(c.imag, 0, atol=1e-6):
+                raise ValueError("expected all Hamiltonian matrix elements to be real")
+            out_s.append(np.ascontiguousarray(s[:, 0]))
+            out_c.append(np.ascontiguousarray(c.real))
+            out_k.append(np.asarray(k, dtype=np.int64))
+        indptr, indices, data = build_csr_from_candidates_device(
+            d_spins, psi, 0,
+            torch.from_numpy(np.hstack(out_s).view(np.int64)).to(dev),
+            torch.from_numpy(np.hstack(out_c)).to(dev),
+            torch.from_numpy(np.hstack(out_k)).to(dev))
+    symmetrize_csr_device(n, indptr, indices, data)
+    if bool((data == 0).any()):  # scipy's binop drops explicit zeros (common.py:194)
+        keep = data != 0
+        rows = torch.repeat_interleave(torch.arange(n, device=dev), indptr[1:] - indptr[:-1])[keep]
+        indices, data = indices[keep].contiguous(), data[keep].contiguous()
+        indptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        indptr[1:] = torch.cumsum(torch.bincount(rows, minlength=n), 0)
+    torch.cuda.synchronize()
+    tock = time.time()
+    logger.debug("extraction took {:.4f} seconds", tock - tick)
+
+    h_indptr = indptr.cpu().numpy()
+    h_indices = indices.cpu().numpy()
+    h_data = data.cpu().numpy()
+    matrix = scipy.sparse.csr_matrix((h_data, h_indices, h_indptr.astype(np.int32) if h_data.shape[0] < 2 ** 31 else h_indptr),
+                                     shape=(n, n)).tocoo()
+    field = np.zeros(n, dtype=np.float64)
+    ising_hamiltonian = sa.Hamiltonian(matrix, field, _device_csr=(indptr, indices, data, None))
+    x0 = sa.signs_to_bits_device(psi).cpu().numpy().view(np.uint64)
+    logger.debug("Took {:.2} seconds", time.time() - start_time)
+    return IsingModel(spins, quantum_hamiltonian, ising_hamiltonian, x0)
+
+
+# ---------------------------------------------------------------------------------------
+# compute_accuracy_and_overlap -- common.py:211-229
+# ---------------------------------------------------------------------------------------
+def compute_accuracy_and_overlap(predicted, exact, weights=None, number_spins: Optional[int] = None) -> Tuple[float, float]:
+    if weights is None and number_spins is None:
+        raise ValueError("'weights' and 'number_spins' cannot be both None")
+    if number_spins is None:
+        number_spins = len(weights)
+    acc, ov = accuracy_and_overlap_batched(np.asarray(predicted, dtype=np.uint64).reshape(1, -1), exact, weights, number_spins)
+    return float(acc[0]), float(ov[0])
+
+
+def accuracy_and_overlap_batched(predicted, exact, weights, number_spins: int):
+    """All replicas at once (full_hilbert_space.py:164-186 loops over repetitions on the CPU)."""
+    dev = require_cuda()
+    p = torch.from_numpy(np.ascontiguousarray(predicted, dtype=np.uint64).view(np.int64)).to(dev)
+    e = torch.from_numpy(np.ascontiguousarray(exact, dtype=np.uint64).view(np.int64)).to(dev)
+    w = None if weights is None else torch.from_numpy(np.ascontiguousarray(weights, dtype=np.float64)).to(dev)
+    acc = torch.empty(p.shape[0], dtype=torch.float64, device=dev)
+    ov = torch.empty(p.shape[0], dtype=torch.float64, device=dev)
+    check(lib().asp_accuracy_overlap(number_spins, p.shape[0], ptr(p, "uint64_t *"), ptr(e, "uint64_t *"),
+                                     ptr(w, "double *"), ptr(acc, "double *"), ptr(ov, "double *"), stream()))
+    return acc.cpu().numpy(), ov.cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------
+# solve_ising_model -- common.py:232-261
+# ---------------------------------------------------------------------------------------
+def binary_search(haystack, needles):  # common.py:544-548
+    haystack = np.asarray(haystack)
+    assert np.all(np.sort(haystack) == haystack)
+    indices = np.searchsorted(haystack, needles)
+    assert np.all(haystack[indices] == needles)
+    return indices
+
+
+def solve_ising_model(
+    model: IsingModel,
+    mode: str = "sa",
+    frozen_spins=None,
+    seed: int = 12345,
+    number_sweeps: int = 5120,
+    repetitions: int = 64,
+    only_best: bool = True,
+):
+    if mode == "sa":
+        x, _ = sa.anneal(
+            model.ising_hamiltonian,
+            seed=seed,
+            number_sweeps=number_sweeps,
+            repetitions=repetitions,
+            only_best=only_best,
+        )
+    elif mode == "greedy":
+        x, _ = sa.greedy_solve(model.ising_hamiltonian)
+    else:
+        raise ValueError("invalid mode specified: '{}'; expected either 'sa' or 'greedy'".format(mode))
+
+    if frozen_spins is not None:
+        frozen_indices = binary_search(model.spins, frozen_spins)
+        frozen_signs = sa.bits_to_signs(x, count=model.spins.size)
+        frozen_signs = frozen_signs[frozen_indices]
+        x = sa.signs_to_bits(frozen_signs)
+    return x

@@ -1,0 +1,339 @@
+// Neighbour generation on the device with the contract of lattice_symmetries'
+// Operator.batched_apply (as called at annealing_sign_problem/common.py:96), including the
+// symmetrised case: image -> orbit representative min_g g(s'), coefficient scaled by
+// chi(g) * norm(rep)/norm(s), norm(x)^2 = sum_g chi(g)[g x == x] / |G|.
+// Plus the canonicalisation kernel (stable per-row column sort + duplicate merge) that
+// turns generation-order rows into the canonical CSR of common.py:193-195.
+#include "operator.cuh"
+
+namespace asp {
+
+struct SymmetryView {
+  const BitPerm *perms;
+  const double *characters;
+  int num_perms;        // non-identity elements
+  int spin_inversion;   // 0, +1, -1
+  uint64_t state_mask;
+  double group_order;   // (num_perms + 1) * (inversion ? 2 : 1)
+};
+
+__device__ __forceinline__ uint64_t delta_swap(uint64_t x, uint64_t m, int d) {
+  const uint64_t t = ((x >> d) ^ x) & m;
+  return x ^ t ^ (t << d);
+}
+
+__device__ __forceinline__ uint64_t permute(const BitPerm &p, uint64_t x) {
+#pragma unroll
+  for (int k = 0; k < 6; ++k) x = delta_swap(x, p.mask[k], 32 >> k);
+#pragma unroll
+  for (int k = 6; k < 11; ++k) x = delta_swap(x, p.mask[k], 2 << (k - 6));
+  return x;
+}
+
+// -> representative, character of the element reaching it, norm
+__device__ __forceinline__ void state_info(const SymmetryView &g, const BitPerm *s_perms, uint64_t c, uint64_t &rep, double &chi_rep, double &norm) {
+  rep = c;
+  chi_rep = 1.0;
+  double stab = 0.0;
+  for (int e = -1; e < g.num_perms; ++e) {
+    const uint64_t y0 = e < 0 ? c : permute(s_perms[e], c);
+    const double chi0 = e < 0 ? 1.0 : g.characters[e];
+    if (y0 == c) stab += chi0;
+    if (y0 < rep) {
+      rep = y0;
+      chi_rep = chi0;
+    }
+    if (g.spin_inversion) {
+      const uint64_t y1 = ~y0 & g.state_mask;
+      const double chi1 = chi0 * static_cast<double>(g.spin_inversion);
+      if (y1 == c) stab += chi1;
+      if (y1 < rep) {
+        rep = y1;
+        chi_rep = chi1;
+      }
+    }
+  }
+  norm = sqrt(fmax(stab, 0.0) / g.group_order);
+}
+
+struct ApplyArgs {
+  uint64_t num_rows;
+  const uint64_t *spins;
+  const Move *moves;
+  int n_moves, n_down;
+  const DiagBond *diag;
+  int n_diag;
+  SymmetryView sym;
+  bool symmetrised;
+  int64_t *counts;         // pass 1 out / unused
+  const int64_t *offsets;  // pass 2 in
+  uint64_t *other_spins;
+  double *other_coeffs;
+};
+
+constexpr int kApplyThreads = 128;
+
+template <bool kFill>
+__global__ void __launch_bounds__(kApplyThreads) apply_kernel(const ApplyArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Move *s_moves = reinterpret_cast<Move *>(smem_raw);
+  DiagBond *s_diag = reinterpret_cast<DiagBond *>(s_moves + a.n_moves);
+  BitPerm *s_perms = reinterpret_cast<BitPerm *>(s_diag + a.n_diag);
+  for (int k = threadIdx.x; k < a.n_moves; k += blockDim.x) s_moves[k] = a.moves[k];
+  for (int k = threadIdx.x; k < a.n_diag; k += blockDim.x) s_diag[k] = a.diag[k];
+  for (int k = threadIdx.x; k < a.sym.num_perms; k += blockDim.x) s_perms[k] = a.sym.perms[k];
+  __syncthreads();
+  const uint64_t r = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= a.num_rows) return;
+  const uint64_t s = a.spins[r];
+  double norm_s = 1.0;
+  if (a.symmetrised) {
+    uint64_t rep;
+    double chi;
+    state_info(a.sym, s_perms, s, rep, chi, norm_s);
+  }
+  int64_t out = kFill ? a.offsets[r] : 0;
+  int64_t cnt = 0;
+  auto emit = [&](uint64_t c, double coef) {
+    if (a.symmetrised) {
+      uint64_t rep;
+      double chi, norm;
+      state_info(a.sym, s_perms, c, rep, chi, norm);
+      if (norm == 0.0) return;  // outside the symmetry sector
+      c = rep;
+      coef = coef * ((chi * norm) / norm_s);
+    }
+    if (kFill) {
+      a.other_spins[out + cnt] = c;
+      a.other_coeffs[out + cnt] = coef;
+    }
+    ++cnt;
+  };
+  for (int m = 0; m < a.n_down; ++m) {
+    const Move mv = s_moves[m];
+    if ((s & mv.mask) == mv.need) emit(s ^ mv.flip, mv.coef);
+  }
+  {
+    double d = 0.0;
+    if (kFill)
+      for (int k = 0; k < a.n_diag; ++k) {
+        const DiagBond db = s_diag[k];
+        d += db.d[((s >> db.i) & 1) * 2 + ((s >> db.j) & 1)];
+      }
+    emit(s, d);
+  }
+  for (int m = a.n_down; m < a.n_moves; ++m) {
+    const Move mv = s_moves[m];
+    if ((s & mv.mask) == mv.need) emit(s ^ mv.flip, mv.coef);
+  }
+  if (!kFill) a.counts[r] = cnt;
+}
+
+// ---- canonicalisation: one warp per row, bitonic sort of (col, seq) keys in smem --------
+constexpr int kCanonThreads = 128;
+constexpr int kCanonMaxRow = 1024;
+
+__global__ void __launch_bounds__(kCanonThreads) canonicalize_kernel(uint64_t num_rows, int row_capacity /* power of two */, const int64_t *__restrict__ row_offsets,
+                                                                        const uint32_t *__restrict__ cols, const double *__restrict__ vals,
+                                                                        uint32_t *__restrict__ tmp_cols, double *__restrict__ tmp_vals,
+                                                                        int64_t *__restrict__ merged_counts, int *__restrict__ overflow) {
+  extern __shared__ __align__(16) unsigned char canon_smem[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  constexpr int kWarps = kCanonThreads / 32;
+  uint64_t *key = reinterpret_cast<uint64_t *>(canon_smem) + static_cast<size_t>(w) * row_capacity;
+  double *val = reinterpret_cast<double *>(canon_smem) + static_cast<size_t>(kWarps) * row_capacity + static_cast<size_t>(w) * row_capacity;
+  const uint64_t r = static_cast<uint64_t>(blockIdx.x) * kWarps + w;
+  if (r >= num_rows) return;
+  const int64_t begin = row_offsets[r];
+  const int len = static_cast<int>(row_offsets[r + 1] - begin);
+  if (len > row_capacity) {
+    if (lane == 0) {
+      atomicExch(overflow, 1);
+      merged_counts[r] = 0;
+    }
+    return;
+  }
+  int P = 1;
+  while (P < len) P <<= 1;
+  for (int e = lane; e < P; e += 32) {
+    key[e] = e < len ? (static_cast<uint64_t>(cols[begin + e]) << 32 | static_cast<uint32_t>(e)) : ~0ull;
+    val[e] = e < len ? vals[begin + e] : 0.0;
+  }
+  __syncwarp();
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < P; i += 32) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const bool asc = (i & k) == 0;
+          const uint64_t a = key[i], b = key[ixj];
+          if ((a > b) == asc) {
+            key[i] = b;
+            key[ixj] = a;
+            const double t = val[i];
+            val[i] = val[ixj];
+            val[ixj] = t;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  // heads of equal-column runs sum their run in generation (seq) order
+  int written = 0;
+  for (int base = 0; base < len; base += 32) {
+    const int e = base + lane;
+    bool head = false;
+    uint32_t col = 0;
+    double sum = 0.0;
+    if (e < len) {
+      col = static_cast<uint32_t>(key[e] >> 32);
+      head = e == 0 || static_cast<uint32_t>(key[e - 1] >> 32) != col;
+      if (head) {
+        sum = val[e];
+        for (int f = e + 1; f < len && static_cast<uint32_t>(key[f] >> 32) == col; ++f) sum += val[f];
+      }
+    }
+    const uint32_t ballot = __ballot_sync(0xffffffffu, head);
+    if (head) {
+      const int pos = written + __popc(ballot & ((1u << lane) - 1));
+      tmp_cols[begin + pos] = col;
+      tmp_vals[begin + pos] = sum;
+    }
+    written += __popc(ballot);
+  }
+  if (lane == 0) merged_counts[r] = written;
+}
+
+__global__ void __launch_bounds__(256) compact_rows_kernel(uint64_t num_rows, const int64_t *__restrict__ row_offsets, const int64_t *__restrict__ indptr,
+                                                           const uint32_t *__restrict__ tmp_cols, const double *__restrict__ tmp_vals,
+                                                           int32_t *__restrict__ indices, double *__restrict__ data) {
+  const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= num_rows) return;
+  const int64_t src = row_offsets[warp], dst = indptr[warp];
+  const int64_t len = indptr[warp + 1] - dst;
+  for (int64_t e = lane; e < len; e += 32) {
+    indices[dst + e] = static_cast<int32_t>(tmp_cols[src + e]);
+    data[dst + e] = tmp_vals[src + e];
+  }
+}
+
+}  // namespace asp
+
+using namespace asp;
+
+extern "C" {
+
+int asp_operator_apply_dev(asp_operator const *op, uint64_t num_rows, uint64_t const *d_spins, uint64_t *d_other_spins,
+                           double *d_other_coeffs, int64_t *d_counts, uint64_t capacity, uint64_t *h_total, void *stream) {
+  auto s = static_cast<cudaStream_t>(stream);
+  ASP_REQUIRE(op != nullptr && op->d_moves != nullptr, "operator is NULL or has no device mirror");
+  ASP_REQUIRE(h_total != nullptr, "h_total is NULL");
+  *h_total = 0;
+  if (num_rows == 0) return ASP_OK;
+  ASP_REQUIRE(d_spins && d_counts, "NULL buffer");
+  ApplyArgs a{};
+  a.num_rows = num_rows;
+  a.spins = d_spins;
+  a.moves = op->d_moves;
+  a.n_moves = static_cast<int>(op->moves.size());
+  a.n_down = static_cast<int>(op->n_down);
+  a.diag = op->d_diag;
+  a.n_diag = static_cast<int>(op->diag.size());
+  a.symmetrised = op->symmetrised();
+  a.sym.perms = op->d_perms;
+  a.sym.characters = op->d_characters;
+  a.sym.num_perms = static_cast<int>(op->perms.size());
+  a.sym.spin_inversion = op->spin_inversion;
+  a.sym.state_mask = op->state_mask;
+  a.sym.group_order = static_cast<double>((op->perms.size() + 1) * (op->spin_inversion ? 2 : 1));
+  a.counts = d_counts;
+  const size_t smem = op->moves.size() * sizeof(Move) + op->diag.size() * sizeof(DiagBond) + op->perms.size() * sizeof(BitPerm) + 16;
+  ASP_REQUIRE(smem <= 200 * 1024, "operator too large for shared memory");
+  const unsigned blocks = static_cast<unsigned>((num_rows + kApplyThreads - 1) / kApplyThreads);
+  ASP_CUDA_CHECK(cudaFuncSetAttribute(apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  ASP_CUDA_CHECK(cudaFuncSetAttribute(apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  apply_kernel<false><<<blocks, kApplyThreads, smem, s>>>(a);
+  ASP_LAUNCH_CHECK();
+  int64_t *d_offsets = nullptr;
+  void *d_tmp = nullptr;
+  ASP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_offsets), (num_rows + 1) * sizeof(int64_t), s));
+  ASP_CUDA_CHECK(cudaMallocAsync(&d_tmp, scan_tmp_bytes(num_rows), s));
+  int rc = scan_exclusive_i64(d_counts, d_offsets, num_rows, d_tmp, s);
+  if (rc != ASP_OK) return rc;
+  int64_t total = 0;
+  ASP_CUDA_CHECK(cudaMemcpyAsync(&total, d_offsets + num_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  ASP_CUDA_CHECK(cudaStreamSynchronize(s));
+  *h_total = static_cast<uint64_t>(total);
+  if (static_cast<uint64_t>(total) > capacity || (total > 0 && (!d_other_spins || !d_other_coeffs))) {
+    cudaFreeAsync(d_offsets, s);
+    cudaFreeAsync(d_tmp, s);
+    set_error("candidate capacity %llu < total %lld", static_cast<unsigned long long>(capacity), static_cast<long long>(total));
+    return ASP_ERR_WORKSPACE;
+  }
+  a.offsets = d_offsets;
+  a.other_spins = d_other_spins;
+  a.other_coeffs = d_other_coeffs;
+  apply_kernel<true><<<blocks, kApplyThreads, smem, s>>>(a);
+  ASP_LAUNCH_CHECK();
+  ASP_CUDA_CHECK(cudaFreeAsync(d_offsets, s));
+  ASP_CUDA_CHECK(cudaFreeAsync(d_tmp, s));
+  return ASP_OK;
+}
+
+int asp_csr_canonicalize(uint64_t num_rows, uint32_t max_row_len, int64_t const *d_row_offsets, uint32_t const *d_cols,
+                         double const *d_vals, uint64_t nnz_in, int64_t *d_indptr, int32_t *d_indices, double *d_data,
+                         uint64_t *h_nnz, void *stream) {
+  auto s = static_cast<cudaStream_t>(stream);
+  ASP_REQUIRE(h_nnz != nullptr && d_indptr != nullptr, "NULL output");
+  *h_nnz = 0;
+  if (num_rows == 0) {
+    ASP_CUDA_CHECK(cudaMemsetAsync(d_indptr, 0, sizeof(int64_t), s));
+    return ASP_OK;
+  }
+  uint32_t *tmp_cols = nullptr;
+  double *tmp_vals = nullptr;
+  int64_t *merged = nullptr;
+  int *overflow = nullptr;
+  void *scan_tmp = nullptr;
+  ASP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&tmp_cols), (nnz_in + 1) * sizeof(uint32_t), s));
+  ASP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&tmp_vals), (nnz_in + 1) * sizeof(double), s));
+  ASP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&merged), num_rows * sizeof(int64_t), s));
+  ASP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&overflow), sizeof(int), s));
+  ASP_CUDA_CHECK(cudaMallocAsync(&scan_tmp, scan_tmp_bytes(num_rows), s));
+  ASP_CUDA_CHECK(cudaMemsetAsync(overflow, 0, sizeof(int), s));
+  int row_capacity = 32;
+  while (row_capacity < static_cast<int>(max_row_len ? max_row_len : kCanonMaxRow)) row_capacity <<= 1;
+  ASP_REQUIRE(row_capacity <= kCanonMaxRow, "max_row_len above 1024 is not supported");
+  constexpr int kWarps = kCanonThreads / 32;
+  const size_t canon_smem = static_cast<size_t>(kWarps) * row_capacity * 16;
+  ASP_CUDA_CHECK(cudaFuncSetAttribute(canonicalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(canon_smem)));
+  canonicalize_kernel<<<static_cast<unsigned>((num_rows + kWarps - 1) / kWarps), kCanonThreads, canon_smem, s>>>(
+      num_rows, row_capacity, d_row_offsets, d_cols, d_vals, tmp_cols, tmp_vals, merged, overflow);
+  ASP_LAUNCH_CHECK();
+  int rc = scan_exclusive_i64(merged, d_indptr, num_rows, scan_tmp, s);
+  if (rc != ASP_OK) return rc;
+  int64_t total = 0;
+  int h_overflow = 0;
+  ASP_CUDA_CHECK(cudaMemcpyAsync(&total, d_indptr + num_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  ASP_CUDA_CHECK(cudaMemcpyAsync(&h_overflow, overflow, sizeof(int), cudaMemcpyDeviceToHost, s));
+  ASP_CUDA_CHECK(cudaStreamSynchronize(s));
+  *h_nnz = static_cast<uint64_t>(total);
+  if (!h_overflow && total > 0 && d_indices && d_data) {
+    compact_rows_kernel<<<static_cast<unsigned>((num_rows * 32 + 255) / 256), 256, 0, s>>>(num_rows, d_row_offsets, d_indptr, tmp_cols, tmp_vals, d_indices, d_data);
+    ASP_LAUNCH_CHECK();
+  }
+  ASP_CUDA_CHECK(cudaFreeAsync(tmp_cols, s));
+  ASP_CUDA_CHECK(cudaFreeAsync(tmp_vals, s));
+  ASP_CUDA_CHECK(cudaFreeAsync(merged, s));
+  ASP_CUDA_CHECK(cudaFreeAsync(overflow, s));
+  ASP_CUDA_CHECK(cudaFreeAsync(scan_tmp, s));
+  if (h_overflow) {
+    set_error("a row has more than %d raw entries", row_capacity);
+    return ASP_ERR_UNSUPPORTED;
+  }
+  return ASP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,443 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: Ising couplings built/s (extraction) and spin flips/s (SA
+sweeps) on B200, as a fraction of the measured HBM roofline, next to the reference CPU path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[3], the shape the metric is quoted on; it fits one GPU):
+heisenberg_kagome_36-shaped U(1) basis (36 spins, 72 bonds), 10^7 sampled states PER GPU
+(weak scaling: the global sorted basis has N x 10^7 states and every rank builds the CSR
+rows of its contiguous row block against the full basis), synthetic log-normal amplitudes,
+cluster-closed sampled subset (about a third of all candidates are hits).  A step is one
+pass: [N>1: all-gather of basis words + amplitudes] -> radix index -> count -> scan -> fill.
+The annealing stage is timed separately on the same extracted model and reported under the
+"anneal" key.  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SYSTEM = "heisenberg_kagome_36"
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--states", type=int, default=10_000_000, help="sampled basis states per GPU")
+    p.add_argument("--replicas", type=int, default=64, help="annealing replicas per GPU")
+    p.add_argument("--sweeps", type=int, default=4, help="annealing sweeps per step")
+    p.add_argument("--cpu-sample", type=int, default=200_000, help="states of the bounded CPU-baseline sample")
+    p.add_argument("--skip-anneal", action="store_true")
+    p.add_argument("--skip-cpu", action="store_true")
+    p.add_argument("--skip-e2e", action="store_true")
+    return p.parse_args()
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_id):
+        self.gpu_id = gpu_id
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_id), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val == "Active":
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def u1_operator(asp):
+    """kagome_36 bond list on the U(1)-only basis (the symmetrised variant is
+    integer-ALU-bound and measured by the tests, not the headline)."""
+    cfg = asp.ls.load_config(asp.ls.system_path(SYSTEM))
+    cfg["basis"]["symmetries"] = []
+    cfg["basis"]["spin_inversion"] = None
+    basis = asp.ls.SpinBasis.load_from_yaml(cfg["basis"])
+    return asp.ls.Operator.load_from_yaml(cfg["hamiltonian"], basis), cfg
+
+
+# ------------------------------------------------------------------------------------------
+# CPU legs (rank 0): the reference's own C (oracle/_ref) on a bounded sample
+# ------------------------------------------------------------------------------------------
+def cpu_sample_inputs(asp, op, cfg, n_sample, dev):
+    from annealing_sign_problem_b200 import synthetic
+    from oracle.operator_np import OperatorNP
+
+    spins = synthetic.cluster_closed_states(op, n_sample, 1234, dev).cpu().numpy().view(np.uint64)
+    psi = synthetic.synthetic_amplitudes(spins.shape[0], 1234).numpy()
+    other_spins, other_coeffs, other_counts = OperatorNP.from_config(cfg).apply_u64(spins)
+    idx = np.clip(np.searchsorted(spins, other_spins), 0, spins.shape[0] - 1)
+    other_psi = np.where(spins[idx] == other_spins, psi[idx], 0.0)
+    return spins, psi, other_spins, other_coeffs, other_counts, other_psi
+
+
+def cpu_extract_once(capi, inputs, impl):
+    spins, psi, other_spins, other_coeffs, other_counts, other_psi = inputs
+    from oracle.capi import pad512
+
+    s512, o512 = pad512(spins), pad512(other_spins)  # the reference ABI takes 512-bit keys
+    counts = np.ones(spins.shape[0], dtype=np.int64)
+    t0 = time.perf_counter()
+    rows, cols, vals, field = capi.build_matrix(s512, counts, psi, o512, other_coeffs, other_counts, other_psi, impl=impl)
+    dt = time.perf_counter() - t0
+    return rows.shape[0], dt
+
+
+def cpu_anneal_once(capi, inputs, sweeps):
+    """Oracle SA (our restatement -- the reference annealer is third-party Haskell, absent)."""
+    from oracle import live_path
+
+    spins, psi, other_spins, other_coeffs, other_counts, other_psi = inputs
+    counts = np.ones(spins.shape[0], dtype=np.int64)
+    rows, cols, vals, _ = capi.build_matrix(spins, counts, psi, other_spins, other_coeffs, other_counts, other_psi, impl="port64")
+    n = spins.shape[0]
+    indptr, indices, data = capi.canonical_csr(n, rows, cols, vals)
+    cores = os.cpu_count() or 1
+    reps = max(cores, 8)
+    betas = live_path.default_betas(indptr, indices, data, None, sweeps)
+    t0 = time.perf_counter()
+    capi.anneal(indptr, indices, data, None, reps, betas, seed=1, threads=cores)
+    dt = time.perf_counter() - t0
+    return reps * sweeps * n / dt, cores, reps
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path (cbits/build_matrix.c
+    compiled where it lies, oracle/_ref) on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    import annealing_sign_problem_b200 as asp
+    from oracle import capi
+
+    capi.build()
+    impl = "ref" if capi.have_ref() else "port"
+    dev = torch.device("cuda", 0) if torch.cuda.is_available() else None
+    if dev is None:
+        print(json.dumps({"impl": "reference", "unavailable": "sample generation needs the CUDA operator; no GPU"}))
+        return
+    op, cfg = u1_operator(asp)
+    inputs = cpu_sample_inputs(asp, op, cfg, args.cpu_sample, dev)
+    nnz, times = 0, []
+    for step in range(args.warmup + args.steps):
+        nnz, dt = cpu_extract_once(capi, inputs, impl)
+        if step >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = nnz * args.steps / total
+    sample = "%d-state kagome_36-shaped cluster-closed subset, %d candidates, time of the C call only (neighbour lists precomputed)" % (
+        inputs[0].shape[0], inputs[2].shape[0])
+    line = {
+        "impl": "reference", "metric": "ising_couplings_built_per_sec", "value": value, "unit": "couplings/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "heisenberg_kagome_36-shaped U(1) basis, Ising extraction (bounded CPU sample)", "states": int(inputs[0].shape[0]),
+                   "candidates": int(inputs[2].shape[0]), "couplings": int(nnz)},
+        "cpu_baseline": {"value": value, "unit": "couplings/s", "cores": 1, "kind": "reference" if impl == "ref" else "port", "sample": sample},
+        "e2e": {"value": value, "unit": "couplings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "candidates_per_sec": inputs[2].shape[0] * args.steps / total,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+
+    import annealing_sign_problem_b200 as asp
+    from annealing_sign_problem_b200 import common, synthetic
+    from annealing_sign_problem_b200 import distributed as D
+    from annealing_sign_problem_b200._lib import ffi, lib
+
+    rank, world, local = D.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    peak, peak_src = hbm_peak()
+    op, cfg = u1_operator(asp)
+
+    # ---- workload: every rank samples its own cluster-closed subset; X1 + global sort --------
+    mine = synthetic.cluster_closed_states(op, args.states, 1000 + rank, dev)
+    if world > 1:
+        import torch.distributed as dist
+
+        every = torch.empty(world * mine.shape[0], dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(every, mine)
+        spins = synthetic._sorted_unique_unsigned(every)
+        del every
+    else:
+        spins = mine
+    del mine
+    n_total = int(spins.shape[0])
+    psi = synthetic.synthetic_amplitudes(n_total, 77, device=dev)
+    row_begin, num_rows = D.block(n_total, rank, world)
+    my_spins = spins[row_begin:row_begin + num_rows].clone()
+    my_psi = psi[row_begin:row_begin + num_rows].clone()
+    need = int(lib().asp_extract_workspace_bytes(op.handle, n_total, num_rows))
+    workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+
+    def one_pass(timers=None):
+        if world > 1:  # X1: the exchange step of the path
+            full_spins = D.all_gather_blocks(my_spins, n_total)
+            full_psi = D.all_gather_blocks(my_psi, n_total)
+        else:
+            full_spins, full_psi = spins, psi
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if timers is not None else None
+        if ev:
+            ev[0].record()
+        nnz = ffi.new("uint64_t *")
+        common.check(lib().asp_extract_count(op.handle, n_total, common.ptr(full_spins, "uint64_t *"), row_begin, num_rows,
+                                             common.ptr(workspace, "void *"), workspace.numel(), nnz, common.stream()))
+        if ev:
+            ev[1].record()
+        m = int(nnz[0])
+        indptr = torch.empty(num_rows + 1, dtype=torch.int64, device=dev)
+        indices = torch.empty(m, dtype=torch.int32, device=dev)
+        data = torch.empty(m, dtype=torch.float64, device=dev)
+        common.check(lib().asp_extract_fill(op.handle, n_total, common.ptr(full_spins, "uint64_t *"), common.ptr(full_psi, "double *"),
+                                            row_begin, num_rows, common.ptr(workspace, "void *"), workspace.numel(),
+                                            common.ptr(indptr, "int64_t *"), common.ptr(indices, "int32_t *"),
+                                            common.ptr(data, "double *"), common.stream()))
+        if ev:
+            ev[2].record()
+            timers.append(ev)
+        return indptr, indices, data
+
+    for _ in range(args.warmup):
+        out = one_pass()
+    nnz_mine = int(out[1].numel())
+    del out
+    uuid = getattr(torch.cuda.get_device_properties(dev), "uuid", None)
+    sampler = ClockSampler("GPU-" + str(uuid) if uuid else local)
+    if rank == 0:
+        sampler.start()
+    launches0 = int(lib().asp_kernel_launch_count())
+    timers = []
+    D.barrier()
+    torch.cuda.synchronize()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(args.steps):
+        out = one_pass(timers)
+    end.record()
+    D.barrier()
+    torch.cuda.synchronize()
+    total_ms = D.max_over_ranks(start.elapsed_time(end), dev)
+    launches = int(lib().asp_kernel_launch_count()) - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    count_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in timers]))
+    fill_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in timers]))
+    nnz_total = D.sum_over_ranks(float(nnz_mine), dev)
+    candidates_mine = None
+    value = nnz_total * args.steps / (total_ms * 1e-3)
+    algo_bytes = 24.0 * num_rows + 20.0 * nnz_mine  # per row 24 B, per coupling 20 B
+    roofline = {
+        "bound": "hbm", "kernel": "extract_sorted_kernel<fill>", "achieved": algo_bytes / (fill_ms * 1e-3) / 1e9, "peak": peak,
+        "unit": "GB/s", "frac": algo_bytes / (fill_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": algo_bytes, "fill_ms": fill_ms, "count_scan_index_ms": count_ms,
+        "frac_whole_path": algo_bytes / ((fill_ms + count_ms) * 1e-3) / 1e9 / peak,
+    }
+    indptr, indices, data = out
+
+    # ---- end to end through the C ABI with HOST (pinned) buffers ----------------------------
+    e2e = None
+    if not args.skip_e2e:
+        h_spins = spins.cpu().pin_memory()
+        h_psi = psi.cpu().pin_memory()
+        h_indptr = torch.empty(num_rows + 1, dtype=torch.int64).pin_memory()
+        h_indices = torch.empty(nnz_mine, dtype=torch.int32).pin_memory()
+        h_data = torch.empty(nnz_mine, dtype=torch.float64).pin_memory()
+
+        def host_pass():
+            nnz = ffi.new("uint64_t *")
+            job = ffi.new("asp_host_job **")
+            common.check(lib().asp_extract_host_begin(op.handle, n_total, ffi.cast("uint64_t *", h_spins.data_ptr()),
+                                                      ffi.cast("double *", h_psi.data_ptr()), row_begin, num_rows, nnz, job))
+            assert int(nnz[0]) == nnz_mine
+            common.check(lib().asp_extract_host_finish(job[0], ffi.cast("int64_t *", h_indptr.data_ptr()),
+                                                       ffi.cast("int32_t *", h_indices.data_ptr()), ffi.cast("double *", h_data.data_ptr())))
+
+        e2e_steps = max(2, min(args.steps, 5))
+        host_pass()
+        D.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            host_pass()
+        torch.cuda.synchronize()
+        e2e_s = D.max_over_ranks(time.perf_counter() - t0, dev)
+        assert int(h_indptr[-1]) == nnz_mine
+        e2e = {"value": nnz_total * e2e_steps / e2e_s, "unit": "couplings/s",
+               "h2d_bytes_per_step": int(n_total * 16), "d2h_bytes_per_step": int((num_rows + 1) * 8 + nnz_mine * 12),
+               "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+               "api": "asp_extract_host_begin/finish (include/asp_b200.h), pinned host buffers"}
+        del h_spins, h_psi, h_indptr, h_indices, h_data
+
+    # ---- annealing stage on the extracted model (replicas shard over ranks) ------------------
+    anneal = None
+    if not args.skip_anneal:
+        if world > 1:
+            # every rank anneals the full single-GPU-sized model of rank 0's shape: rebuild locally
+            a_spins = synthetic.cluster_closed_states(op, args.states, 1000, dev)
+            a_psi = synthetic.synthetic_amplitudes(a_spins.shape[0], 77, device=dev)
+            del indptr, indices, data
+            indptr, indices, data = common.extract_csr_device(op, a_spins, a_psi)
+        n_model = int(indptr.shape[0] - 1)
+        import scipy.sparse  # noqa: F401
+
+        class _Shape:  # Hamiltonian wants a .shape; skip the host scipy copy at this size
+            shape = (n_model, n_model)
+
+        ham = asp.sa.Hamiltonian(_Shape(), np.zeros(n_model), _device_csr=(indptr, indices, data, None))
+        t0 = time.perf_counter()
+        plan = asp.sa.AnnealPlan(ham)
+        torch.cuda.synchronize()
+        plan_ms = 1e3 * (time.perf_counter() - t0)
+        betas = asp.sa.default_betas(ham, max(args.sweeps * 8, 64))[: args.sweeps] if args.sweeps > 1 else asp.sa.default_betas(ham, 1)
+        escale = asp.sa.energy_scale(ham)
+        R = args.replicas
+
+        def anneal_pass(seed):
+            bits, energies = plan.anneal_device(R, betas, seed, escale=escale, replica_offset=rank * ((R + 31) // 32 * 32))
+            best = int(torch.argmin(energies))
+            return D.reduce_best(float(energies[best]), bits[best])  # X2
+
+        for w in range(args.warmup):
+            anneal_pass(w)
+        launches_a0 = int(lib().asp_kernel_launch_count())
+        D.barrier()
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for k in range(args.steps):
+            e_best, _, _ = anneal_pass(100 + k)
+        a1.record()
+        D.barrier()
+        torch.cuda.synchronize()
+        a_ms = D.max_over_ranks(a0.elapsed_time(a1), dev)
+        flips = float(R) * world * args.sweeps * n_model * args.steps
+        a_value = flips / (a_ms * 1e-3)
+        nnz_model = int(indices.numel())
+        sweep_bytes = 12.0 * nnz_model + 16.0 * n_model + 8.0  # SURVEY.md 8d, per replica per sweep
+        a_achieved = R * args.sweeps * sweep_bytes * args.steps / (a_ms * 1e-3) / 1e9
+        anneal = {
+            "metric": "spin_flips_per_sec", "value": a_value, "unit": "proposals/s", "ms_per_step": a_ms / args.steps,
+            "config": {"spins": n_model, "couplings": nnz_model, "replicas_per_gpu": R, "sweeps_per_step": args.sweeps,
+                       "colour_classes": plan.num_classes, "plan_ms": plan_ms, "best_energy": e_best},
+            "roofline": {"bound": "hbm", "kernel": "sa_sweep_kernel", "achieved": a_achieved, "peak": peak, "unit": "GB/s",
+                         "frac": a_achieved / peak, "traffic": None,
+                         "note": "algorithmic bytes = R*S*(12 nnz + 16 n + 8): one CSR stream per replica per sweep; the kernel "
+                                 "shares each row across 32 replicas, so frac can exceed 1"},
+            "gpu_launches": int(lib().asp_kernel_launch_count()) - launches_a0,
+        }
+
+    # ---- CPU baseline on rank 0 (N = 1 only) -------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        from oracle import capi
+
+        capi.build()
+        impl = "ref" if capi.have_ref() else "port"
+        inputs = cpu_sample_inputs(asp, op, cfg, args.cpu_sample, dev)
+        nnz_s, dt = cpu_extract_once(capi, inputs, impl)
+        flips_s, cores, reps = cpu_anneal_once(capi, inputs, 4)
+        cpu = {"value": nnz_s / dt, "unit": "couplings/s", "cores": 1, "kind": "reference" if impl == "ref" else "port",
+               "sample": "%d-state subset of the same shape, %d candidates; cbits/build_matrix.c call only (serial C, 512-bit keys), "
+                         "neighbour lists precomputed" % (inputs[0].shape[0], inputs[2].shape[0]),
+               "candidates_per_sec": inputs[2].shape[0] / dt,
+               "anneal": {"value": flips_s, "unit": "proposals/s", "cores": cores, "kind": "port",
+                          "sample": "oracle/anneal_port.c, %d replicas x 4 sweeps on the %d-spin sample model" % (reps, inputs[0].shape[0])}}
+
+    if rank == 0:
+        line = {
+            "metric": "ising_couplings_built_per_sec", "value": value, "unit": "couplings/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "heisenberg_kagome_36-shaped U(1) basis (36 spins, 72 bonds), %d sampled states per GPU, "
+                                   "cluster-closed subset, Ising extraction to CSR" % args.states,
+                       "states_total": n_total, "rows_per_gpu": num_rows, "couplings_total": int(nnz_total),
+                       "candidates_per_row": 37.0, "parallelism": "row blocks x%d, basis all-gathered" % world,
+                       "l2": "inputs (%.0f MB) larger than L2" % ((n_total * 16 + need) / 1e6)},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "anneal": anneal,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

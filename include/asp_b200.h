@@ -1,0 +1,198 @@
+/* asp_b200.h -- C ABI of the B200-native Ising-extraction + annealing hot path.
+ *
+ * Drop-in boundary for twesterhout/annealing-sign-problem.  Every entry point takes plain
+ * pointers and sizes (no torch / C++ types) so the reference's cffi layer
+ * (annealing_sign_problem/build_extension.py:5-21) can bind it unchanged; INTEGRATION.md
+ * shows the cdef a maintainer would add.
+ *
+ * Conventions (those of cbits/build_matrix.h:7-14 unless noted):
+ *   - the caller owns every buffer; the callee never frees caller memory;
+ *   - `*_host` / legacy entry points take HOST pointers and do their own H2D/D2H;
+ *     all other entry points take DEVICE pointers valid on the current CUDA device and
+ *     enqueue on `stream` (a cudaStream_t passed as void*; NULL = default stream);
+ *   - ADDITION to the reference (which has no error channel): functions returning `int`
+ *     give ASP_OK or a negative ASP_ERR_* and leave a message in asp_last_error();
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with
+ *     ASP_ERR_CUDA.
+ *
+ * Bit layout of packed sign vectors: word i/64, bit i%64, 1 <=> s_i = +1
+ * (cbits/build_matrix.c:67-76).
+ */
+#ifndef ASP_B200_H
+#define ASP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ASP_OK 0
+#define ASP_ERR_CUDA (-1)     /* CUDA runtime error or no device */
+#define ASP_ERR_ARG (-2)      /* invalid argument */
+#define ASP_ERR_WORKSPACE (-3) /* workspace too small */
+#define ASP_ERR_UNSUPPORTED (-4)
+
+/* == struct ls_bits512, cbits/build_matrix.h:3-5 */
+typedef struct asp_bits512 {
+  uint64_t words[8];
+} asp_bits512;
+
+typedef struct asp_operator asp_operator; /* Hamiltonian bond list compiled to XOR moves */
+typedef struct asp_sa_plan asp_sa_plan;   /* Ising model prepared for replica annealing  */
+typedef struct asp_host_job asp_host_job; /* in-flight host-buffer extraction            */
+
+int asp_version(void);
+const char *asp_last_error(void);
+/* Number of CUDA devices visible (0 when none / no driver). */
+int asp_device_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * 1. Legacy drop-ins (HOST pointers).  Replace cbits/build_matrix.h:7-14 one to one:
+ *    same argument list, same outputs (COO triplets in generation order, field[]
+ *    accumulated in candidate order, returns nnz).  On failure returns UINT64_MAX.
+ * ---------------------------------------------------------------------------------- */
+uint64_t asp_build_matrix(uint64_t num_spins, asp_bits512 const spins[], int64_t const *counts,
+                          double const *psi, asp_bits512 const *other_spins,
+                          double const *other_coeffs, int64_t const *other_counts,
+                          double const *other_psi, uint32_t *row_indices, uint32_t *col_indices,
+                          double *elements, double *field);
+
+void asp_extract_signs(uint64_t num_spins, double const *psi, uint64_t *signs);
+
+/* Same two on DEVICE pointers with 64-bit keys (the reference's glue only fills words[0],
+ * common.py:58-68,100), for the row block [row_begin, row_begin+num_rows) of the basis.
+ * d_spins, d_psi: the FULL basis [n_total].  d_counts (NULL = all 1), d_offsets, d_field:
+ * per row of the block; d_offsets = exclusive scan of other_counts, [num_rows+1]
+ * (asp_exclusive_scan_i64).  d_other_psi == NULL: a hit uses |d_psi[column]| and no field
+ * is accumulated (the live path, common.py:71-82).  d_row_offsets[num_rows+1] receives the
+ * row starts of the emitted triplets.  Synchronises; *h_nnz = emitted triplets. */
+int asp_build_matrix_dev(uint64_t n_total, uint64_t const *d_spins, uint64_t row_begin,
+                         uint64_t num_rows, int64_t const *d_counts, double const *d_psi,
+                         uint64_t const *d_other_spins, double const *d_other_coeffs,
+                         int64_t const *d_offsets, double const *d_other_psi,
+                         int64_t *d_row_offsets /* [num_rows+1] out */, uint32_t *d_row_indices,
+                         uint32_t *d_col_indices, double *d_elements, double *d_field,
+                         uint64_t capacity, uint64_t *h_nnz, void *stream);
+int asp_extract_signs_dev(uint64_t num_spins, double const *d_psi, uint64_t *d_signs, void *stream);
+/* out[0..m] = exclusive prefix sums of in[0..m) (out has m+1 entries). tmp: >= asp_scan_tmp_bytes(m). */
+size_t asp_scan_tmp_bytes(uint64_t m);
+int asp_exclusive_scan_i64(int64_t const *d_in, int64_t *d_out, uint64_t m, void *d_tmp, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * 2. Fused extraction: neighbour generation (replaces lattice_symmetries'
+ *    Operator.batched_apply as called at common.py:85-106) + search in the sorted sampled
+ *    set (common.py:116-128,173 / build_matrix.c:36-37) + coupling
+ *    J_ij = c_ij |psi_i| |psi_j| (build_matrix.c:38-43 / common.py:71-82) + two-pass CSR.
+ *    Output is canonical CSR: columns ascending inside a row, duplicates summed in
+ *    generation order, diagonal kept (what common.py:193-196 ends with, before its
+ *    0.5(M+M^T) which asp_csr_symmetrize performs).
+ * ---------------------------------------------------------------------------------- */
+
+/* matrices: [num_terms][16] row-major 4x4 two-site matrices; term t acts on the bonds
+ * sites[2*b], sites[2*b+1] for b in [term_offsets[t], term_offsets[t+1]).
+ * Local state index a = 2*bit(s, site0) + bit(s, site1); coefficient of s -> s' is
+ * matrix[a][a'].  hamming_weight < 0: unrestricted.  spin_inversion in {0, +1, -1}.
+ * perms: [num_perms][number_spins] -- ALL non-identity elements of the permutation group
+ * (new bit k = old bit perm[k]) with real characters[num_perms]; num_perms = 0 for none. */
+int asp_operator_create(asp_operator **out, uint32_t number_spins, int32_t hamming_weight,
+                        int32_t spin_inversion, uint32_t num_terms, double const *matrices,
+                        uint32_t const *term_offsets, uint32_t const *sites, uint32_t num_perms,
+                        uint32_t const *perms, double const *characters);
+void asp_operator_destroy(asp_operator *op);
+/* Upper bound on candidates per row (off-diagonal moves + the diagonal). */
+uint32_t asp_operator_max_candidates(asp_operator const *op);
+/* 1 if rows come out column-sorted and duplicate-free without a canonicalisation pass. */
+int asp_operator_is_sorted_emitter(asp_operator const *op);
+
+/* batched_apply on device (common.py:96 contract, 64-bit keys): writes up to
+ * max_candidates per row in row-major order; d_counts[num_rows]; returns total in *h_total. */
+int asp_operator_apply_dev(asp_operator const *op, uint64_t num_rows, uint64_t const *d_spins,
+                           uint64_t *d_other_spins, double *d_other_coeffs, int64_t *d_counts,
+                           uint64_t capacity, uint64_t *h_total, void *stream);
+
+size_t asp_extract_workspace_bytes(asp_operator const *op, uint64_t n_total, uint64_t num_rows);
+
+/* Pass 1: index the sorted basis, count couplings of rows [row_begin, row_begin+num_rows)
+ * against the FULL basis d_spins[0..n_total), scan.  Synchronises; *h_nnz = couplings. */
+int asp_extract_count(asp_operator const *op, uint64_t n_total, uint64_t const *d_spins,
+                      uint64_t row_begin, uint64_t num_rows, void *d_workspace,
+                      size_t workspace_bytes, uint64_t *h_nnz, void *stream);
+
+/* Pass 2: d_psi[n_total] amplitudes (sign ignored).  d_indptr[num_rows+1] int64 (starts at
+ * 0 for this row block), d_indices[nnz] int32 GLOBAL column numbers, d_data[nnz] f64. */
+int asp_extract_fill(asp_operator const *op, uint64_t n_total, uint64_t const *d_spins,
+                     double const *d_psi, uint64_t row_begin, uint64_t num_rows,
+                     void *d_workspace, size_t workspace_bytes, int64_t *d_indptr,
+                     int32_t *d_indices, double *d_data, void *stream);
+
+/* Canonical CSR of generation-order rows (raw output of asp_build_matrix_dev): inside each
+ * row a stable sort by column, duplicates summed in generation order -- what scipy's
+ * csr_matrix + sort_indices yield at common.py:193-195.  max_row_len: upper bound on raw
+ * row length (<= 1024; 0 = 1024).  d_indices/d_data need capacity nnz_in. */
+int asp_csr_canonicalize(uint64_t num_rows, uint32_t max_row_len, int64_t const *d_row_offsets,
+                         uint32_t const *d_cols, double const *d_vals, uint64_t nnz_in,
+                         int64_t *d_indptr, int32_t *d_indices, double *d_data, uint64_t *h_nnz,
+                         void *stream);
+
+/* In-place J <- 0.5 (J + J^T) for a structurally symmetric canonical CSR (Hermitian H);
+ * *h_asymmetric = number of entries whose transpose is missing (then nothing is changed). */
+int asp_csr_symmetrize(uint64_t n, int64_t const *d_indptr, int32_t const *d_indices,
+                       double *d_data, uint64_t *h_asymmetric, void *stream);
+
+/* HOST-buffer convenience (the end-to-end path) for rows [row_begin, row_begin+num_rows):
+ * begin = H2D of the full basis + index + count (returns nnz), finish = fill + D2H into
+ * caller buffers (h_indptr[num_rows+1], h_indices/h_data[nnz]), then frees the job. */
+int asp_extract_host_begin(asp_operator const *op, uint64_t n_total, uint64_t const *h_spins,
+                           double const *h_psi, uint64_t row_begin, uint64_t num_rows,
+                           uint64_t *h_nnz, asp_host_job **job);
+int asp_extract_host_finish(asp_host_job *job, int64_t *h_indptr, int32_t *h_indices, double *h_data);
+
+/* ------------------------------------------------------------------------------------
+ * 3. Energies and overlaps (replace sa.Hamiltonian.energy, full_hilbert_space.py:144, and
+ *    compute_accuracy_and_overlap, common.py:211-229), batched over R packed replicas.
+ *    d_bits: [R][ceil(n/64)].  d_field / d_weights may be NULL (zeros / ones).
+ * ---------------------------------------------------------------------------------- */
+int asp_energy(uint64_t n, int64_t const *d_indptr, int32_t const *d_indices, double const *d_data,
+               double const *d_field, uint32_t num_replicas, uint64_t const *d_bits,
+               double *d_energy, void *stream);
+int asp_accuracy_overlap(uint64_t n, uint32_t num_replicas, uint64_t const *d_predicted,
+                         uint64_t const *d_exact, double const *d_weights, double *d_accuracy,
+                         double *d_overlap, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * 4. Replica simulated annealing (replaces ising_glass_annealer.anneal as called at
+ *    common.py:242-248).  The plan colours the coupling graph, relabels spins so every
+ *    colour class is a contiguous range (classes padded to multiples of 4), and keeps the
+ *    relabelled CSR on the device.  A sweep visits positions 0..n_padded-1 in order; spins
+ *    of one class do not interact, so the kernel updates a class in parallel and the
+ *    result equals the sequential sweep (DESIGN.md "SA chain definition").
+ * ---------------------------------------------------------------------------------- */
+int asp_sa_plan_create(asp_sa_plan **out, uint64_t n, int64_t const *d_indptr,
+                       int32_t const *d_indices, double const *d_data, double const *d_field,
+                       void *stream);
+void asp_sa_plan_destroy(asp_sa_plan *plan);
+/* sizes: n_padded positions, number of colour classes, nnz of the relabelled CSR. */
+int asp_sa_plan_info(asp_sa_plan const *plan, uint64_t *n_padded, uint32_t *num_classes, uint64_t *nnz);
+/* Copy the relabelled model to HOST buffers (tests feed it to the CPU oracle):
+ * order[n_padded] (position -> original spin, -1 = padding), class_ptr[num_classes+1],
+ * indptr[n_padded+1], indices[nnz], data[nnz], field[n_padded]. Any pointer may be NULL. */
+int asp_sa_plan_export(asp_sa_plan const *plan, int32_t *h_order, int64_t *h_class_ptr,
+                       int64_t *h_indptr, int32_t *h_indices, double *h_data, double *h_field);
+/* h_betas[num_sweeps] inverse temperatures (host).  d_x0: packed start configuration in
+ * ORIGINAL spin order or NULL (random start).  replica_offset: global index of this call's
+ * first replica (a multiple of 32) -- replica r draws the random stream of global replica
+ * replica_offset + r, so R replicas split over G GPUs reproduce one G*R-replica run.
+ * Outputs, original spin order: d_best_bits [R][ceil(n/64)], d_best_energy[R] (exact,
+ * recomputed in f64; may be NULL). */
+int asp_sa_anneal(asp_sa_plan *plan, uint32_t num_replicas, uint32_t replica_offset,
+                  uint32_t num_sweeps, double const *h_betas, uint64_t seed, uint64_t const *d_x0,
+                  double energy_scale, uint64_t *d_best_bits, double *d_best_energy, void *stream);
+/* Number of kernel launches the library has issued in this process (bench accounting). */
+uint64_t asp_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASP_B200_H */

@@ -135,7 +135,8 @@ def default_betas(indptr, indices, data, field, number_sweeps: int, beta0=None, 
     """Geometric inverse-temperature ladder (OUR definition -- the reference leaves
     beta0/beta1 to the absent annealer, common.py:242-248).  Hot end: the largest
     single-flip barrier is accepted with probability 1/2; cold end: the smallest non-zero
-    coupling barrier with probability 1/100."""
+    coupling barrier with probability 1/100 (capped at 1e4 x hot), then number_sweeps//50
+    zero-temperature sweeps (beta = inf)."""
     indptr = np.asarray(indptr)
     n = indptr.shape[0] - 1
     rows = np.repeat(np.arange(n), np.diff(indptr))
@@ -155,8 +156,14 @@ def default_betas(indptr, indices, data, field, number_sweeps: int, beta0=None, 
     if max_de <= 0:
         max_de = 1.0
     b0 = np.log(2.0) / max_de if beta0 is None else float(beta0)
-    b1 = np.log(100.0) / min_de if beta1 is None else float(beta1)
-    if number_sweeps == 1:
-        return np.array([b1], dtype=np.float64)
-    t = np.arange(number_sweeps, dtype=np.float64) / (number_sweeps - 1)
-    return np.ascontiguousarray(b0 * (b1 / b0) ** t)
+    # cold end: the smallest barrier, but at most 4 decades above the hot end -- amplitudes
+    # span many decades and a ladder reaching 1/min|J| would spend its sweeps frozen
+    b1 = min(np.log(100.0) / min_de, b0 * 1e4) if beta1 is None else float(beta1)
+    quench = number_sweeps // 50 if beta1 is None else 0  # final zero-temperature sweeps
+    ladder = number_sweeps - quench
+    if ladder <= 1:
+        betas = np.full(number_sweeps, b1, dtype=np.float64)
+    else:
+        t = np.arange(ladder, dtype=np.float64) / (ladder - 1)
+        betas = np.concatenate([b0 * (b1 / b0) ** t, np.full(quench, np.inf)])
+    return np.ascontiguousarray(betas, dtype=np.float64)

@@ -1,0 +1,106 @@
+"""CPU (-m "not gpu") tests of the drop-in boundary: the C-ABI library builds, loads and
+exports every symbol include/asp_b200.h declares; the host-side mirror validates inputs the
+way the reference does; the product fails loudly without a GPU and never touches oracle/."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+@pytest.fixture(scope="module")
+def asp():
+    import annealing_sign_problem_b200 as mod
+    from annealing_sign_problem_b200.build_extension import build
+
+    build()
+    return mod
+
+
+def test_library_exports_every_declared_symbol(asp):
+    from annealing_sign_problem_b200._lib import lib
+
+    header = open(os.path.join(ROOT, "include", "asp_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(asp_[a-z0-9_]+)\s*\(", header)))
+    assert len(names) >= 25
+    handle = lib()
+    for name in names:
+        assert hasattr(handle, name), name
+    out = subprocess.check_output(["nm", "-D", "--defined-only", os.path.join(ROOT, "annealing-sign-problem_b200", "libasp_b200.so")]).decode()
+    exported = set(re.findall(r" T (asp_[a-z0-9_]+)", out))
+    assert set(names) <= exported
+    assert handle.asp_version() >= 100
+
+
+def test_library_is_built_for_sm_100a():
+    lib_path = os.path.join(ROOT, "annealing-sign-problem_b200", "libasp_b200.so")
+    out = subprocess.run(["cuobjdump", "--list-elf", lib_path], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in out.stdout
+
+
+def test_no_cpu_fallback(asp):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from annealing_sign_problem_b200._lib import AspError
+
+    op = asp.load_hamiltonian(asp.ls.system_path("j1j2_square_4x4"))
+    with pytest.raises(AspError):
+        asp.make_ising_model(np.array([255, 510], dtype=np.uint64), op, log_psi=np.zeros(2))
+    with pytest.raises(AspError):
+        asp.sa.signs_to_bits(np.ones(4))
+    with pytest.raises(AspError):
+        asp.compute_accuracy_and_overlap(np.zeros(1, dtype=np.uint64), np.zeros(1, dtype=np.uint64), number_spins=3)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "annealing-sign-problem_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "oracle/" not in text or f.endswith((".cu", ".cuh")), f
+
+
+def test_argument_validation_matches_the_reference(asp):
+    op = asp.load_hamiltonian(asp.ls.system_path("heisenberg_kagome_16"))
+    with pytest.raises(ValueError):  # common.py:140-141
+        asp.make_ising_model(np.zeros(3, dtype=np.uint64), op)
+    with pytest.raises(ValueError):  # common.py:142-143
+        asp.make_ising_model(np.zeros(3, dtype=np.uint64), op, log_psi=np.zeros(3), external_field=True)
+    with pytest.raises(ValueError):  # common.py:217-218
+        asp.compute_accuracy_and_overlap(np.zeros(1, dtype=np.uint64), np.zeros(1, dtype=np.uint64))
+    assert np.array_equal(asp.binary_search(np.array([1, 5, 9]), np.array([9, 1])), [2, 0])
+    with pytest.raises(AssertionError):  # common.py:544-548
+        asp.binary_search(np.array([1, 5, 9]), np.array([4]))
+    assert np.array_equal(asp.sa.bits_to_signs(np.array([0b101], dtype=np.uint64), 4), [1, -1, 1, -1])
+
+
+def test_symmetry_groups_and_system_files(asp):
+    for name, order in [("heisenberg_kagome_36", 144), ("heisenberg_pyrochlore_2x2x2", 384), ("j1j2_square_4x4", 1)]:
+        op = asp.load_hamiltonian(asp.ls.system_path(name))
+        assert len(op.basis.group_elements) + 1 == order
+    bad = {"number_spins": 4, "hamming_weight": 2, "symmetries": [{"permutation": [1, 2, 3, 0], "sector": 1}]}
+    with pytest.raises(ValueError):  # complex character: the reference rejects non-real coefficients
+        asp.ls.SpinBasis.load_from_yaml(bad)
+    with pytest.raises(ValueError):
+        asp.ls.Operator(asp.ls.SpinBasis(4), [{"matrix": np.eye(3), "sites": [[0, 1]]}])
+
+
+def test_two_rank_sharding_plan_over_gloo(tmp_path):
+    """world_size-2 gloo run of the row-block / replica partition used by bench.py --gpus N."""
+    script = os.path.join(ROOT, "tests", "_gloo_sharding.py")
+    port = 29500 + os.getpid() % 2000
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), script]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "SHARDING_OK" in out.stdout

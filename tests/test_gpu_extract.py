@@ -1,0 +1,317 @@
+"""-m gpu parity tests of the extraction path: CUDA (through the C ABI) vs the CPU oracle,
+vs golden vectors produced by the reference itself, and size-independent properties."""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+import annealing_sign_problem_b200 as asp  # noqa: E402
+from annealing_sign_problem_b200 import common, synthetic  # noqa: E402
+from annealing_sign_problem_b200._lib import ffi, lib  # noqa: E402
+from oracle import live_path  # noqa: E402
+from oracle.operator_np import OperatorNP  # noqa: E402
+
+GOLDEN = ["live_j1j2_square_4x4.npz", "live_heisenberg_kagome_18.npz", "live_sk_16_1.npz"]
+DEV = torch.device("cuda")
+
+
+def _coo_to_csr(row, col, data, n):
+    m = scipy.sparse.coo_matrix((data, (row, col)), shape=(n, n)).tocsr()
+    m.sort_indices()
+    return m
+
+
+def _assert_same_matrix(ours: scipy.sparse.spmatrix, ref: scipy.sparse.spmatrix, rtol=1e-12):
+    ours, ref = ours.tocsr(), ref.tocsr()
+    ours.sort_indices()
+    ref.sort_indices()
+    assert ours.shape == ref.shape
+    assert np.array_equal(ours.indptr, ref.indptr)
+    assert np.array_equal(ours.indices, ref.indices)  # bit-exact structure
+    np.testing.assert_allclose(ours.data, ref.data, rtol=rtol, atol=0)  # 1e-12 relative (north_star)
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_make_ising_model_matches_reference_golden(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name))
+    op = asp.load_hamiltonian(asp.ls.system_path(str(g["system"])))
+    model = asp.make_ising_model(g["spins"], op, log_psi=g["log_psi"])
+    n = g["spins"].shape[0]
+    assert np.array_equal(model.spins, g["spins"])
+    ex = model.ising_hamiltonian.exchange
+    assert isinstance(ex, scipy.sparse.coo_matrix) and ex.shape == (n, n)
+    _assert_same_matrix(ex, _coo_to_csr(g["live_row"], g["live_col"], g["live_data"], n))
+    assert np.array_equal(model.initial_signs, g["live_x0"])
+    assert not model.ising_hamiltonian.field.any()
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_legacy_build_matrix_dropin_is_bitwise_the_reference_c(golden_dir, name):
+    """asp_build_matrix / asp_extract_signs with the reference's argument list (HOST pointers,
+    512-bit keys) against outputs of the reference's own compiled C."""
+    g = np.load(os.path.join(golden_dir, name))
+    spins = g["spins"]
+    n, T = spins.shape[0], g["other_spins"].shape[0]
+    psi = np.exp(g["log_psi"]).real
+    psi = np.ascontiguousarray(psi / np.linalg.norm(psi))
+    s512 = np.zeros((n, 8), dtype=np.uint64)
+    s512[:, 0] = spins
+    o512 = np.zeros((T, 8), dtype=np.uint64)
+    o512[:, 0] = g["other_spins"]
+    counts = np.ones(n, dtype=np.int64)
+    rows = np.zeros(T, dtype=np.uint32)
+    cols = np.zeros(T, dtype=np.uint32)
+    vals = np.zeros(T, dtype=np.float64)
+    field = np.full(n, 7.0)
+    c = lambda a, t: ffi.cast(t, a.ctypes.data)  # noqa: E731
+    nnz = lib().asp_build_matrix(n, c(s512, "asp_bits512 *"), c(counts, "int64_t *"), c(psi, "double *"),
+                                 c(o512, "asp_bits512 *"), c(np.ascontiguousarray(g["other_coeffs"]), "double *"),
+                                 c(np.ascontiguousarray(g["other_counts"]), "int64_t *"),
+                                 c(np.ascontiguousarray(g["other_psi"]), "double *"),
+                                 c(rows, "uint32_t *"), c(cols, "uint32_t *"), c(vals, "double *"), c(field, "double *"))
+    assert nnz == g["c_rows"].shape[0]
+    assert np.array_equal(rows[:nnz], g["c_rows"])
+    assert np.array_equal(cols[:nnz], g["c_cols"])
+    assert np.array_equal(vals[:nnz], g["c_vals"])  # same association, no FMA: bitwise
+    assert np.array_equal(field, g["c_field"])
+    signs = np.full((n + 63) // 64, 0xFFFFFFFFFFFFFFFF, dtype=np.uint64)
+    lib().asp_extract_signs(n, c(psi, "double *"), c(signs, "uint64_t *"))
+    assert np.array_equal(signs, g["c_signs"])
+
+
+def test_extract_signs_edge_cases(oracle_capi):
+    rng = np.random.default_rng(0)
+    for n in [1, 31, 32, 63, 64, 65, 130, 1000, 4097]:
+        psi = rng.standard_normal(n)
+        if n > 4:
+            psi[1], psi[2], psi[3] = 0.0, -0.0, np.nan
+        assert np.array_equal(asp.sa.signs_to_bits(psi), oracle_capi.extract_signs(psi))
+
+
+def _oracle_csr(op_np, spins, psi):
+    m = live_path.make_ising_model(spins, op_np, log_psi=np.log(psi.astype(np.complex128)))
+    return m.exchange.tocsr()
+
+
+@pytest.mark.parametrize("system,n,seed", [
+    ("j1j2_square_4x4", 3000, 0), ("heisenberg_kagome_16", 5000, 1), ("sk_16_2", 1500, 2),
+    ("heisenberg_kagome_18", 4000, 3), ("heisenberg_kagome_36", 20000, 4), ("heisenberg_pyrochlore_2x2x2", 20000, 5),
+])
+def test_fused_extraction_vs_oracle_on_random_subsets(system, n, seed):
+    """U(1)-only operators (symmetries stripped for the 32/36-spin shapes)."""
+    cfg = asp.ls.load_config(asp.ls.system_path(system))
+    if system in ("heisenberg_kagome_36", "heisenberg_pyrochlore_2x2x2"):
+        cfg["basis"]["symmetries"] = []
+        cfg["basis"]["spin_inversion"] = None
+    basis = asp.ls.SpinBasis.load_from_yaml(cfg["basis"])
+    op = asp.ls.Operator.load_from_yaml(cfg["hamiltonian"], basis)
+    op_np = OperatorNP.from_config(cfg)
+    if basis.is_symmetrised:
+        pool = torch.from_numpy(op_np.basis.states.view(np.int64))
+        spins = pool[torch.sort(torch.randperm(pool.shape[0], generator=torch.Generator().manual_seed(seed))[:n]).values].to(DEV)
+    else:
+        spins = synthetic.cluster_closed_states(op, n, seed, DEV)
+    psi = synthetic.synthetic_amplitudes(spins.shape[0], seed, device=DEV)
+    indptr, indices, data = common.extract_csr_device(op, spins, psi)
+    n = spins.shape[0]
+    ours = scipy.sparse.csr_matrix((data.cpu().numpy(), indices.cpu().numpy(), indptr.cpu().numpy()), shape=(n, n))
+    assert ours.has_sorted_indices
+    ref = _oracle_csr(op_np, spins.cpu().numpy().view(np.uint64), psi.cpu().numpy())
+    sym = (0.5 * (ours + ours.T)).tocsr()
+    _assert_same_matrix(sym, ref)
+    assert ours.nnz > n  # more than the diagonal: the subsets are cluster-closed
+
+
+def test_foreign_operator_goes_through_its_own_batched_apply(golden_dir):
+    g = np.load(os.path.join(golden_dir, GOLDEN[0]))
+    foreign = OperatorNP.load(asp.ls.system_path(str(g["system"])))  # only .basis.number_spins + .batched_apply
+    model = asp.make_ising_model(g["spins"], foreign, log_psi=g["log_psi"])
+    n = g["spins"].shape[0]
+    _assert_same_matrix(model.ising_hamiltonian.exchange, _coo_to_csr(g["live_row"], g["live_col"], g["live_data"], n))
+
+
+def test_input_normalisation_duplicates_unsorted_and_n8(golden_dir):
+    g = np.load(os.path.join(golden_dir, GOLDEN[0]))
+    op = asp.load_hamiltonian(asp.ls.system_path(str(g["system"])))
+    n = g["spins"].shape[0]
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(n)
+    dup = np.concatenate([perm, perm[:50]])
+    spins8 = np.zeros((dup.shape[0], 8), dtype=np.uint64)
+    spins8[:, 0] = g["spins"][dup]
+    model = asp.make_ising_model(spins8, op, log_psi=g["log_psi"][dup])
+    assert np.array_equal(model.spins, g["spins"])
+    _assert_same_matrix(model.ising_hamiltonian.exchange, _coo_to_csr(g["live_row"], g["live_col"], g["live_data"], n))
+    with pytest.raises(ValueError):
+        asp.make_ising_model(g["spins"], op)
+    with pytest.raises(ValueError):
+        asp.make_ising_model(np.zeros((4, 3), dtype=np.uint64), op, log_psi=np.zeros(4))
+    with pytest.raises(ValueError):
+        asp.make_ising_model(g["spins"], op, log_psi=g["log_psi"] + 0.3j)  # complex amplitudes
+
+
+def test_tiny_and_empty_inputs():
+    op = asp.load_hamiltonian(asp.ls.system_path("heisenberg_kagome_16"))
+    one = torch.tensor([0b0000000011111111], dtype=torch.int64, device=DEV)
+    psi = torch.ones(1, dtype=torch.float64, device=DEV)
+    indptr, indices, data = common.extract_csr_device(op, one, psi)
+    assert indptr.tolist() == [0, 1] and indices.tolist() == [0]
+    empty = torch.zeros(0, dtype=torch.int64, device=DEV)
+    indptr, indices, data = common.extract_csr_device(op, empty, torch.zeros(0, dtype=torch.float64, device=DEV))
+    assert indptr.tolist() == [0] and indices.numel() == 0
+
+
+def test_full_basis_known_answers(golden_dir, oracle_capi):
+    """KAT-1 (E(sign psi_ED) = E0), KAT-3 (nnz incl. one diagonal per row), KAT-6 (J = J^T)."""
+    from oracle.operator_np import ground_state
+
+    table = json.load(open(os.path.join(golden_dir, "known_answers.json")))
+    for name in ["j1j2_square_4x4", "heisenberg_kagome_18"]:
+        op_np = OperatorNP.load(asp.ls.system_path(name))
+        e0, psi, _ = ground_state(op_np)
+        op = asp.load_hamiltonian(asp.ls.system_path(name))
+        assert np.array_equal(op.basis.states, op_np.basis.states)
+        with np.errstate(divide="ignore"):
+            log_psi = np.log(psi.astype(np.complex128))
+        model = asp.make_ising_model(op.basis.states, op, log_psi=log_psi)
+        ex = model.ising_hamiltonian.exchange.tocsr()
+        if name == "j1j2_square_4x4":
+            assert ex.nnz == table[name]["T"] == 452166
+        assert np.all(ex.diagonal() != 0) or name != "j1j2_square_4x4"
+        assert abs(ex - ex.T).max() == 0.0
+        e = model.ising_hamiltonian.energy(model.initial_signs)
+        assert abs(e - table[name]["E0"]) < 1e-10
+        assert abs(e - oracle_capi.energy(ex.indptr, ex.indices, ex.data, None, model.initial_signs)) < 1e-10
+
+
+def test_row_block_shards_concatenate_to_the_unsharded_result():
+    """KAT-7: what each of G GPUs would build from its row block, bit for bit."""
+    op = asp.load_hamiltonian(asp.ls.system_path("sk_16_3"))
+    spins = synthetic.cluster_closed_states(op, 6000, 11, DEV)
+    psi = synthetic.synthetic_amplitudes(spins.shape[0], 11, device=DEV)
+    n = spins.shape[0]
+    indptr, indices, data = common.extract_csr_device(op, spins, psi)
+    for shards in [2, 3, 8]:
+        bounds = [n * k // shards for k in range(shards + 1)]
+        parts = [common.extract_csr_device(op, spins, psi, bounds[k], bounds[k + 1] - bounds[k]) for k in range(shards)]
+        assert torch.equal(torch.cat([p[1] for p in parts]), indices)
+        assert torch.equal(torch.cat([p[2] for p in parts]), data)
+        offset, glued = 0, [torch.zeros(1, dtype=torch.int64, device=DEV)]
+        for p in parts:
+            glued.append(p[0][1:] + offset)
+            offset += int(p[0][-1])
+        assert torch.equal(torch.cat(glued), indptr)
+
+
+def test_batched_apply_device_matches_oracle_including_symmetry_groups():
+    """Neighbour generation incl. orbit representatives / norms for the full kagome_36
+    (|G| = 144 x 2) and pyrochlore (|G| = 384 x 2) groups; canonical per-row comparison."""
+    for system, m in [("heisenberg_kagome_36", 300), ("heisenberg_pyrochlore_2x2x2", 200), ("heisenberg_kagome_18", 500),
+                      ("j1j2_square_4x4", 500)]:
+        cfg = asp.ls.load_config(asp.ls.system_path(system))
+        op_np = OperatorNP.from_config(cfg)
+        op = asp.load_hamiltonian(asp.ls.system_path(system))
+        raw = synthetic.random_sector_states(op.basis.number_spins, op.basis.hamming_weight, m, 5).numpy().view(np.uint64)
+        rep, _, norm = op_np.basis.state_info(raw)
+        rows = np.unique(rep[norm > 0])
+        s_ref, c_ref, k_ref = op_np.apply_u64(rows)
+        s, c, k = op.batched_apply(rows)
+        assert np.array_equal(k, k_ref)
+        off = np.concatenate([[0], np.cumsum(k)])
+        for r in range(rows.shape[0]):
+            a = np.argsort(s[off[r]:off[r + 1], 0], kind="stable")
+            b = np.argsort(s_ref[off[r]:off[r + 1]], kind="stable")
+            assert np.array_equal(s[off[r]:off[r + 1], 0][a], s_ref[off[r]:off[r + 1]][b])
+            got = np.bincount(np.unique(s[off[r]:off[r + 1], 0][a], return_inverse=True)[1], weights=c[off[r]:off[r + 1]].real[a])
+            exp = np.bincount(np.unique(s_ref[off[r]:off[r + 1]][b], return_inverse=True)[1], weights=c_ref[off[r]:off[r + 1]][b])
+            np.testing.assert_allclose(got, exp, rtol=1e-12, atol=1e-300)
+
+
+def test_symmetrised_kagome_36_extraction_vs_oracle():
+    """Full symmetrised path (orbit representatives + canonicalisation) on a subset of
+    representatives of the 36-spin kagome basis."""
+    system = "heisenberg_kagome_36"
+    op_np = OperatorNP.load(asp.ls.system_path(system))
+    op = asp.load_hamiltonian(asp.ls.system_path(system))
+    raw = synthetic.random_sector_states(36, 18, 15, 9).numpy().view(np.uint64)
+    rep, _, norm = op_np.basis.state_info(raw)
+    seeds = np.unique(rep[norm > 0])
+    shell, _, _ = op_np.apply_u64(seeds)
+    spins = np.unique(np.concatenate([seeds, shell]))
+    psi = synthetic.synthetic_amplitudes(spins.shape[0], 3).numpy()
+    d_spins = torch.from_numpy(spins.view(np.int64)).to(DEV)
+    indptr, indices, data = common.extract_csr_device(op, d_spins, torch.from_numpy(psi).to(DEV))
+    n = spins.shape[0]
+    ours = scipy.sparse.csr_matrix((data.cpu().numpy(), indices.cpu().numpy(), indptr.cpu().numpy()), shape=(n, n))
+    ref = _oracle_csr(op_np, spins, psi)
+    _assert_same_matrix((0.5 * (ours + ours.T)).tocsr(), ref)
+
+
+def test_properties_at_scale():
+    """Size-independent properties on a 2e6-state kagome_36-shaped U(1) subset: rows sorted and
+    duplicate-free, one diagonal per row, structurally symmetric, values symmetric bitwise,
+    random rows equal to the oracle's."""
+    cfg = asp.ls.load_config(asp.ls.system_path("heisenberg_kagome_36"))
+    cfg["basis"]["symmetries"], cfg["basis"]["spin_inversion"] = [], None
+    op = asp.ls.Operator.load_from_yaml(cfg["hamiltonian"], asp.ls.SpinBasis.load_from_yaml(cfg["basis"]))
+    op_np = OperatorNP.from_config(cfg)
+    spins = synthetic.cluster_closed_states(op, 2_000_000, 21, DEV)
+    n = spins.shape[0]
+    psi = synthetic.synthetic_amplitudes(n, 21, device=DEV)
+    indptr, indices, data = common.extract_csr_device(op, spins, psi)
+    lens = indptr[1:] - indptr[:-1]
+    rows = torch.repeat_interleave(torch.arange(n, device=DEV), lens)
+    assert int(indptr[0]) == 0 and int(indptr[-1]) == indices.numel() and bool((lens >= 1).all())
+    same_row = rows[1:] == rows[:-1]
+    assert bool((indices[1:][same_row] > indices[:-1][same_row]).all())  # strictly ascending
+    assert int((indices.to(torch.int64) == rows).sum()) == n  # exactly one diagonal per row
+    before = data.clone()
+    common.symmetrize_csr_device(n, indptr, indices, data)  # raises if the pattern is asymmetric
+    assert torch.equal(before, data)  # c (|psi_i| |psi_j|) is already symmetric bitwise
+    # spot check 200 random rows against the oracle
+    pick = np.sort(np.random.default_rng(0).choice(n, 200, replace=False))
+    h_spins = spins.cpu().numpy().view(np.uint64)
+    h_psi = psi.cpu().numpy()
+    s, c, k = op_np.apply_u64(h_spins[pick])
+    pos = np.clip(np.searchsorted(h_spins, s), 0, n - 1)
+    hit = h_spins[pos] == s
+    off = np.concatenate([[0], np.cumsum(k)])
+    h_indptr, h_indices, h_data = indptr.cpu().numpy(), indices.cpu().numpy(), data.cpu().numpy()
+    for q, r in enumerate(pick):
+        sel = slice(off[q], off[q + 1])
+        cols = pos[sel][hit[sel]]
+        vals = c[sel][hit[sel]] * np.abs(h_psi[cols]) * abs(h_psi[r])
+        order = np.argsort(cols)
+        assert np.array_equal(h_indices[h_indptr[r]:h_indptr[r + 1]], cols[order])
+        np.testing.assert_allclose(h_data[h_indptr[r]:h_indptr[r + 1]], vals[order], rtol=1e-12)
+
+
+def test_host_buffer_entry_points_match_device_path():
+    op = asp.load_hamiltonian(asp.ls.system_path("j1j2_square_4x4"))
+    spins = synthetic.cluster_closed_states(op, 5000, 2, DEV)
+    psi = synthetic.synthetic_amplitudes(spins.shape[0], 2, device=DEV)
+    indptr, indices, data = common.extract_csr_device(op, spins, psi)
+    h_spins = spins.cpu().numpy().view(np.uint64)
+    h_psi = psi.cpu().numpy()
+    n = h_spins.shape[0]
+    nnz = ffi.new("uint64_t *")
+    job = ffi.new("asp_host_job **")
+    rc = lib().asp_extract_host_begin(op.handle, n, ffi.cast("uint64_t *", h_spins.ctypes.data),
+                                      ffi.cast("double *", h_psi.ctypes.data), 0, n, nnz, job)
+    assert rc == 0 and nnz[0] == indices.numel()
+    hp = np.zeros(n + 1, dtype=np.int64)
+    hi = np.zeros(nnz[0], dtype=np.int32)
+    hd = np.zeros(nnz[0], dtype=np.float64)
+    rc = lib().asp_extract_host_finish(job[0], ffi.cast("int64_t *", hp.ctypes.data), ffi.cast("int32_t *", hi.ctypes.data),
+                                       ffi.cast("double *", hd.ctypes.data))
+    assert rc == 0
+    assert np.array_equal(hp, indptr.cpu().numpy()) and np.array_equal(hi, indices.cpu().numpy())
+    assert np.array_equal(hd, data.cpu().numpy())
