@@ -124,14 +124,15 @@ __device__ __forceinline__ int64_t basis_find(const BasisIndex &ix, uint64_t c) 
   if (b >= ix.num_buckets) return -1;
   const uint2 se = __ldg(&ix.table[b]);
   uint32_t lo = se.x, hi = se.y;
-  while (hi - lo > 4) {
+  const uint32_t end = se.y;
+  while (hi - lo > 4) {  // invariant: first key >= c lies in [lo, hi]
     const uint32_t mid = lo + ((hi - lo) >> 1);
     if (__ldg(&ix.spins[mid]) < c)
       lo = mid + 1;
     else
       hi = mid;
   }
-  for (; lo < hi; ++lo) {
+  for (; lo < end; ++lo) {  // at most 5 steps: spins[hi] >= c when hi < end
     const uint64_t k = __ldg(&ix.spins[lo]);
     if (k >= c) return k == c ? static_cast<int64_t>(lo) : -1;
   }
@@ -375,11 +376,12 @@ int asp_extract_fill(asp_operator const *op, uint64_t n_total, uint64_t const *d
   ExtractArgs a{};
   int rc = fused_args(op, n_total, d_spins, row_begin, num_rows, d_workspace, workspace_bytes, w, a);
   if (rc != ASP_OK) return rc;
-  ASP_REQUIRE(d_psi && d_indptr, "NULL output/input buffer");
+  ASP_REQUIRE(d_indptr != nullptr, "d_indptr is NULL");
   if (num_rows == 0 || n_total == 0) {
     ASP_CUDA_CHECK(cudaMemsetAsync(d_indptr, 0, sizeof(int64_t), s));
     return ASP_OK;
   }
+  ASP_REQUIRE(d_psi != nullptr, "d_psi is NULL");
   const int key_bits = static_cast<int>(op->number_spins);
   int bits = 0;
   while ((1ull << bits) < w.num_buckets) ++bits;

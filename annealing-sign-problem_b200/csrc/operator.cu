@@ -166,19 +166,33 @@ int asp_operator_create(asp_operator **out, uint32_t number_spins, int32_t hammi
     }
   }
   std::stable_sort(keyed.begin(), keyed.end(), [](const Keyed &x, const Keyed &y) { return x.delta < y.delta; });
+  // identical moves (same bond listed twice) are merged, coefficients summed in listed order
   op->n_down = 0;
   for (const auto &k : keyed) {
+    bool merged = false;
+    for (auto &m : op->moves)
+      if (m.mask == k.m.mask && m.need == k.m.need && m.flip == k.m.flip) {
+        m.coef += k.m.coef;
+        merged = true;
+        break;
+      }
+    if (merged) continue;
     if (k.delta < 0) ++op->n_down;
     op->moves.push_back(k.m);
   }
-  // Two moves with the same flip can apply to the same word (same candidate twice):
-  // then rows are not duplicate-free and the canonicalising path must be used.
-  {
-    std::vector<uint64_t> flips;
-    for (const auto &m : op->moves) flips.push_back(m.flip);
-    std::sort(flips.begin(), flips.end());
-    op->distinct_flips = std::adjacent_find(flips.begin(), flips.end()) == flips.end();
-  }
+  // Two different moves with the same flip that can both apply to one word would emit the
+  // same candidate twice: then rows are not duplicate-free and the canonicalising path must
+  // be used.  (The two directions of an exchange share a flip but never apply together.)
+  op->distinct_flips = true;
+  for (size_t a = 0; a < op->moves.size() && op->distinct_flips; ++a)
+    for (size_t b = a + 1; b < op->moves.size(); ++b) {
+      if (op->moves[b].flip != op->moves[a].flip) continue;
+      const uint64_t shared = op->moves[a].mask & op->moves[b].mask;
+      if (((op->moves[a].need ^ op->moves[b].need) & shared) == 0) {
+        op->distinct_flips = false;
+        break;
+      }
+    }
   for (uint32_t g = 0; g < num_perms; ++g) {
     asp::BitPerm net;
     if (!asp::make_bit_perm(perms + static_cast<size_t>(g) * number_spins, number_spins, net)) {

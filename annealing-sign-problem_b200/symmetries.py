@@ -168,8 +168,7 @@ class Operator:
     # -- C-ABI handle -----------------------------------------------------------------
     @property
     def handle(self):
-        if self._handle is None:
-            require_cuda()
+        if self._handle is None:  # host-side compilation needs no device; kernels do
             mats = np.ascontiguousarray(np.stack([m for m, _ in self.terms]).reshape(-1), dtype=np.float64) \
                 if self.terms else np.zeros(0, dtype=np.float64)
             offsets = np.zeros(len(self.terms) + 1, dtype=np.uint32)

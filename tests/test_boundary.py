@@ -95,6 +95,27 @@ def test_symmetry_groups_and_system_files(asp):
         asp.ls.Operator(asp.ls.SpinBasis(4), [{"matrix": np.eye(3), "sites": [[0, 1]]}])
 
 
+def test_operator_compiles_to_sorted_moves_on_the_host(asp):
+    """Bond list -> delta-sorted XOR moves: exchange terms on distinct pairs give a sorted,
+    duplicate-free emitter (2 moves per bond + the diagonal); symmetrised bases do not."""
+    for name, bonds in [("heisenberg_kagome_36", 72), ("j1j2_square_4x4", 64), ("sk_32_1", 496)]:
+        cfg = asp.ls.load_config(asp.ls.system_path(name))
+        cfg["basis"]["symmetries"], cfg["basis"]["spin_inversion"] = [], None
+        op = asp.ls.Operator.load_from_yaml(cfg["hamiltonian"], asp.ls.SpinBasis.load_from_yaml(cfg["basis"]))
+        assert op.max_candidates == 2 * bonds + 1
+        assert op.is_sorted_emitter
+    assert not asp.load_hamiltonian(asp.ls.system_path("heisenberg_kagome_18")).is_sorted_emitter
+    assert not asp.load_hamiltonian(asp.ls.system_path("heisenberg_kagome_36")).is_sorted_emitter  # Benes networks self-check
+    # the same bond twice merges into one move; a single-site-like flip from two bonds is not sorted
+    basis = asp.ls.SpinBasis(4)
+    heis = [[1, 0, 0, 0], [0, -1, 2, 0], [0, 2, -1, 0], [0, 0, 0, 1]]
+    twice = asp.ls.Operator(basis, [{"matrix": heis, "sites": [[0, 1], [0, 1]]}])
+    assert twice.max_candidates == 3 and twice.is_sorted_emitter
+    flip_j = [[0, 1, 0, 0], [1, 0, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]]  # sigma^x on the second site
+    clash = asp.ls.Operator(basis, [{"matrix": flip_j, "sites": [[0, 2], [1, 2]]}])
+    assert not clash.is_sorted_emitter
+
+
 def test_two_rank_sharding_plan_over_gloo(tmp_path):
     """world_size-2 gloo run of the row-block / replica partition used by bench.py --gpus N."""
     script = os.path.join(ROOT, "tests", "_gloo_sharding.py")

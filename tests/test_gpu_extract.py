@@ -71,11 +71,13 @@ def test_legacy_build_matrix_dropin_is_bitwise_the_reference_c(golden_dir, name)
     cols = np.zeros(T, dtype=np.uint32)
     vals = np.zeros(T, dtype=np.float64)
     field = np.full(n, 7.0)
+    other_coeffs = np.ascontiguousarray(g["other_coeffs"])  # keep the buffers alive across the call
+    other_counts = np.ascontiguousarray(g["other_counts"])
+    other_psi = np.ascontiguousarray(g["other_psi"])
     c = lambda a, t: ffi.cast(t, a.ctypes.data)  # noqa: E731
     nnz = lib().asp_build_matrix(n, c(s512, "asp_bits512 *"), c(counts, "int64_t *"), c(psi, "double *"),
-                                 c(o512, "asp_bits512 *"), c(np.ascontiguousarray(g["other_coeffs"]), "double *"),
-                                 c(np.ascontiguousarray(g["other_counts"]), "int64_t *"),
-                                 c(np.ascontiguousarray(g["other_psi"]), "double *"),
+                                 c(o512, "asp_bits512 *"), c(other_coeffs, "double *"), c(other_counts, "int64_t *"),
+                                 c(other_psi, "double *"),
                                  c(rows, "uint32_t *"), c(cols, "uint32_t *"), c(vals, "double *"), c(field, "double *"))
     assert nnz == g["c_rows"].shape[0]
     assert np.array_equal(rows[:nnz], g["c_rows"])
