@@ -52,7 +52,9 @@ def cluster_closed_states(operator, n: int, seed: int, device="cuda", interior_f
     extensions.  About `interior_fraction` of the rows keep all their neighbours, so roughly a
     third of all candidates are hits (the regime of SURVEY.md section 8d).  Needs CUDA."""
     basis = operator.basis
-    d = max(2.0, operator.max_candidates / 2.0)
+    # candidates per row: one of a bond's two exchange moves applies to an antiparallel pair,
+    # about half of the bonds are antiparallel at half filling
+    d = max(2.0, operator.max_candidates / 4.0)
     m = max(1, int(n * interior_fraction / (d + 1.0)))
     seeds = random_sector_states(basis.number_spins, basis.hamming_weight, m, seed, device)
     shell1, _, _ = operator.batched_apply_device(seeds)

@@ -54,55 +54,60 @@ def hbm_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock + throttle reasons sampled through NVML every 5 ms DURING the timed region."""
 
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, gpu_id):
-        self.gpu_id = gpu_id
-        self.proc = None
-        self.lines = []
+    def __init__(self, gpu_uuid, gpu_index):
+        self.uuid, self.index = gpu_uuid, gpu_index
+        self.samples, self.reason_bits = [], 0
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.max_mhz = None
+        self.error = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu_id), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+            import pynvml
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            pynvml.nvmlInit()
+            try:
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(self.uuid.encode() if isinstance(self.uuid, str) else self.uuid)
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+        except Exception as exc:  # pragma: no cover
+            self.error = repr(exc)
+
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            except Exception as exc:  # pragma: no cover
+                self.error = repr(exc)
+                return
+            time.sleep(0.005)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
-            parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[3:7]):
-                if val == "Active":
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self.stop_flag.set()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        names = []
+        if self.thread is not None:
+            nv = self.nv
+            table = [("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", 0x8), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                     ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", 0x20), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", 0x4)]
+            for name, attr, default in table:
+                if self.reason_bits & int(getattr(nv, attr, default)):
+                    names.append(name)
+        out = {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+               "samples": len(self.samples), "reasons": names}
+        if self.error:
+            out["error"] = self.error
+        return out
 
 
 def u1_operator(asp):
@@ -272,7 +277,7 @@ def run_ours(args):
     nnz_mine = int(out[1].numel())
     del out
     uuid = getattr(torch.cuda.get_device_properties(dev), "uuid", None)
-    sampler = ClockSampler("GPU-" + str(uuid) if uuid else local)
+    sampler = ClockSampler("GPU-" + str(uuid) if uuid else "", local)
     if rank == 0:
         sampler.start()
     launches0 = int(lib().asp_kernel_launch_count())

@@ -148,6 +148,9 @@ int asp_extract_host_begin(asp_operator const *op, uint64_t n_total, uint64_t co
                            double const *h_psi, uint64_t row_begin, uint64_t num_rows,
                            uint64_t *h_nnz, asp_host_job **job);
 int asp_extract_host_finish(asp_host_job *job, int64_t *h_indptr, int32_t *h_indices, double *h_data);
+/* The host entry points keep their device buffers in a process-wide arena that only grows
+ * (one job in flight at a time); this frees it. */
+void asp_host_release(void);
 
 /* ------------------------------------------------------------------------------------
  * 3. Energies and overlaps (replace sa.Hamiltonian.energy, full_hilbert_space.py:144, and
