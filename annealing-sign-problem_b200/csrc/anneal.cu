@@ -45,6 +45,7 @@ struct asp_sa_plan {
   double *d_field = nullptr;      // [n_padded]
   int64_t *d_class_ptr = nullptr; // [num_classes + 1]
   std::vector<int64_t> class_ptr;
+  double diag_sum = 0.0;          // sum_i J_ii of the original model (constant part of the energy)
 };
 
 namespace asp {
@@ -224,8 +225,9 @@ struct SaArgs {
   unsigned long long *barriers;  // [num_teams] zeroed by the host
 };
 
-constexpr int kSaThreads = 512;
+constexpr int kSaThreads = 256;
 constexpr int kSaWarps = kSaThreads / 32;
+constexpr int kSaCtasPerSm = 3;  // 24 warps/SM: hides the indptr -> entries -> spin-word load chain
 
 struct TeamBarrier {
   unsigned long long *counter;
@@ -255,7 +257,56 @@ struct __align__(16) StagedEntry {
   uint32_t pad;
 };
 
-__global__ void __launch_bounds__(kSaThreads, 1) sa_sweep_kernel(const SaArgs a) {
+// +val when bit `lane` of `word` is set, -val otherwise (sign-bit XOR: exact)
+__device__ __forceinline__ double signed_by_bit(double val, uint32_t word, uint32_t lane) {
+  const uint32_t flip = (((~word) >> lane) & 1u) << 31;
+  return __hiloint2double(__double2hiint(val) ^ static_cast<int>(flip), __double2loint(val));
+}
+
+// A warp-task = 4 consecutive positions x 32 replicas.  The entries of the 4 rows are ONE
+// contiguous span of the CSR: lanes load (value, column) coalesced, gather the 32-replica
+// spin word of their column, and stage the pairs in shared memory; then every lane (= one
+// replica) walks the staged span and sums each row's local field in stored order.
+struct TaskRows {
+  int32_t b[5];  // row boundaries relative to the first entry of the span
+};
+
+// sums[j] = sum over row j of (+/-) val in stored order, for this lane's replica.
+// first-chunk (value, word) of the span arrive in (pv, wv); later chunks are loaded here.
+__device__ __forceinline__ void accumulate_rows(const TaskRows &rows, int64_t e_begin, double pv, uint32_t wv, const int32_t *__restrict__ indices,
+                                                const double *__restrict__ data, const uint32_t *words, StagedEntry *stage, uint32_t lane,
+                                                double acc[4]) {
+  acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
+  const int32_t span = rows.b[4];
+  for (int32_t cb = 0; cb < span; cb += 32) {
+    if (cb != 0) {
+      pv = 0.0;
+      wv = 0u;
+      if (cb + static_cast<int32_t>(lane) < span) {
+        const int64_t e = e_begin + cb + lane;
+        pv = __ldg(&data[e]);
+        wv = __ldcg(&words[__ldg(&indices[e])]);
+      }
+    }
+    __syncwarp();
+    StagedEntry se;
+    se.val = pv;
+    se.word = wv;
+    se.pad = 0;
+    stage[lane] = se;
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int32_t lo = max(rows.b[j], cb) - cb, hi = min(rows.b[j + 1], cb + 32) - cb;
+      for (int32_t k = lo; k < hi; ++k) {
+        const StagedEntry x = stage[k];
+        acc[j] = __dadd_rn(acc[j], signed_by_bit(x.val, x.word, lane));
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm) sa_sweep_kernel(const SaArgs a) {
   __shared__ StagedEntry s_stage[kSaWarps][32];
   const uint32_t lane = threadIdx.x & 31, warp_in_cta = threadIdx.x >> 5;
   const uint32_t team = blockIdx.x / a.team_size;
@@ -278,36 +329,60 @@ __global__ void __launch_bounds__(kSaThreads, 1) sa_sweep_kernel(const SaArgs a)
       long long rel_delta = 0;
       for (uint32_t c = 0; c < a.num_classes; ++c) {
         const uint64_t q_begin = static_cast<uint64_t>(a.class_ptr[c]) >> 2, q_end = static_cast<uint64_t>(a.class_ptr[c + 1]) >> 2;
-        for (uint64_t q = q_begin + my_warp; q < q_end; q += team_warps) {
+        uint64_t q = q_begin + my_warp;
+        // software pipeline over this warp's tasks of the class: row pointers two tasks ahead,
+        // first-chunk (value, column) one task ahead (the CSR is read-only, so prefetching is safe;
+        // spin words are only read after the class barrier)
+        int64_t ip0 = 0, ip1 = 0;
+        double pv = 0.0;
+        int32_t pi = 0;
+        if (q < q_end && lane < 5) ip0 = __ldg(&a.indptr[q * 4 + lane]);
+        if (q + team_warps < q_end && lane < 5) ip1 = __ldg(&a.indptr[(q + team_warps) * 4 + lane]);
+        if (q < q_end) {
+          const int64_t eb = __shfl_sync(0xffffffffu, ip0, 0), ee = __shfl_sync(0xffffffffu, ip0, 4);
+          if (eb + lane < ee) {
+            pv = __ldg(&a.data[eb + lane]);
+            pi = __ldg(&a.indices[eb + lane]);
+          }
+        }
+        for (; q < q_end; q += team_warps) {
           const uint64_t p0 = q * 4;
+          const int64_t e_begin = __shfl_sync(0xffffffffu, ip0, 0);
+          const int32_t rel_ip = static_cast<int32_t>(ip0 - e_begin);
+          TaskRows rows;
+          rows.b[0] = 0;
+#pragma unroll
+          for (int j = 1; j < 5; ++j) rows.b[j] = __shfl_sync(0xffffffffu, rel_ip, j);
+          // this task's spin words (after the barrier: always fresh from L2)
+          uint32_t wv = 0u;
+          if (static_cast<int32_t>(lane) < rows.b[4]) wv = __ldcg(&words[pi]);
           const uint4 cur = __ldcg(reinterpret_cast<const uint4 *>(words + p0));
+          const double my_field = lane < 4 ? __ldg(&a.field[p0 + lane]) : 0.0;
+          const double cur_pv = pv;
+          // prefetch for the following tasks
+          int64_t ip2 = 0;
+          if (q + 2ull * team_warps < q_end && lane < 5) ip2 = __ldg(&a.indptr[(q + 2ull * team_warps) * 4 + lane]);
+          pv = 0.0;
+          pi = 0;
+          if (q + team_warps < q_end) {
+            const int64_t eb = __shfl_sync(0xffffffffu, ip1, 0), ee = __shfl_sync(0xffffffffu, ip1, 4);
+            if (eb + lane < ee) {
+              pv = __ldg(&a.data[eb + lane]);
+              pi = __ldg(&a.indices[eb + lane]);
+            }
+          }
+          ip0 = ip1;
+          ip1 = ip2;
+
+          double acc[4];
+          accumulate_rows(rows, e_begin, cur_pv, wv, a.indices, a.data, words, stage, lane, acc);
           const uint32_t cur_w[4] = {cur.x, cur.y, cur.z, cur.w};
           double dE[4];
           bool need_rng = false;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int64_t e_begin = a.indptr[p0 + j], e_end = a.indptr[p0 + j + 1];
-            double acc = 0.0;
-            for (int64_t chunk = e_begin; chunk < e_end; chunk += 32) {
-              const int64_t e = chunk + lane;
-              StagedEntry se;
-              se.val = 0.0;
-              se.word = 0;
-              se.pad = 0;
-              if (e < e_end) {
-                se.val = __ldg(&a.data[e]);
-                se.word = __ldcg(&words[__ldg(&a.indices[e])]);
-              }
-              __syncwarp();
-              stage[lane] = se;
-              __syncwarp();
-              const int cnt = static_cast<int>(min(static_cast<int64_t>(32), e_end - chunk));
-              for (int k = 0; k < cnt; ++k) {
-                const StagedEntry x = stage[k];
-                acc = __dadd_rn(acc, ((x.word >> lane) & 1) ? x.val : -x.val);
-              }
-            }
-            const double gsum = __dadd_rn(__dmul_rn(4.0, acc), __dmul_rn(2.0, a.field[p0 + j]));
+            const double fj = __shfl_sync(0xffffffffu, my_field, j);
+            const double gsum = __dadd_rn(__dmul_rn(4.0, acc[j]), __dmul_rn(2.0, fj));
             dE[j] = ((cur_w[j] >> lane) & 1) ? -gsum : gsum;
             need_rng |= dE[j] > 0.0 && __dmul_rn(beta, dE[j]) < kRejectAbove;
           }
@@ -359,27 +434,154 @@ __global__ void __launch_bounds__(kSaThreads, 1) sa_sweep_kernel(const SaArgs a)
   }
 }
 
+// ---- exact energies of the relabelled, replica-sliced configurations --------------------
+// E_r = sum_p s_p (sum_{j != p} J_pj s_j + h_p) + sum_i J_ii: same task shape as the sweep
+// (a CSR row is read once per 32 replicas).  Fixed grid + fixed summation order: deterministic.
+constexpr int kEnWarps = 8;
+
+__global__ void __launch_bounds__(kEnWarps * 32) energy_sliced_kernel(uint64_t n_padded, const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                                                                      const double *__restrict__ data, const double *__restrict__ field,
+                                                                      const uint32_t *__restrict__ all_words, double *__restrict__ partial) {
+  __shared__ StagedEntry s_stage[kEnWarps][32];
+  const uint32_t lane = threadIdx.x & 31, warp_in_cta = threadIdx.x >> 5;
+  const uint32_t g = blockIdx.y;
+  const uint32_t *words = all_words + static_cast<uint64_t>(g) * n_padded;
+  const uint64_t total_warps = static_cast<uint64_t>(gridDim.x) * kEnWarps;
+  const uint64_t warp_global = static_cast<uint64_t>(blockIdx.x) * kEnWarps + warp_in_cta;
+  StagedEntry *stage = s_stage[warp_in_cta];
+  double e = 0.0;
+  for (uint64_t q = warp_global; q < n_padded / 4; q += total_warps) {
+    const uint64_t p0 = q * 4;
+    const int64_t ip = lane < 5 ? __ldg(&indptr[p0 + lane]) : 0;
+    const int64_t e_begin = __shfl_sync(0xffffffffu, ip, 0);
+    const int32_t rel_ip = static_cast<int32_t>(ip - e_begin);
+    TaskRows rows;
+    rows.b[0] = 0;
+#pragma unroll
+    for (int j = 1; j < 5; ++j) rows.b[j] = __shfl_sync(0xffffffffu, rel_ip, j);
+    double pv = 0.0;
+    uint32_t wv = 0u;
+    if (static_cast<int32_t>(lane) < rows.b[4]) {
+      pv = __ldg(&data[e_begin + lane]);
+      wv = __ldg(&words[__ldg(&indices[e_begin + lane])]);
+    }
+    const uint4 cur = __ldg(reinterpret_cast<const uint4 *>(words + p0));
+    const double my_field = lane < 4 ? __ldg(&field[p0 + lane]) : 0.0;
+    double acc[4];
+    accumulate_rows(rows, e_begin, pv, wv, indices, data, words, stage, lane, acc);
+    const uint32_t cur_w[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double local = __dadd_rn(acc[j], __shfl_sync(0xffffffffu, my_field, j));
+      e = __dadd_rn(e, ((cur_w[j] >> lane) & 1) ? local : -local);
+    }
+  }
+  partial[(static_cast<uint64_t>(g) * total_warps + warp_global) * 32 + lane] = e;
+}
+
+// one CTA per group: thread (w, lane) sums the partials of warps w, w+8, ...; the 8 strided
+// sums are combined in a fixed order, then the diagonal constant is added.
+__global__ void __launch_bounds__(256) energy_sliced_final_kernel(const double *__restrict__ partial, uint64_t total_warps, double diag_sum,
+                                                                  uint32_t num_replicas, double *__restrict__ out) {
+  __shared__ double s_sum[8][32];
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = blockIdx.x;
+  const double *p = partial + static_cast<uint64_t>(g) * total_warps * 32;
+  double acc = 0.0;
+  for (uint64_t k = w; k < total_warps; k += 8) acc = __dadd_rn(acc, p[k * 32 + lane]);
+  s_sum[w][lane] = acc;
+  __syncthreads();
+  if (w == 0) {
+    double total = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) total = __dadd_rn(total, s_sum[k][lane]);
+    const uint32_t r = g * 32 + lane;
+    if (r < num_replicas) out[r] = __dadd_rn(total, diag_sum);
+  }
+}
+
+// sum of the diagonal of the ORIGINAL model (dropped from the relabelled CSR): block partials
+__global__ void __launch_bounds__(256) diag_partial_kernel(uint64_t n, const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                                                           const double *__restrict__ data, double *__restrict__ partial) {
+  __shared__ double smem[8];
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x;
+  double d = 0.0;
+  if (i < n)
+    for (int64_t k = indptr[i]; k < indptr[i + 1]; ++k)
+      if (static_cast<uint64_t>(indices[k]) == i) d = __dadd_rn(d, data[k]);
+  d = warp_sum(d);
+  if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = d;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t = __dadd_rn(t, smem[k]);
+    partial[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) diag_final_kernel(const double *__restrict__ partial, uint64_t count, double *__restrict__ out) {
+  __shared__ double smem[256];
+  double acc = 0.0;
+  for (uint64_t k = threadIdx.x; k < count; k += 256) acc = __dadd_rn(acc, partial[k]);
+  smem[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < 256; ++k) t = __dadd_rn(t, smem[k]);
+    *out = t;
+  }
+}
+
 // ---- outputs: relabelled [groups][n_padded] words -> original-order packed [R][words64] --
+// A warp transposes 256 consecutive original spins of one replica group: lane = spin while
+// gathering (position[] coalesced), lane = replica after 32 ballots, so every replica writes
+// 32 contiguous bytes of its packed vector.
 __global__ void __launch_bounds__(256) sa_unpermute_kernel(uint64_t n, uint64_t n_padded, uint32_t num_replicas, const int32_t *__restrict__ position,
                                                            const uint32_t *__restrict__ best_words, uint64_t *__restrict__ out) {
-  const uint64_t words64 = (n + 63) / 64;
-  const uint64_t idx = static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x;
-  if (idx >= words64 * num_replicas) return;
-  const uint32_t r = static_cast<uint32_t>(idx / words64);
-  const uint64_t w = idx % words64;
-  const uint32_t *src = best_words + static_cast<uint64_t>(r >> 5) * n_padded;
-  uint64_t bits = 0;
-  for (int b = 0; b < 64; ++b) {
-    const uint64_t i = w * 64 + b;
-    if (i >= n) break;
-    bits |= static_cast<uint64_t>((src[position[i]] >> (r & 31)) & 1) << b;
+  const uint64_t warp_global = (static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31, g = blockIdx.y;
+  const uint64_t i0 = warp_global * 256;
+  if (i0 >= n) return;
+  const uint32_t *src = best_words + static_cast<uint64_t>(g) * n_padded;
+  uint32_t mine[8];
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    const uint64_t i = i0 + 32 * s + lane;
+    const uint32_t w = i < n ? __ldg(&src[__ldg(&position[i])]) : 0u;
+    uint32_t m = 0;
+#pragma unroll
+    for (uint32_t r = 0; r < 32; ++r) {
+      const uint32_t b = __ballot_sync(0xffffffffu, (w >> r) & 1u);
+      if (lane == r) m = b;
+    }
+    mine[s] = m;
   }
-  out[idx] = bits;
+  const uint32_t r = g * 32 + lane;
+  if (r >= num_replicas) return;
+  const uint64_t words64 = (n + 63) / 64;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint64_t wi = i0 / 64 + k;
+    if (wi < words64) out[static_cast<uint64_t>(r) * words64 + wi] = static_cast<uint64_t>(mine[2 * k]) | (static_cast<uint64_t>(mine[2 * k + 1]) << 32);
+  }
 }
 
 }  // namespace asp
 
 using namespace asp;
+
+// The stream-ordered allocations of a call are returned to the default pool at its end; keep
+// them cached there instead of handing them back to the driver at every synchronisation.
+static cudaError_t keep_pool_memory(int device) {
+  static bool done[64] = {};
+  if (device < 0 || device >= 64 || done[device]) return cudaSuccess;
+  cudaMemPool_t pool;
+  cudaError_t e = cudaDeviceGetDefaultMemPool(&pool, device);
+  if (e != cudaSuccess) return e;
+  uint64_t threshold = UINT64_MAX;
+  e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+  if (e == cudaSuccess) done[device] = true;
+  return e;
+}
 
 extern "C" {
 
@@ -491,6 +693,18 @@ int asp_sa_plan_create(asp_sa_plan **out, uint64_t n, int64_t const *d_indptr, i
   relabel_fill_kernel<<<pblocks, 256, 0, s>>>(np, plan->d_order, plan->d_position, d_indptr, d_indices, d_data, d_field,
                                               plan->d_indptr, plan->d_indices, plan->d_data, plan->d_field);
   ASP_LAUNCH_CHECK();
+  {  // constant part of the energy: the diagonal, summed in a fixed order
+    const unsigned dblocks = static_cast<unsigned>((n + 255) / 256);
+    double *d_part = nullptr;
+    ASP_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&d_part), (dblocks + 1) * sizeof(double)));
+    diag_partial_kernel<<<dblocks, 256, 0, s>>>(n, d_indptr, d_indices, d_data, d_part);
+    ASP_LAUNCH_CHECK();
+    diag_final_kernel<<<1, 256, 0, s>>>(d_part, dblocks, d_part + dblocks);
+    ASP_LAUNCH_CHECK();
+    ASP_CUDA_CHECK(cudaMemcpyAsync(&plan->diag_sum, d_part + dblocks, sizeof(double), cudaMemcpyDeviceToHost, s));
+    ASP_CUDA_CHECK(cudaStreamSynchronize(s));
+    cudaFree(d_part);
+  }
   ASP_CUDA_CHECK(cudaStreamSynchronize(s));
   guard.p = nullptr;
   *out = plan;
@@ -533,6 +747,7 @@ int asp_sa_anneal(asp_sa_plan *plan, uint32_t num_replicas, uint32_t replica_off
 
   int device = 0, sms = 0, per_sm = 0, coop = 0;
   ASP_CUDA_CHECK(cudaGetDevice(&device));
+  ASP_CUDA_CHECK(keep_pool_memory(device));
   ASP_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   ASP_CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
   ASP_REQUIRE(coop != 0, "device does not support cooperative launches");
@@ -596,13 +811,24 @@ int asp_sa_anneal(asp_sa_plan *plan, uint32_t num_replicas, uint32_t replica_off
     g_launches.fetch_add(1, std::memory_order_relaxed);
   }
   {
-    const uint64_t total = ((plan->n + 63) / 64) * num_replicas;
-    sa_unpermute_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(plan->n, np, num_replicas, plan->d_position, a.best_words, d_best_bits);
+    const uint64_t warps = (plan->n + 255) / 256;
+    sa_unpermute_kernel<<<dim3(static_cast<unsigned>((warps + 7) / 8), groups), 256, 0, s>>>(plan->n, np, num_replicas, plan->d_position, a.best_words, d_best_bits);
     ASP_LAUNCH_CHECK();
   }
   int rc = ASP_OK;
-  if (d_best_energy)
-    rc = asp_energy(plan->n, plan->d_indptr0, plan->d_indices0, plan->d_data0, plan->d_field0, num_replicas, d_best_bits, d_best_energy, s);
+  if (d_best_energy) {
+    // exact f64 energies straight from the replica-sliced best configurations
+    const uint64_t tasks = np / 4;
+    const unsigned en_ctas = static_cast<unsigned>(std::min<uint64_t>((tasks + kEnWarps - 1) / kEnWarps, static_cast<uint64_t>(kNumSMs) * 8));
+    const uint64_t total_warps = static_cast<uint64_t>(en_ctas) * kEnWarps;
+    double *partial = nullptr;
+    ASP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&partial), groups * total_warps * 32 * sizeof(double), s));
+    energy_sliced_kernel<<<dim3(en_ctas, groups), kEnWarps * 32, 0, s>>>(np, plan->d_indptr, plan->d_indices, plan->d_data, plan->d_field, a.best_words, partial);
+    ASP_LAUNCH_CHECK();
+    energy_sliced_final_kernel<<<groups, 256, 0, s>>>(partial, total_warps, plan->diag_sum, num_replicas, d_best_energy);
+    ASP_LAUNCH_CHECK();
+    ASP_CUDA_CHECK(cudaFreeAsync(partial, s));
+  }
   ASP_CUDA_CHECK(cudaFreeAsync(d_betas, s));
   ASP_CUDA_CHECK(cudaFreeAsync(a.words, s));
   ASP_CUDA_CHECK(cudaFreeAsync(a.best_words, s));
