@@ -77,31 +77,82 @@ def _sort_unique_device(x: torch.Tensor):
 # ---------------------------------------------------------------------------------------
 # Device-resident extraction (what bench.py times as `value`; host wrappers below add I/O)
 # ---------------------------------------------------------------------------------------
+def extract_csr_two_pass_device(operator: ls.Operator, spins: torch.Tensor, psi: torch.Tensor,
+                                row_begin: int = 0, num_rows: Optional[int] = None, workspace: Optional[torch.Tensor] = None):
+    """asp_extract_count + asp_extract_fill: the exact-allocation two-call API (every candidate
+    is searched twice).  Same result as :func:`extract_csr_device`."""
+    dev = require_cuda()
+    n_total = int(spins.shape[0])
+    if num_rows is None:
+        num_rows = n_total - row_begin
+    need = int(lib().asp_extract_workspace_bytes(operator.handle, n_total, num_rows))
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+    nnz = ffi.new("uint64_t *")
+    check(lib().asp_extract_count(operator.handle, n_total, ptr(spins, "uint64_t *"), row_begin, num_rows,
+                                  ptr(workspace, "void *"), workspace.numel(), nnz, stream()))
+    indptr = torch.empty(num_rows + 1, dtype=torch.int64, device=dev)
+    indices = torch.empty(int(nnz[0]), dtype=torch.int32, device=dev)
+    data = torch.empty(int(nnz[0]), dtype=torch.float64, device=dev)
+    check(lib().asp_extract_fill(operator.handle, n_total, ptr(spins, "uint64_t *"), ptr(psi, "double *"),
+                                 row_begin, num_rows, ptr(workspace, "void *"), workspace.numel(),
+                                 ptr(indptr, "int64_t *"), ptr(indices, "int32_t *"), ptr(data, "double *"), stream()))
+    return indptr, indices, data
+
+
+_WORST_CASE_BYTES = 1 << 30  # allocate num_rows * max_candidates outright below this many bytes
+
+
 def extract_csr_device(operator: ls.Operator, spins: torch.Tensor, psi: torch.Tensor,
-                       row_begin: int = 0, num_rows: Optional[int] = None, workspace: Optional[torch.Tensor] = None):
+                       row_begin: int = 0, num_rows: Optional[int] = None, workspace: Optional[torch.Tensor] = None,
+                       nnz_hint: Optional[int] = None):
     """Rows [row_begin, row_begin+num_rows) of J against the full sorted basis ``spins``.
 
     spins: int64 bit patterns, ascending (unsigned), unique, CUDA.  psi: f64 CUDA, same length.
     -> (indptr int64 [num_rows+1], indices int32 [nnz] global columns, data f64 [nnz]).
+
+    Unsymmetrised operators take the single-pass kernel (asp_extract_csr).  Its outputs are
+    sized by the caller like the reference's C contract (cbits/build_matrix.c:22-28): the worst
+    case num_rows * max_candidates when that is small, else ``nnz_hint`` (default 8 per row);
+    if the guess was short the call reports the exact count and is repeated once.
     """
     dev = require_cuda()
     n_total = int(spins.shape[0])
     if num_rows is None:
         num_rows = n_total - row_begin
     if operator.is_sorted_emitter:
-        need = int(lib().asp_extract_workspace_bytes(operator.handle, n_total, num_rows))
+        need = int(lib().asp_extract_csr_workspace_bytes(operator.handle, n_total, num_rows))
         if workspace is None or workspace.numel() < need:
             workspace = torch.empty(need, dtype=torch.uint8, device=dev)
-        nnz = ffi.new("uint64_t *")
-        check(lib().asp_extract_count(operator.handle, n_total, ptr(spins, "uint64_t *"), row_begin, num_rows,
-                                      ptr(workspace, "void *"), workspace.numel(), nnz, stream()))
+        worst = num_rows * operator.max_candidates
+        if nnz_hint is not None:
+            capacity = min(worst, int(nnz_hint))
+        elif worst * 12 <= _WORST_CASE_BYTES:
+            capacity = worst
+        else:
+            capacity = min(worst, 8 * num_rows)
         indptr = torch.empty(num_rows + 1, dtype=torch.int64, device=dev)
-        indices = torch.empty(int(nnz[0]), dtype=torch.int32, device=dev)
-        data = torch.empty(int(nnz[0]), dtype=torch.float64, device=dev)
-        check(lib().asp_extract_fill(operator.handle, n_total, ptr(spins, "uint64_t *"), ptr(psi, "double *"),
-                                     row_begin, num_rows, ptr(workspace, "void *"), workspace.numel(),
-                                     ptr(indptr, "int64_t *"), ptr(indices, "int32_t *"), ptr(data, "double *"), stream()))
-        return indptr, indices, data
+        nnz = ffi.new("uint64_t *")
+        for _ in range(2):
+            indices = torch.empty(capacity, dtype=torch.int32, device=dev)
+            data = torch.empty(capacity, dtype=torch.float64, device=dev)
+            rc = lib().asp_extract_csr(operator.handle, n_total, ptr(spins, "uint64_t *"), ptr(psi, "double *"),
+                                       row_begin, num_rows, ptr(workspace, "void *"), workspace.numel(), capacity,
+                                       ptr(indptr, "int64_t *"), ptr(indices, "int32_t *"), ptr(data, "double *"), nnz, stream())
+            if rc == lib().ASP_ERR_UNSUPPORTED:  # more distinct moves than the kernel's tag layout holds
+                return extract_csr_two_pass_device(operator, spins, psi, row_begin, num_rows)
+            if rc == lib().ASP_ERR_WORKSPACE and int(nnz[0]) > capacity:
+                capacity = int(nnz[0])  # the guess was short: exact size, second (last) attempt
+                del indices, data
+                continue
+            check(rc)
+            break
+        m = int(nnz[0])
+        if m == capacity:
+            return indptr, indices, data
+        if 2 * m < capacity:  # do not pin an oversized buffer behind a small view
+            return indptr, indices[:m].clone(), data[:m].clone()
+        return indptr, indices[:m], data[:m]
     # symmetrised / non-sorted operators: neighbour lists on the device, then the
     # explicit-candidate kernel, then canonicalisation
     rows = spins[row_begin:row_begin + num_rows]

@@ -1,31 +1,57 @@
-// HOST-buffer convenience entry points: the end-to-end path a binding without device
-// memory management uses (H2D of basis + amplitudes, extraction, D2H of the CSR).
-// Device buffers and the copy stream live in a process-wide arena that only grows, so
-// repeated calls pay no cudaMalloc/cudaFree (each costs a device synchronisation).
+// HOST-buffer entry points: the end-to-end path a binding without device memory management
+// uses (H2D of basis + amplitudes, single-pass extraction, D2H of the CSR).
+//
+//   asp_extract_host             one call, caller-sized outputs (the reference's C contract,
+//                                cbits/build_matrix.c:22-28).  The row block is cut into chunks:
+//                                while chunk c+1 is extracted, chunk c's rows are already on
+//                                their way back over PCIe (separate copy stream), so the call
+//                                costs about H2D + one chunk + D2H instead of the sum.
+//   asp_extract_host_begin/finish  two calls with exact-size outputs (begin returns nnz).
+//
+// Device buffers, streams and events live in a process-wide arena that only grows, so repeated
+// calls pay no cudaMalloc/cudaFree (each costs a device synchronisation).
 #include <mutex>
 
-#include "operator.cuh"
+#include "fused.cuh"
 
 namespace {
+
+using asp::kFusedMaxChunks;
+using asp::kFusedTileRows;
 
 struct Arena {
   std::mutex mu;
   bool busy = false;
   int device = -1;
-  cudaStream_t stream = nullptr;
+  cudaStream_t compute = nullptr, copy_in = nullptr, copy_out = nullptr;
+  cudaEvent_t ev_spins = nullptr, ev_psi = nullptr, ev_chunk[kFusedMaxChunks] = {};
+  unsigned long long *h_totals = nullptr;  // pinned + mapped: running totals written by the kernels
   struct Buf {
     void *p = nullptr;
     size_t cap = 0;
   } spins, psi, workspace, indptr, indices, data;
 
-  int reserve(Buf &b, size_t bytes) {
+  int reserve(Buf &b, size_t bytes, bool headroom = true) {
     if (bytes <= b.cap) return ASP_OK;
     if (b.p) cudaFree(b.p);
     b.p = nullptr;
     b.cap = 0;
-    const size_t want = bytes + bytes / 8 + 256;  // headroom: nnz drifts a little between calls
+    const size_t want = headroom ? bytes + bytes / 8 + 256 : bytes + 256;  // nnz drifts a little between calls
     ASP_CUDA_CHECK(cudaMalloc(&b.p, want));
     b.cap = want;
+    return ASP_OK;
+  }
+  int init(int dev) {
+    if (device == dev && compute) return ASP_OK;
+    release();
+    device = dev;
+    ASP_CUDA_CHECK(cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking));
+    ASP_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_in, cudaStreamNonBlocking));
+    ASP_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_out, cudaStreamNonBlocking));
+    ASP_CUDA_CHECK(cudaEventCreateWithFlags(&ev_spins, cudaEventDisableTiming));
+    ASP_CUDA_CHECK(cudaEventCreateWithFlags(&ev_psi, cudaEventDisableTiming));
+    for (auto &e : ev_chunk) ASP_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ASP_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void **>(&h_totals), kFusedMaxChunks * sizeof(unsigned long long), cudaHostAllocMapped));
     return ASP_OK;
   }
   void release() {
@@ -34,20 +60,57 @@ struct Arena {
       b->p = nullptr;
       b->cap = 0;
     }
-    if (stream) cudaStreamDestroy(stream);
-    stream = nullptr;
+    for (cudaStream_t *s : {&compute, &copy_in, &copy_out}) {
+      if (*s) cudaStreamDestroy(*s);
+      *s = nullptr;
+    }
+    for (cudaEvent_t *e : {&ev_spins, &ev_psi}) {
+      if (*e) cudaEventDestroy(*e);
+      *e = nullptr;
+    }
+    for (auto &e : ev_chunk) {
+      if (e) cudaEventDestroy(e);
+      e = nullptr;
+    }
+    if (h_totals) cudaFreeHost(h_totals);
+    h_totals = nullptr;
     device = -1;
   }
 };
 
 Arena g_arena;
 
+int acquire(Arena &A) {
+  std::lock_guard<std::mutex> lock(A.mu);
+  ASP_REQUIRE(!A.busy, "another host extraction is in flight (one job at a time per process)");
+  int device = 0;
+  ASP_CUDA_CHECK(cudaGetDevice(&device));
+  int rc = A.init(device);
+  if (rc != ASP_OK) return rc;
+  A.busy = true;
+  return ASP_OK;
+}
+
+void release_busy(Arena &A) {
+  std::lock_guard<std::mutex> lock(A.mu);
+  A.busy = false;
+}
+
+#define HOST_CUDA(expr)                                                      \
+  do {                                                                       \
+    cudaError_t _e = (expr);                                                 \
+    if (_e != cudaSuccess) {                                                 \
+      ::asp::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,         \
+                       cudaGetErrorString(_e));                              \
+      rc = ASP_ERR_CUDA;                                                     \
+      goto out;                                                              \
+    }                                                                        \
+  } while (0)
+
 }  // namespace
 
 struct asp_host_job {
-  const asp_operator *op = nullptr;
-  uint64_t n = 0, row_begin = 0, num_rows = 0, nnz = 0;
-  size_t workspace_bytes = 0;
+  uint64_t num_rows = 0, nnz = 0;
 };
 
 extern "C" {
@@ -57,86 +120,171 @@ void asp_host_release(void) {
   if (!g_arena.busy) g_arena.release();
 }
 
-int asp_extract_host_begin(asp_operator const *op, uint64_t n, uint64_t const *h_spins, double const *h_psi,
-                           uint64_t row_begin, uint64_t num_rows, uint64_t *h_nnz, asp_host_job **out) {
-  ASP_REQUIRE(op && h_nnz && out, "NULL argument");
+int asp_extract_host(asp_operator const *op, uint64_t n, uint64_t const *h_spins, double const *h_psi, uint64_t row_begin,
+                     uint64_t num_rows, uint64_t capacity, int64_t *h_indptr, int32_t *h_indices, double *h_data,
+                     uint64_t *h_nnz) {
+  int rc = asp::fused_check_operator(op);
+  if (rc != ASP_OK) return rc;
+  ASP_REQUIRE(h_nnz && h_indptr, "NULL argument");
   ASP_REQUIRE(n == 0 || (h_spins && h_psi), "NULL input buffer");
+  ASP_REQUIRE(capacity == 0 || (h_indices && h_data), "NULL output buffer");
+  ASP_REQUIRE(n < (1ull << 31), "int32 column indices need n_total < 2^31 (scipy picks int32 the same way)");
+  ASP_REQUIRE(row_begin + num_rows <= n, "row block exceeds the basis");
+  *h_nnz = 0;
+  if (num_rows == 0 || n == 0) {
+    h_indptr[0] = 0;
+    return ASP_OK;
+  }
+  Arena &A = g_arena;
+  rc = acquire(A);
+  if (rc != ASP_OK) return rc;
+  {
+    // row chunks: multiples of the tile, at most kFusedMaxChunks, about 2^20 rows each
+    uint64_t chunk_rows = (num_rows + 7) / 8;
+    if (chunk_rows < (1u << 17)) chunk_rows = 1u << 17;
+    chunk_rows = (chunk_rows + kFusedTileRows - 1) / kFusedTileRows * kFusedTileRows;
+    const int chunks = static_cast<int>((num_rows + chunk_rows - 1) / chunk_rows);
+    const size_t ws_bytes = asp::fused_workspace_bytes(op, n, num_rows);
+    const uint64_t worst = num_rows * op->max_candidates();
+    const uint64_t dev_capacity = std::min(capacity, worst);
+    rc = A.reserve(A.spins, (n + 1) * sizeof(uint64_t));
+    if (rc == ASP_OK) rc = A.reserve(A.psi, (n + 1) * sizeof(double));
+    if (rc == ASP_OK) rc = A.reserve(A.workspace, ws_bytes);
+    if (rc == ASP_OK) rc = A.reserve(A.indptr, (num_rows + 1) * sizeof(int64_t));
+    if (rc == ASP_OK) rc = A.reserve(A.indices, (dev_capacity + 1) * sizeof(int32_t), false);
+    if (rc == ASP_OK) rc = A.reserve(A.data, (dev_capacity + 1) * sizeof(double), false);
+    if (rc != ASP_OK) goto out;
+    auto *d_spins = static_cast<uint64_t *>(A.spins.p);
+    auto *d_psi = static_cast<double *>(A.psi.p);
+    auto *d_indptr = static_cast<int64_t *>(A.indptr.p);
+    auto *d_indices = static_cast<int32_t *>(A.indices.p);
+    auto *d_data = static_cast<double *>(A.data.p);
+    unsigned long long *d_totals = nullptr;
+    HOST_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&d_totals), A.h_totals, 0));
+
+    HOST_CUDA(cudaMemcpyAsync(d_spins, h_spins, n * sizeof(uint64_t), cudaMemcpyHostToDevice, A.copy_in));
+    HOST_CUDA(cudaEventRecord(A.ev_spins, A.copy_in));
+    HOST_CUDA(cudaMemcpyAsync(d_psi, h_psi, n * sizeof(double), cudaMemcpyHostToDevice, A.copy_in));
+    HOST_CUDA(cudaEventRecord(A.ev_psi, A.copy_in));
+    // the index only needs the basis words: it is built while the amplitudes are still in flight
+    HOST_CUDA(cudaStreamWaitEvent(A.compute, A.ev_spins, 0));
+    rc = asp::fused_prepare(op, n, d_spins, num_rows, A.workspace.p, A.workspace.cap, A.compute);
+    if (rc != ASP_OK) goto out;
+    HOST_CUDA(cudaStreamWaitEvent(A.compute, A.ev_psi, 0));
+    for (int c = 0; c < chunks; ++c) {
+      const uint64_t begin = c * chunk_rows, rows = std::min(chunk_rows, num_rows - begin);
+      rc = asp::fused_launch(op, n, d_spins, d_psi, row_begin, num_rows, c, begin, rows, A.workspace.p, dev_capacity, d_indptr,
+                             d_indices, d_data, d_totals + c, A.compute);
+      if (rc != ASP_OK) goto out;
+      HOST_CUDA(cudaEventRecord(A.ev_chunk[c], A.compute));
+    }
+    // drain: as soon as a chunk is done its rows go back while the next chunk is extracted
+    unsigned long long done = 0;
+    bool overflow = false;
+    for (int c = 0; c < chunks; ++c) {
+      HOST_CUDA(cudaEventSynchronize(A.ev_chunk[c]));
+      const unsigned long long total = *static_cast<volatile unsigned long long *>(A.h_totals + c);
+      const uint64_t begin = c * chunk_rows, rows = std::min(chunk_rows, num_rows - begin);
+      const uint64_t extra = (c == chunks - 1) ? 1 : 0;  // the closing indptr entry
+      HOST_CUDA(cudaMemcpyAsync(h_indptr + begin, d_indptr + begin, (rows + extra) * sizeof(int64_t), cudaMemcpyDeviceToHost, A.copy_out));
+      if (total > capacity) overflow = true;
+      if (!overflow && total > done) {
+        HOST_CUDA(cudaMemcpyAsync(h_indices + done, d_indices + done, (total - done) * sizeof(int32_t), cudaMemcpyDeviceToHost, A.copy_out));
+        HOST_CUDA(cudaMemcpyAsync(h_data + done, d_data + done, (total - done) * sizeof(double), cudaMemcpyDeviceToHost, A.copy_out));
+      }
+      done = total;
+    }
+    HOST_CUDA(cudaStreamSynchronize(A.copy_out));
+    *h_nnz = done;
+    if (overflow) {
+      asp::set_error("output capacity too small: %llu couplings, room for %llu (h_indptr is complete; call again with the larger capacity)",
+                     done, static_cast<unsigned long long>(capacity));
+      rc = ASP_ERR_WORKSPACE;
+    }
+  }
+out:
+  if (rc == ASP_ERR_CUDA) cudaDeviceSynchronize();  // leave no work in flight behind a failed call
+  release_busy(A);
+  return rc;
+}
+
+int asp_extract_host_begin(asp_operator const *op, uint64_t n, uint64_t const *h_spins, double const *h_psi,
+                           uint64_t row_begin, uint64_t num_rows, uint64_t *h_nnz, asp_host_job **out_job) {
+  int rc = asp::fused_check_operator(op);
+  if (rc != ASP_OK) return rc;
+  ASP_REQUIRE(h_nnz && out_job, "NULL argument");
+  ASP_REQUIRE(n == 0 || (h_spins && h_psi), "NULL input buffer");
+  ASP_REQUIRE(n < (1ull << 31), "int32 column indices need n_total < 2^31 (scipy picks int32 the same way)");
   ASP_REQUIRE(row_begin + num_rows <= n, "row block exceeds the basis");
   Arena &A = g_arena;
-  {
-    std::lock_guard<std::mutex> lock(A.mu);
-    ASP_REQUIRE(!A.busy, "another host extraction is in flight (one job at a time per process)");
-    int device = 0;
-    ASP_CUDA_CHECK(cudaGetDevice(&device));
-    if (A.device != device) {
-      A.release();
-      A.device = device;
-    }
-    if (!A.stream) ASP_CUDA_CHECK(cudaStreamCreateWithFlags(&A.stream, cudaStreamNonBlocking));
-    A.busy = true;
-  }
+  rc = acquire(A);
+  if (rc != ASP_OK) return rc;
   auto *job = new asp_host_job();
-  job->op = op;
-  job->n = n;
-  job->row_begin = row_begin;
   job->num_rows = num_rows;
-  job->workspace_bytes = asp_extract_workspace_bytes(op, n, num_rows);
-  auto fail = [&](int rc) {
-    delete job;
-    std::lock_guard<std::mutex> lock(A.mu);
-    A.busy = false;
-    return rc;
-  };
-  int rc = A.reserve(A.spins, (n + 1) * sizeof(uint64_t));
-  if (rc == ASP_OK) rc = A.reserve(A.psi, (n + 1) * sizeof(double));
-  if (rc == ASP_OK) rc = A.reserve(A.workspace, job->workspace_bytes);
-  if (rc != ASP_OK) return fail(rc);
-  cudaError_t e = cudaMemcpyAsync(A.spins.p, h_spins, n * sizeof(uint64_t), cudaMemcpyHostToDevice, A.stream);
-  // the amplitudes ride behind the count pass (same stream, consumed only by the fill)
-  if (e == cudaSuccess) e = cudaMemcpyAsync(A.psi.p, h_psi, n * sizeof(double), cudaMemcpyHostToDevice, A.stream);
-  if (e != cudaSuccess) {
-    asp::set_error("asp_extract_host_begin: %s", cudaGetErrorString(e));
-    return fail(ASP_ERR_CUDA);
+  {
+    const size_t ws_bytes = asp::fused_workspace_bytes(op, n, num_rows);
+    const uint64_t worst = num_rows * op->max_candidates();
+    rc = A.reserve(A.spins, (n + 1) * sizeof(uint64_t));
+    if (rc == ASP_OK) rc = A.reserve(A.psi, (n + 1) * sizeof(double));
+    if (rc == ASP_OK) rc = A.reserve(A.workspace, ws_bytes);
+    if (rc == ASP_OK) rc = A.reserve(A.indptr, (num_rows + 1) * sizeof(int64_t));
+    if (rc != ASP_OK) goto out;
+    HOST_CUDA(cudaMemcpyAsync(A.spins.p, h_spins, n * sizeof(uint64_t), cudaMemcpyHostToDevice, A.compute));
+    HOST_CUDA(cudaMemcpyAsync(A.psi.p, h_psi, n * sizeof(double), cudaMemcpyHostToDevice, A.compute));
+    // outputs: what the arena already holds, at least 8 couplings per row; a short guess is
+    // answered with the exact count and repeated once
+    uint64_t capacity = std::max<uint64_t>(std::min<uint64_t>(worst, 8 * num_rows), std::min(A.indices.cap / sizeof(int32_t), A.data.cap / sizeof(double)));
+    capacity = std::min(capacity, worst);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      rc = A.reserve(A.indices, (capacity + 1) * sizeof(int32_t));
+      if (rc == ASP_OK) rc = A.reserve(A.data, (capacity + 1) * sizeof(double));
+      if (rc != ASP_OK) goto out;
+      uint64_t nnz = 0;
+      rc = asp_extract_csr(op, n, static_cast<uint64_t *>(A.spins.p), static_cast<double *>(A.psi.p), row_begin, num_rows, A.workspace.p,
+                           A.workspace.cap, capacity, static_cast<int64_t *>(A.indptr.p), static_cast<int32_t *>(A.indices.p),
+                           static_cast<double *>(A.data.p), &nnz, A.compute);
+      job->nnz = nnz;
+      if (rc == ASP_ERR_WORKSPACE && nnz > capacity && attempt == 0) {
+        capacity = nnz;
+        continue;
+      }
+      break;
+    }
+    if (rc != ASP_OK) goto out;
+    *h_nnz = job->nnz;
+    *out_job = job;
+    return ASP_OK;  // the arena stays busy until asp_extract_host_finish
   }
-  rc = asp_extract_count(op, n, static_cast<uint64_t *>(A.spins.p), row_begin, num_rows, A.workspace.p, A.workspace.cap, &job->nnz, A.stream);
-  if (rc != ASP_OK) return fail(rc);
-  *h_nnz = job->nnz;
-  *out = job;
-  return ASP_OK;
+out:
+  delete job;
+  release_busy(A);
+  return rc;
 }
 
 int asp_extract_host_finish(asp_host_job *job, int64_t *h_indptr, int32_t *h_indices, double *h_data) {
   ASP_REQUIRE(job != nullptr, "job is NULL");
   Arena &A = g_arena;
-  auto done = [&](int rc) {
-    delete job;
-    std::lock_guard<std::mutex> lock(A.mu);
-    A.busy = false;
-    return rc;
-  };
+  int rc = ASP_OK;
   if (!h_indptr || (job->nnz != 0 && (!h_indices || !h_data))) {
     asp::set_error("asp_extract_host_finish: NULL output buffer");
-    return done(ASP_ERR_ARG);
+    rc = ASP_ERR_ARG;
+    goto out;
   }
-  int rc = A.reserve(A.indptr, (job->num_rows + 1) * sizeof(int64_t));
-  if (rc == ASP_OK) rc = A.reserve(A.indices, (job->nnz + 1) * sizeof(int32_t));
-  if (rc == ASP_OK) rc = A.reserve(A.data, (job->nnz + 1) * sizeof(double));
-  if (rc != ASP_OK) return done(rc);
-  rc = asp_extract_fill(job->op, job->n, static_cast<uint64_t *>(A.spins.p), static_cast<double *>(A.psi.p), job->row_begin,
-                        job->num_rows, A.workspace.p, A.workspace.cap, static_cast<int64_t *>(A.indptr.p),
-                        static_cast<int32_t *>(A.indices.p), static_cast<double *>(A.data.p), A.stream);
-  if (rc != ASP_OK) return done(rc);
-  cudaError_t e = cudaMemcpyAsync(h_indptr, A.indptr.p, (job->num_rows + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, A.stream);
-  if (e == cudaSuccess && job->nnz)
-    e = cudaMemcpyAsync(h_indices, A.indices.p, job->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, A.stream);
-  if (e == cudaSuccess && job->nnz)
-    e = cudaMemcpyAsync(h_data, A.data.p, job->nnz * sizeof(double), cudaMemcpyDeviceToHost, A.stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(A.stream);
-  if (e != cudaSuccess) {
-    asp::set_error("asp_extract_host_finish: %s", cudaGetErrorString(e));
-    return done(ASP_ERR_CUDA);
+  if (job->num_rows == 0) {
+    h_indptr[0] = 0;
+    goto out;
   }
-  return done(ASP_OK);
+  HOST_CUDA(cudaMemcpyAsync(h_indptr, A.indptr.p, (job->num_rows + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, A.compute));
+  if (job->nnz) {
+    HOST_CUDA(cudaMemcpyAsync(h_indices, A.indices.p, job->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, A.copy_out));
+    HOST_CUDA(cudaMemcpyAsync(h_data, A.data.p, job->nnz * sizeof(double), cudaMemcpyDeviceToHost, A.compute));
+  }
+  HOST_CUDA(cudaStreamSynchronize(A.compute));
+  HOST_CUDA(cudaStreamSynchronize(A.copy_out));
+out:
+  delete job;
+  release_busy(A);
+  return rc;
 }
 
 }  // extern "C"

@@ -8,8 +8,9 @@ Workload (BASELINE.json configs[3], the shape the metric is quoted on; it fits o
 heisenberg_kagome_36-shaped U(1) basis (36 spins, 72 bonds), 10^7 sampled states PER GPU
 (weak scaling: the global sorted basis has N x 10^7 states and every rank builds the CSR
 rows of its contiguous row block against the full basis), synthetic log-normal amplitudes,
-cluster-closed sampled subset (about a third of all candidates are hits).  A step is one
-pass: [N>1: all-gather of basis words + amplitudes] -> radix index -> count -> scan -> fill.
+cluster-closed sampled subset (about a tenth of all candidates are hits).  A step is one
+pass: [N>1: all-gather of basis words + amplitudes] -> bucket index -> single-pass extraction
+kernel (search once, decoupled look-back, CSR written in place).
 The annealing stage is timed separately on the same extracted model and reported under the
 "anneal" key.  One JSON line on stdout (rank 0).
 """
@@ -27,6 +28,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SYSTEM = "heisenberg_kagome_36"
+TRAFFIC_BYTES = None  # dram__bytes_read.sum + dram__bytes_write.sum of extract_csr_kernel from the ncu --set full capture (profiles/)
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
 
 
@@ -241,9 +243,15 @@ def run_ours(args):
     row_begin, num_rows = D.block(n_total, rank, world)
     my_spins = spins[row_begin:row_begin + num_rows].clone()
     my_psi = psi[row_begin:row_begin + num_rows].clone()
-    need = int(lib().asp_extract_workspace_bytes(op.handle, n_total, num_rows))
+    need = int(lib().asp_extract_csr_workspace_bytes(op.handle, n_total, num_rows))
     workspace = torch.empty(need, dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
+    # caller-sized outputs (the reference's C contract): the first pass finds the coupling count,
+    # every later pass allocates that much (+1/16 slack) and makes ONE kernel launch
+    first = common.extract_csr_device(op, spins, psi, row_begin, num_rows, workspace=workspace)
+    nnz_known = int(first[1].numel())
+    capacity = nnz_known + nnz_known // 16
+    del first
 
     def one_pass(timers=None):
         if world > 1:  # X1: the exchange step of the path
@@ -251,26 +259,22 @@ def run_ours(args):
             full_psi = D.all_gather_blocks(my_psi, n_total)
         else:
             full_spins, full_psi = spins, psi
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if timers is not None else None
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)] if timers is not None else None
+        indptr = torch.empty(num_rows + 1, dtype=torch.int64, device=dev)
+        indices = torch.empty(capacity, dtype=torch.int32, device=dev)
+        data = torch.empty(capacity, dtype=torch.float64, device=dev)
         if ev:
             ev[0].record()
         nnz = ffi.new("uint64_t *")
-        common.check(lib().asp_extract_count(op.handle, n_total, common.ptr(full_spins, "uint64_t *"), row_begin, num_rows,
-                                             common.ptr(workspace, "void *"), workspace.numel(), nnz, common.stream()))
+        common.check(lib().asp_extract_csr(op.handle, n_total, common.ptr(full_spins, "uint64_t *"), common.ptr(full_psi, "double *"),
+                                           row_begin, num_rows, common.ptr(workspace, "void *"), workspace.numel(), capacity,
+                                           common.ptr(indptr, "int64_t *"), common.ptr(indices, "int32_t *"),
+                                           common.ptr(data, "double *"), nnz, common.stream()))
         if ev:
             ev[1].record()
-        m = int(nnz[0])
-        indptr = torch.empty(num_rows + 1, dtype=torch.int64, device=dev)
-        indices = torch.empty(m, dtype=torch.int32, device=dev)
-        data = torch.empty(m, dtype=torch.float64, device=dev)
-        common.check(lib().asp_extract_fill(op.handle, n_total, common.ptr(full_spins, "uint64_t *"), common.ptr(full_psi, "double *"),
-                                            row_begin, num_rows, common.ptr(workspace, "void *"), workspace.numel(),
-                                            common.ptr(indptr, "int64_t *"), common.ptr(indices, "int32_t *"),
-                                            common.ptr(data, "double *"), common.stream()))
-        if ev:
-            ev[2].record()
             timers.append(ev)
-        return indptr, indices, data
+        m = int(nnz[0])
+        return indptr, indices[:m], data[:m]
 
     for _ in range(args.warmup):
         out = one_pass()
@@ -294,17 +298,17 @@ def run_ours(args):
     total_ms = D.max_over_ranks(start.elapsed_time(end), dev)
     launches = int(lib().asp_kernel_launch_count()) - launches0
     clocks = sampler.stop() if rank == 0 else None
-    count_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in timers]))
-    fill_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in timers]))
+    kernel_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in timers]))  # index + single-pass kernel + count read-back
     nnz_total = D.sum_over_ranks(float(nnz_mine), dev)
     candidates_mine = None
     value = nnz_total * args.steps / (total_ms * 1e-3)
     algo_bytes = 24.0 * num_rows + 20.0 * nnz_mine  # per row 24 B, per coupling 20 B
     roofline = {
-        "bound": "hbm", "kernel": "extract_sorted_kernel<fill>", "achieved": algo_bytes / (fill_ms * 1e-3) / 1e9, "peak": peak,
-        "unit": "GB/s", "frac": algo_bytes / (fill_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-        "algorithmic_bytes_per_launch": algo_bytes, "fill_ms": fill_ms, "count_scan_index_ms": count_ms,
-        "frac_whole_path": algo_bytes / ((fill_ms + count_ms) * 1e-3) / 1e9 / peak,
+        "bound": "hbm", "kernel": "extract_csr_kernel", "achieved": algo_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peak,
+        "unit": "GB/s", "frac": algo_bytes / (kernel_ms * 1e-3) / 1e9 / peak, "traffic": TRAFFIC_BYTES, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": kernel_ms,
+        "note": "CUDA events around asp_extract_csr on the launching stream: build_starts_kernel (index) + extract_csr_kernel "
+                "(single pass) + the 8-byte count read-back; algorithmic bytes = 24 B/row + 20 B/coupling (SURVEY.md 8d)",
     }
     indptr, indices, data = out
 
@@ -314,17 +318,16 @@ def run_ours(args):
         h_spins = spins.cpu().pin_memory()
         h_psi = psi.cpu().pin_memory()
         h_indptr = torch.empty(num_rows + 1, dtype=torch.int64).pin_memory()
-        h_indices = torch.empty(nnz_mine, dtype=torch.int32).pin_memory()
-        h_data = torch.empty(nnz_mine, dtype=torch.float64).pin_memory()
+        h_indices = torch.empty(capacity, dtype=torch.int32).pin_memory()
+        h_data = torch.empty(capacity, dtype=torch.float64).pin_memory()
 
         def host_pass():
             nnz = ffi.new("uint64_t *")
-            job = ffi.new("asp_host_job **")
-            common.check(lib().asp_extract_host_begin(op.handle, n_total, ffi.cast("uint64_t *", h_spins.data_ptr()),
-                                                      ffi.cast("double *", h_psi.data_ptr()), row_begin, num_rows, nnz, job))
+            common.check(lib().asp_extract_host(op.handle, n_total, ffi.cast("uint64_t *", h_spins.data_ptr()),
+                                                ffi.cast("double *", h_psi.data_ptr()), row_begin, num_rows, capacity,
+                                                ffi.cast("int64_t *", h_indptr.data_ptr()), ffi.cast("int32_t *", h_indices.data_ptr()),
+                                                ffi.cast("double *", h_data.data_ptr()), nnz))
             assert int(nnz[0]) == nnz_mine
-            common.check(lib().asp_extract_host_finish(job[0], ffi.cast("int64_t *", h_indptr.data_ptr()),
-                                                       ffi.cast("int32_t *", h_indices.data_ptr()), ffi.cast("double *", h_data.data_ptr())))
 
         e2e_steps = max(2, min(args.steps, 5))
         host_pass()
@@ -339,7 +342,7 @@ def run_ours(args):
         e2e = {"value": nnz_total * e2e_steps / e2e_s, "unit": "couplings/s",
                "h2d_bytes_per_step": int(n_total * 16), "d2h_bytes_per_step": int((num_rows + 1) * 8 + nnz_mine * 12),
                "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
-               "api": "asp_extract_host_begin/finish (include/asp_b200.h), pinned host buffers"}
+               "api": "asp_extract_host (include/asp_b200.h), pinned host buffers, row chunks copied back while the next chunk is extracted"}
         del h_spins, h_psi, h_indptr, h_indices, h_data
 
     # ---- annealing stage on the extracted model (replicas shard over ranks) ------------------

@@ -127,6 +127,24 @@ int asp_extract_fill(asp_operator const *op, uint64_t n_total, uint64_t const *d
                      void *d_workspace, size_t workspace_bytes, int64_t *d_indptr,
                      int32_t *d_indices, double *d_data, void *stream);
 
+/* Single pass (the fast path): index + generate + search + couplings + CSR in one kernel;
+ * every candidate is searched once and a tile of rows obtains its CSR offset by decoupled
+ * look-back.  Like the reference's C contract (cbits/build_matrix.c:22-28: outputs sized by
+ * the caller to a worst case) the caller passes the room of d_indices/d_data in `capacity`
+ * (entries); an upper bound is num_rows * asp_operator_max_candidates(op).  d_indptr
+ * [num_rows+1] is always complete.  h_nnz != NULL: synchronises, *h_nnz = couplings; when
+ * that exceeds `capacity` nothing past the capacity was written and ASP_ERR_WORKSPACE is
+ * returned (call again with the larger capacity).  h_nnz == NULL: no synchronisation, the
+ * count is d_indptr[num_rows]. */
+size_t asp_extract_csr_workspace_bytes(asp_operator const *op, uint64_t n_total, uint64_t num_rows);
+int asp_extract_csr(asp_operator const *op, uint64_t n_total, uint64_t const *d_spins,
+                    double const *d_psi, uint64_t row_begin, uint64_t num_rows, void *d_workspace,
+                    size_t workspace_bytes, uint64_t capacity, int64_t *d_indptr,
+                    int32_t *d_indices, double *d_data, uint64_t *h_nnz, void *stream);
+/* Test hook: hit-list entries per warp of the single-pass kernel (0 = automatic). Small values
+ * force its lane-per-row fallback. */
+void asp_debug_set_hit_list_capacity(int entries_per_warp);
+
 /* Canonical CSR of generation-order rows (raw output of asp_build_matrix_dev): inside each
  * row a stable sort by column, duplicates summed in generation order -- what scipy's
  * csr_matrix + sort_indices yield at common.py:193-195.  max_row_len: upper bound on raw
@@ -141,8 +159,16 @@ int asp_csr_canonicalize(uint64_t num_rows, uint32_t max_row_len, int64_t const 
 int asp_csr_symmetrize(uint64_t n, int64_t const *d_indptr, int32_t const *d_indices,
                        double *d_data, uint64_t *h_asymmetric, void *stream);
 
-/* HOST-buffer convenience (the end-to-end path) for rows [row_begin, row_begin+num_rows):
- * begin = H2D of the full basis + index + count (returns nnz), finish = fill + D2H into
+/* HOST-buffer entry points (the end-to-end path) for rows [row_begin, row_begin+num_rows).
+ * One call, caller-sized outputs (`capacity` entries of h_indices/h_data, as in
+ * cbits/build_matrix.c:22-28): H2D of the full basis, single-pass extraction in row chunks,
+ * each chunk's rows copied back while the next chunk is extracted.  *h_nnz = couplings;
+ * ASP_ERR_WORKSPACE when that exceeds `capacity` (h_indptr is complete, call again).
+ * Pinned host buffers make the copies asynchronous. */
+int asp_extract_host(asp_operator const *op, uint64_t n_total, uint64_t const *h_spins,
+                     double const *h_psi, uint64_t row_begin, uint64_t num_rows, uint64_t capacity,
+                     int64_t *h_indptr, int32_t *h_indices, double *h_data, uint64_t *h_nnz);
+/* Two calls, exact-size outputs: begin = H2D + extraction (returns nnz), finish = D2H into
  * caller buffers (h_indptr[num_rows+1], h_indices/h_data[nnz]), then frees the job. */
 int asp_extract_host_begin(asp_operator const *op, uint64_t n_total, uint64_t const *h_spins,
                            double const *h_psi, uint64_t row_begin, uint64_t num_rows,

@@ -317,3 +317,97 @@ def test_host_buffer_entry_points_match_device_path():
     assert rc == 0
     assert np.array_equal(hp, indptr.cpu().numpy()) and np.array_equal(hi, indices.cpu().numpy())
     assert np.array_equal(hd, data.cpu().numpy())
+
+
+def _u1_operator(system):
+    cfg = asp.ls.load_config(asp.ls.system_path(system))
+    cfg["basis"]["symmetries"], cfg["basis"]["spin_inversion"] = [], None
+    return asp.ls.Operator.load_from_yaml(cfg["hamiltonian"], asp.ls.SpinBasis.load_from_yaml(cfg["basis"]))
+
+
+@pytest.mark.parametrize("system,n,seed", [
+    ("j1j2_square_4x4", 12870, 0), ("sk_16_1", 4000, 1), ("heisenberg_kagome_36", 300000, 2), ("sk_32_1", 30000, 3),
+    ("heisenberg_kagome_16", 1, 4), ("heisenberg_kagome_16", 127, 5), ("heisenberg_kagome_16", 129, 6),
+])
+def test_single_pass_kernel_equals_two_pass_bitwise(system, n, seed):
+    """asp_extract_csr (single pass, decoupled look-back, compacted searches) against
+    asp_extract_count/fill (lane per row, two passes): identical indptr, indices AND values, for
+    sparse subsets, a full basis (every candidate hits) and partial tiles."""
+    op = _u1_operator(system)
+    spins = synthetic.cluster_closed_states(op, n, seed, DEV)
+    psi = synthetic.synthetic_amplitudes(spins.shape[0], seed, device=DEV)
+    ref = common.extract_csr_two_pass_device(op, spins, psi)
+    for cap in (0, 96, 160):  # automatic hit list; tiny lists force the lane-per-row fallback
+        lib().asp_debug_set_hit_list_capacity(cap)
+        try:
+            got = common.extract_csr_device(op, spins, psi)
+        finally:
+            lib().asp_debug_set_hit_list_capacity(0)
+        for a, b in zip(got, ref):
+            assert torch.equal(a, b), (system, cap)
+    # row blocks (what each GPU of a sharded run builds)
+    m = spins.shape[0]
+    lo, hi = m // 3, m - m // 5
+    part = common.extract_csr_device(op, spins, psi, lo, hi - lo)
+    base = int(ref[0][lo])
+    assert torch.equal(part[0], ref[0][lo:hi + 1] - base)
+    assert torch.equal(part[1], ref[1][base:int(ref[0][hi])]) and torch.equal(part[2], ref[2][base:int(ref[0][hi])])
+
+
+def test_single_pass_capacity_contract():
+    """Caller-sized outputs (cbits/build_matrix.c:22-28 convention): a short guess reports the
+    exact count with ASP_ERR_WORKSPACE and complete indptr; the retry succeeds."""
+    op = _u1_operator("heisenberg_kagome_36")
+    spins = synthetic.cluster_closed_states(op, 50000, 8, DEV)
+    psi = synthetic.synthetic_amplitudes(spins.shape[0], 8, device=DEV)
+    n = spins.shape[0]
+    ref = common.extract_csr_two_pass_device(op, spins, psi)
+    nnz_true = int(ref[1].numel())
+    got = common.extract_csr_device(op, spins, psi, nnz_hint=nnz_true // 3)  # forces the retry
+    for a, b in zip(got, ref):
+        assert torch.equal(a, b)
+    ws = torch.empty(int(lib().asp_extract_csr_workspace_bytes(op.handle, n, n)), dtype=torch.uint8, device=DEV)
+    indptr = torch.empty(n + 1, dtype=torch.int64, device=DEV)
+    small = nnz_true // 2
+    indices = torch.full((small + 16,), -7, dtype=torch.int32, device=DEV)
+    data = torch.zeros(small + 16, dtype=torch.float64, device=DEV)
+    nnz = ffi.new("uint64_t *")
+    rc = lib().asp_extract_csr(op.handle, n, common.ptr(spins, "uint64_t *"), common.ptr(psi, "double *"), 0, n,
+                               common.ptr(ws, "void *"), ws.numel(), small, common.ptr(indptr, "int64_t *"),
+                               common.ptr(indices, "int32_t *"), common.ptr(data, "double *"), nnz, common.stream())
+    assert rc == lib().ASP_ERR_WORKSPACE and int(nnz[0]) == nnz_true
+    assert torch.equal(indptr, ref[0])
+    assert torch.equal(indices[:small], ref[1][:small]) and bool((indices[small:] == -7).all())  # nothing past the capacity
+    rc = lib().asp_extract_csr(op.handle, n, common.ptr(spins, "uint64_t *"), common.ptr(psi, "double *"), 0, n,
+                               common.ptr(ws, "void *"), 10, small, common.ptr(indptr, "int64_t *"),
+                               common.ptr(indices, "int32_t *"), common.ptr(data, "double *"), nnz, common.stream())
+    assert rc == lib().ASP_ERR_WORKSPACE
+
+
+def test_one_call_host_pipeline_with_row_chunks():
+    """asp_extract_host: several row chunks (> 2^17 rows each), D2H overlapped with extraction;
+    equal to the device path, for the whole basis and for a row block; capacity contract."""
+    op = _u1_operator("heisenberg_kagome_36")
+    spins = synthetic.cluster_closed_states(op, 400000, 13, DEV)
+    psi = synthetic.synthetic_amplitudes(spins.shape[0], 13, device=DEV)
+    n = spins.shape[0]
+    h_spins = spins.cpu().numpy().view(np.uint64)
+    h_psi = psi.cpu().numpy()
+    for lo, rows in [(0, n), (n // 7, n - n // 3)]:
+        indptr, indices, data = common.extract_csr_device(op, spins, psi, lo, rows)
+        m = int(indices.numel())
+        cap = m + 100
+        hp = np.full(rows + 1, -1, dtype=np.int64)
+        hi = np.full(cap, -1, dtype=np.int32)
+        hd = np.zeros(cap, dtype=np.float64)
+        nnz = ffi.new("uint64_t *")
+        c = lambda a, t: ffi.cast(t, a.ctypes.data)  # noqa: E731
+        rc = lib().asp_extract_host(op.handle, n, c(h_spins, "uint64_t *"), c(h_psi, "double *"), lo, rows, cap,
+                                    c(hp, "int64_t *"), c(hi, "int32_t *"), c(hd, "double *"), nnz)
+        assert rc == 0 and int(nnz[0]) == m
+        assert np.array_equal(hp, indptr.cpu().numpy())
+        assert np.array_equal(hi[:m], indices.cpu().numpy()) and np.array_equal(hd[:m], data.cpu().numpy())
+        assert np.all(hi[m:] == -1)
+        rc = lib().asp_extract_host(op.handle, n, c(h_spins, "uint64_t *"), c(h_psi, "double *"), lo, rows, m // 2,
+                                    c(hp, "int64_t *"), c(hi, "int32_t *"), c(hd, "double *"), nnz)
+        assert rc == lib().ASP_ERR_WORKSPACE and int(nnz[0]) == m and np.array_equal(hp, indptr.cpu().numpy())
