@@ -7,29 +7,36 @@
 //   _make_ising_model_compute_elements             (common.py:71-82)
 //   csr_matrix(...) + sort_indices                 (common.py:193-195)
 //
-// Differences from the two-pass kernels of extract.cu (kept for the count/fill API):
-//   * every candidate is searched ONCE.  A tile (128 rows) keeps its hits in shared memory,
-//     publishes its coupling count and obtains its CSR offset by decoupled look-back over
-//     earlier tiles (tiles are handed out by an atomic ticket, so a tile only ever waits for
-//     tiles that are already running), then writes indptr / indices / data in place;
-//   * searches run on full warps: a warp walks the delta-sorted move list for its 32 rows,
-//     pushes the (row, move) pairs that apply into a FIFO and pops 64 of them at a time, two
-//     per lane with interleaved load chains.  The FIFO is move-major, so hits are discovered
-//     in ascending column order per row and get their in-row rank on the fly;
-//   * the radix index is a 4-byte first-position table with about one key per bucket: most
-//     misses are decided by two adjacent table reads without touching the keys.
-// Positions are exact indices into the sorted basis (bit-exact CSR), values are
+// The path is bound by instruction issue, not by HBM: ~37 candidates are
+// generated and looked up per row and only a tenth of them are couplings.  The kernel therefore
+// spends its instructions where the candidates are:
+//   A. applicability of all moves for the 32 rows of a warp is computed on bit planes (the
+//      32 x N key matrix transposed with warp shuffles): one LOP3 decides a move for 32 rows;
+//      transposed back, every lane holds the bit mask of the moves that apply to ITS row;
+//   B. every lane walks its own mask (all 32 lanes busy) and pre-sieves each candidate in an
+//      order-preserving blocked Bloom filter (one 8-byte word per candidate, two hashed bits:
+//      ~2 % false positives) -- nine misses in ten end here, after ~25 instructions;
+//   C. survivors are re-dealt evenly over the lanes, searched exactly (4-byte first-position
+//      table over the top key bits + a short scan of the keys) and appended, with their in-row
+//      rank, to the warp's hit list (global scratch, L2-resident);
+//   D. a tile (256 rows) publishes its coupling count, obtains its CSR offset by decoupled
+//      look-back over earlier tiles (tiles are handed out by an atomic ticket, so a tile only
+//      waits for tiles that already run) and writes indptr / indices / data in place.
+// Every lane enumerates its moves in ascending key-delta order, so hits get ascending columns;
+// positions are exact indices into the sorted basis (bit-exact CSR) and values are
 // coef * (|psi_i| * |psi_j|) exactly as in extract.cu.
 #include "fused.cuh"
 
 namespace asp {
 
-constexpr int kFxWarps = 4;
+constexpr int kFxWarps = 8;
 constexpr int kFxThreads = kFxWarps * 32;
 constexpr int kFxTileRows = kFxThreads;
 static_assert(kFxTileRows == kFusedTileRows, "fused.cuh out of sync");
-constexpr int kFxQueue = 128;  // FIFO slots per warp (power of two, > 64 + 32 + 31)
-constexpr uint32_t kFxMaxMoves = 2046;  // tag layout: move 11 bits in the FIFO / 16 bits in the hit list
+constexpr uint32_t kFxMaxMoves = 2046;  // tag layout: move 11 bits | row lane 5 bits | in-row rank 12 bits
+constexpr int kFxSurvSlotsDefault = 16; // survivor slots per lane between two exact-search rounds
+constexpr int kFxMaxCtasPerSM = 8;
+constexpr size_t kFxScratchBudget = 512ull << 20;  // hit-list scratch never exceeds this
 
 constexpr unsigned long long kFlagAggregate = 1ull << 62;
 constexpr unsigned long long kFlagPrefix = 2ull << 62;
@@ -37,17 +44,22 @@ constexpr unsigned long long kValueMask = (1ull << 62) - 1;
 
 struct FusedArgs {
   const uint64_t *spins;   // [n_total] ascending, unique
-  const uint32_t *starts;  // [num_buckets + 1] first position with key >= bucket << shift
-  uint64_t num_buckets;
-  int shift;
-  uint32_t n_total;
   const double *psi;
+  const uint32_t *starts;  // [2^tbits + 1] first position with key >= bucket << tshift
+  int tshift;
+  const uint2 *filter;     // [2^fbits] blocked Bloom filter, word = key >> fshift
+  int fshift;
+  uint64_t state_mask;     // keys with bits outside are never candidates
+  uint32_t n_total;
   uint64_t row_begin, num_rows, num_tiles;
   const Move *moves;
-  int n_moves, n_down;
+  int n_moves, n_down, n_words;
   const DiagBond *diag;
   int n_diag;
-  int list_cap;  // hit-list entries per warp
+  int surv_slots;          // survivor slots per lane
+  int planes_ok;           // every move mask has exactly two bits: stage A on bit planes
+  uint2 *scratch;          // [gridDim.x * kFxWarps][scratch_per_warp] hit lists {position, tag}
+  uint32_t scratch_per_warp;
   unsigned long long *status;  // [num_tiles] look-back words (zeroed)
   unsigned int *ticket;        // zeroed
   uint64_t capacity;           // entries the caller's indices/data can hold
@@ -68,71 +80,41 @@ __device__ __forceinline__ void st_status(unsigned long long *p, unsigned long l
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(256) build_starts_kernel(const uint64_t *__restrict__ spins, uint32_t n, int shift, uint64_t num_buckets, uint32_t *__restrict__ starts) {
+// Two hashed bit positions (5 bits each) of a key inside its filter word.
+__device__ __forceinline__ uint32_t filter_hash(uint64_t key) {
+  return (static_cast<uint32_t>(key) + static_cast<uint32_t>(key >> 32) * 0x85EBCA6Bu) * 0x9E3779B1u;
+}
+
+// Index of the sorted basis: first-position table + Bloom filter, one thread per key.
+__global__ void __launch_bounds__(256) build_index_kernel(const uint64_t *__restrict__ spins, uint32_t n, uint64_t state_mask, int tshift,
+                                                          uint64_t num_buckets, uint32_t *__restrict__ starts, int fshift,
+                                                          uint2 *__restrict__ filter) {
   const uint32_t i = blockIdx.x * 256u + threadIdx.x;
   if (i >= n) return;
   const uint64_t last = num_buckets;  // keys wider than the operator's word sort after every bucket
-  uint64_t b = spins[i] >> shift;
-  if (b > last) b = last;
+  const uint64_t key = spins[i];
+  uint64_t b = (key & ~state_mask) ? last : key >> tshift;
   uint64_t prev = 0;  // first bucket this thread fills
   if (i > 0) {
-    uint64_t pb = spins[i - 1] >> shift;
-    if (pb > last) pb = last;
-    prev = pb + 1;
+    const uint64_t pk = spins[i - 1];
+    prev = ((pk & ~state_mask) ? last : pk >> tshift) + 1;
   }
   for (uint64_t k = prev; k <= b && k <= last; ++k) starts[k] = i;
   if (i == n - 1)
     for (uint64_t k = b + 1; k <= last; ++k) starts[k] = n;
-}
-
-// Joint search of two candidates (independent load chains interleaved): position of cX in
-// keys[loX, hiX) or -1.  Keys ascend inside a bucket.
-__device__ __forceinline__ void search_two(const uint64_t *__restrict__ keys, uint64_t cA, uint32_t loA, uint32_t hiA, uint64_t cB, uint32_t loB,
-                                           uint32_t hiB, int32_t &posA, int32_t &posB) {
-  while (hiA - loA > 8) {  // pathological bucket: bisect down to a short scan
-    const uint32_t mid = loA + ((hiA - loA) >> 1);
-    if (__ldg(&keys[mid]) < cA)
-      loA = mid + 1;
-    else
-      hiA = mid + 1;
-  }
-  while (hiB - loB > 8) {
-    const uint32_t mid = loB + ((hiB - loB) >> 1);
-    if (__ldg(&keys[mid]) < cB)
-      loB = mid + 1;
-    else
-      hiB = mid + 1;
-  }
-  posA = -1;
-  posB = -1;
-  bool actA = loA < hiA, actB = loB < hiB;
-  while (actA | actB) {
-    const uint64_t kA = actA ? __ldg(&keys[loA]) : 0ull;
-    const uint64_t kB = actB ? __ldg(&keys[loB]) : 0ull;
-    if (actA) {
-      if (kA >= cA) {
-        if (kA == cA) posA = static_cast<int32_t>(loA);
-        actA = false;
-      } else if (++loA >= hiA) {
-        actA = false;
-      }
-    }
-    if (actB) {
-      if (kB >= cB) {
-        if (kB == cB) posB = static_cast<int32_t>(loB);
-        actB = false;
-      } else if (++loB >= hiB) {
-        actB = false;
-      }
-    }
+  if ((key & ~state_mask) == 0) {
+    const uint32_t h = filter_hash(key);
+    uint2 *w = filter + (key >> fshift);
+    atomicOr(&w->x, 1u << (h >> 27));
+    atomicOr(&w->y, 1u << ((h >> 22) & 31u));
   }
 }
 
+// Position of c (< 2^number_spins) in the sorted basis, or -1.
 __device__ __forceinline__ int32_t search_one(const FusedArgs &a, uint64_t c) {
-  const uint64_t b = c >> a.shift;
-  if (b >= a.num_buckets) return -1;
+  const uint64_t b = c >> a.tshift;
   uint32_t lo = __ldg(&a.starts[b]), hi = __ldg(&a.starts[b + 1]);
-  while (hi - lo > 8) {
+  while (hi - lo > 8) {  // pathological bucket: bisect down to a short scan
     const uint32_t mid = lo + ((hi - lo) >> 1);
     if (__ldg(&a.spins[mid]) < c)
       lo = mid + 1;
@@ -146,37 +128,66 @@ __device__ __forceinline__ int32_t search_one(const FusedArgs &a, uint64_t c) {
   return -1;
 }
 
+// 32 x 32 bit-matrix transpose across a warp: result bit k of lane l = bit l of lane k's x.
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, uint32_t lane) {
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+    const uint32_t low = d == 16 ? 0x0000FFFFu : d == 8 ? 0x00FF00FFu : d == 4 ? 0x0F0F0F0Fu : d == 2 ? 0x33333333u : 0x55555555u;
+    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, d);
+    x = (lane & d) ? ((x & ~low) | ((y >> d) & low)) : ((x & low) | ((y << d) & ~low));
+  }
+  return x;
+}
+
+// Diagonal matrix element of one basis word: bond contributions summed in (term, bond) order.
+__device__ __forceinline__ double diagonal_element(uint64_t s, const DiagBond *s_diag, int n_diag) {
+  double d = 0.0;
+  for (int k = 0; k < n_diag; ++k) {
+    const DiagBond &db = s_diag[k];
+    const int idx = static_cast<int>(((s >> db.i) & 1) * 2 + ((s >> db.j) & 1));
+    d += db.d[idx];
+  }
+  return d;
+}
+
 // Per-warp shared-memory state.
 struct WarpSmem {
-  uint32_t *list_pos;  // [list_cap]
-  uint32_t *list_tag;  // [list_cap]  move | row lane << 16 | in-row rank << 21
-  uint16_t *queue;     // [kFxQueue]  move << 5 | row lane
-  uint32_t *cnt;       // [32] couplings found so far per row
-  double *abs_psi;     // [32]
-  uint32_t *row_off;   // [32] row start relative to the tile's first coupling
+  uint32_t *planes;   // [64] bit planes of the 32 keys
+  uint32_t *amask;    // [n_words][32] moves that apply, per lane
+  uint16_t *surv;     // [surv_slots][32] moves whose candidate passed the filter, per lane
+  uint32_t *pre;      // [33] exclusive prefix of survivor counts
+  uint32_t *cnt;      // [32] couplings found so far per row | those below the diagonal << 16
+  uint32_t *row_off;  // [32] row start relative to the tile's first coupling
+  double *abs_psi;    // [32]
 };
+
+__host__ __device__ inline size_t fx_per_warp_bytes(int n_words, int surv_slots) {
+  return 32 * 8 + 64 * 4 + static_cast<size_t>(n_words) * 128 + 36 * 4 + 32 * 4 + 32 * 4 + static_cast<size_t>(surv_slots) * 64;
+}
 
 __global__ void __launch_bounds__(kFxThreads) extract_csr_kernel(const FusedArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // ---- shared memory carve-up: move table (SoA), diagonal table, per-warp state ------------
-  uint64_t *s_mask = reinterpret_cast<uint64_t *>(smem_raw);
-  uint64_t *s_need = s_mask + a.n_moves;
-  uint64_t *s_flip = s_need + a.n_moves;
+  // ---- shared memory carve-up: move tables (SoA), diagonal table, per-warp state ------------
+  uint64_t *s_flip = reinterpret_cast<uint64_t *>(smem_raw);
   double *s_coef = reinterpret_cast<double *>(s_flip + a.n_moves);
-  DiagBond *s_diag = reinterpret_cast<DiagBond *>(s_coef + a.n_moves);
-  unsigned char *cursor = reinterpret_cast<unsigned char *>(s_diag + a.n_diag);
+  uint64_t *s_mask = reinterpret_cast<uint64_t *>(s_coef + a.n_moves);
+  uint64_t *s_need = s_mask + a.n_moves;
+  DiagBond *s_diag = reinterpret_cast<DiagBond *>(s_need + a.n_moves);
+  uint32_t *s_desc = reinterpret_cast<uint32_t *>(s_diag + a.n_diag);  // [n_words * 32] site i | site j << 8 | need_i << 16 | need_j << 17 | valid << 18
+  unsigned char *cursor = reinterpret_cast<unsigned char *>(s_desc + a.n_words * 32);
+  cursor = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(cursor) + 15) & ~static_cast<uintptr_t>(15));
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
   WarpSmem ws;
   {
-    const size_t per_warp = static_cast<size_t>(a.list_cap) * 8 + kFxQueue * 2 + 32 * 4 + 32 * 8 + 32 * 4;
-    unsigned char *base = cursor + per_warp * warp;
+    unsigned char *base = cursor + fx_per_warp_bytes(a.n_words, a.surv_slots) * warp;
     ws.abs_psi = reinterpret_cast<double *>(base);
-    ws.list_pos = reinterpret_cast<uint32_t *>(base + 32 * 8);
-    ws.list_tag = ws.list_pos + a.list_cap;
-    ws.cnt = ws.list_tag + a.list_cap;
+    ws.planes = reinterpret_cast<uint32_t *>(base + 32 * 8);
+    ws.amask = ws.planes + 64;
+    ws.pre = ws.amask + a.n_words * 32;
+    ws.cnt = ws.pre + 36;
     ws.row_off = ws.cnt + 32;
-    ws.queue = reinterpret_cast<uint16_t *>(ws.row_off + 32);
+    ws.surv = reinterpret_cast<uint16_t *>(ws.row_off + 32);
   }
   __shared__ unsigned int s_tile;
   __shared__ unsigned int s_warp_total[kFxWarps];
@@ -184,12 +195,25 @@ __global__ void __launch_bounds__(kFxThreads) extract_csr_kernel(const FusedArgs
 
   for (int k = threadIdx.x; k < a.n_moves; k += kFxThreads) {
     const Move mv = a.moves[k];
-    s_mask[k] = mv.mask;
-    s_need[k] = mv.need;
     s_flip[k] = mv.flip;
     s_coef[k] = mv.coef;
+    s_mask[k] = mv.mask;
+    s_need[k] = mv.need;
+  }
+  for (int k = threadIdx.x; k < a.n_words * 32; k += kFxThreads) {
+    uint32_t desc = 0;
+    if (k < a.n_moves) {
+      const Move mv = a.moves[k];
+      const int i = __ffsll(static_cast<long long>(mv.mask)) - 1;
+      const int j = 63 - __clzll(static_cast<long long>(mv.mask));
+      desc = static_cast<uint32_t>(i) | (static_cast<uint32_t>(j) << 8) | (static_cast<uint32_t>((mv.need >> i) & 1) << 16) |
+             (static_cast<uint32_t>((mv.need >> j) & 1) << 17) | (1u << 18);
+    }
+    s_desc[k] = desc;
   }
   for (int k = threadIdx.x; k < a.n_diag; k += kFxThreads) s_diag[k] = a.diag[k];
+  uint2 *const my_list = a.scratch + (static_cast<size_t>(blockIdx.x) * kFxWarps + warp) * a.scratch_per_warp;
+  const uint32_t slots = static_cast<uint32_t>(a.surv_slots);
 
   for (;;) {
     __syncthreads();  // previous tile fully written; tables loaded
@@ -203,110 +227,114 @@ __global__ void __launch_bounds__(kFxThreads) extract_csr_kernel(const FusedArgs
     const uint64_t row = a.row_begin + r;
     const uint64_t s = live ? a.spins[row] : 0ull;
     const uint32_t s_lo = static_cast<uint32_t>(s), s_hi = static_cast<uint32_t>(s >> 32);
+    const bool generates = live && (s & ~a.state_mask) == 0;  // keys wider than the word have no images in the basis
 
-    // =========================== phase 1: generate, compact, search ==========================
+    // =========================== A: which moves apply to which row ===========================
+    if (a.planes_ok) {
+      const uint32_t gen_mask = __ballot_sync(0xffffffffu, generates);
+      ws.planes[lane] = transpose32(s_lo, lane);
+      ws.planes[32 + lane] = transpose32(s_hi, lane);
+      __syncwarp();
+      for (int w = 0; w < a.n_words; ++w) {
+        const uint32_t desc = s_desc[w * 32 + lane];
+        const uint32_t pi = ws.planes[desc & 63u], pj = ws.planes[(desc >> 8) & 63u];
+        const uint32_t xi = ((desc >> 16) & 1u) - 1u, xj = ((desc >> 17) & 1u) - 1u;  // need 1 -> 0, need 0 -> ~0
+        uint32_t app = (pi ^ xi) & (pj ^ xj) & gen_mask;                              // rows this lane's move applies to
+        if (!(desc & (1u << 18))) app = 0;
+        ws.amask[w * 32 + lane] = transpose32(app, lane);                             // moves that apply to this lane's row
+      }
+    } else {
+      for (int w = 0; w < a.n_words; ++w) {
+        uint32_t bits = 0;
+        const int m_end = min(32, a.n_moves - w * 32);
+        for (int k = 0; k < m_end; ++k)
+          if ((s & s_mask[w * 32 + k]) == s_need[w * 32 + k]) bits |= 1u << k;
+        ws.amask[w * 32 + lane] = generates ? bits : 0u;
+      }
+    }
     ws.cnt[lane] = 0;
-    uint32_t list_count = 0;  // warp-uniform
-    uint32_t qhead = 0, qcount = 0;
-    int overflow_from = a.n_moves;  // first move handled by the lane-per-row fallback
-    uint32_t down_cnt = 0;
     __syncwarp();
 
-    // pops `nb` (<= 64) FIFO entries: lane handles entries lane and lane + 32
-    auto process = [&](uint32_t nb) {
-      const bool vA = lane < nb, vB = lane + 32 < nb;
-      const uint32_t tagA = ws.queue[(qhead + lane) & (kFxQueue - 1)];
-      const uint32_t tagB = ws.queue[(qhead + 32 + lane) & (kFxQueue - 1)];
-      const uint32_t srcA = tagA & 31u, srcB = tagB & 31u;
-      const uint32_t mA = vA ? (tagA >> 5) : 0u, mB = vB ? (tagB >> 5) : 0u;
-      const uint64_t sA = (static_cast<uint64_t>(__shfl_sync(0xffffffffu, s_hi, srcA)) << 32) | __shfl_sync(0xffffffffu, s_lo, srcA);
-      const uint64_t sB = (static_cast<uint64_t>(__shfl_sync(0xffffffffu, s_hi, srcB)) << 32) | __shfl_sync(0xffffffffu, s_lo, srcB);
-      const uint64_t cA = sA ^ s_flip[mA], cB = sB ^ s_flip[mB];
-      const uint64_t bA = cA >> a.shift, bB = cB >> a.shift;
-      uint32_t loA = 0, hiA = 0, loB = 0, hiB = 0;
-      if (vA && bA < a.num_buckets) {
-        loA = __ldg(&a.starts[bA]);
-        hiA = __ldg(&a.starts[bA + 1]);
-      }
-      if (vB && bB < a.num_buckets) {
-        loB = __ldg(&a.starts[bB]);
-        hiB = __ldg(&a.starts[bB + 1]);
-      }
-      int32_t posA, posB;
-      search_two(a.spins, cA, loA, hiA, cB, loB, hiB, posA, posB);
-      // record hits: A entries precede B entries in FIFO (= move-major) order
+    // =========================== B + C: sieve, search, record ================================
+    uint32_t list_count = 0;  // warp-uniform
+    uint32_t h = 0;           // survivors waiting in this lane's slots
+
+    // C: deal the waiting survivors evenly over the lanes, search them exactly, record the hits
+    auto flush = [&]() {
+      uint32_t incl = h;
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int32_t pos = half ? posB : posA;
-        const uint32_t src = half ? srcB : srcA, m = half ? mB : mA;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+      ws.pre[lane] = incl - h;
+      if (lane == 31) ws.pre[32] = total;
+      __syncwarp();
+      for (uint32_t base = 0; base < total; base += 32) {
+        const uint32_t e = base + lane;
+        const bool valid = e < total;
+        uint32_t src = 0;  // last lane whose first survivor is at or before e
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1)
+          if (ws.pre[src + step] <= e) src += step;
+        const uint32_t m = valid ? ws.surv[(e - ws.pre[src]) * 32 + src] : 0u;
+        const uint64_t s_src = (static_cast<uint64_t>(__shfl_sync(0xffffffffu, s_hi, src)) << 32) | __shfl_sync(0xffffffffu, s_lo, src);
+        int32_t pos = -1;
+        if (valid) pos = search_one(a, s_src ^ s_flip[m]);
         const bool hit = pos >= 0;
         const uint32_t hits = __ballot_sync(0xffffffffu, hit);
-        if (hits == 0) continue;
-        if (hit) {
-          const uint32_t peers = __match_any_sync(hits, src);  // hits of the same row in this half-batch
-          const uint32_t base = ws.cnt[src];
-          __syncwarp(hits);
-          if ((peers & lt_mask) == 0) ws.cnt[src] = base + __popc(peers);
-          const uint32_t slot = list_count + __popc(hits & lt_mask);
-          ws.list_pos[slot] = static_cast<uint32_t>(pos);
-          ws.list_tag[slot] = m | (src << 16) | ((base + __popc(peers & lt_mask)) << 21);
+        if (hits) {
+          const bool below = static_cast<int>(m) < a.n_down;
+          const uint32_t belows = __ballot_sync(0xffffffffu, hit && below);
+          if (hit) {
+            const uint32_t peers = __match_any_sync(hits, src);  // hits of the same row in this batch (ascending move order by lane)
+            const uint32_t packed = ws.cnt[src];
+            __syncwarp(hits);
+            const uint32_t before = __popc(peers & lt_mask);
+            if (before == 0) ws.cnt[src] = packed + __popc(peers) + (__popc(peers & belows) << 16);
+            const uint32_t rank = (packed & 0xFFFFu) + before + (below ? 0u : 1u);  // the diagonal sits after the negative deltas
+            my_list[list_count + __popc(hits & lt_mask)] = make_uint2(static_cast<uint32_t>(pos), m | (src << 11) | (rank << 16));
+          }
+          list_count += __popc(hits);
         }
-        list_count += __popc(hits);
         __syncwarp();
       }
-      qhead += nb;
-      qcount -= nb;
+      h = 0;
     };
 
-    for (int m = 0; m < a.n_moves; ++m) {
-      if (list_count + qcount + 32 > static_cast<uint32_t>(a.list_cap)) {  // hit list may not take this move
-        overflow_from = m;
-        break;
-      }
-      if (m == a.n_down) {  // the diagonal sits between the negative and the positive deltas
-        while (qcount > 0) {
+    {
+      int w = 0;
+      uint32_t cur = a.n_words ? ws.amask[lane] : 0u;
+      for (;;) {
+        while (cur == 0 && w + 1 < a.n_words) cur = ws.amask[++w * 32 + lane];
+        const bool act = cur != 0;
+        if (!__any_sync(0xffffffffu, act)) break;
+        if (act) {
+          const uint32_t bit = __ffs(cur) - 1;
+          cur &= cur - 1;
+          const uint32_t m = (w << 5) + bit;
+          const uint64_t c = s ^ s_flip[m];
+          const uint32_t hsh = filter_hash(c);
+          const uint2 word = __ldg(&a.filter[c >> a.fshift]);
+          if (__funnelshift_r(word.x, 0u, hsh >> 27) & __funnelshift_r(word.y, 0u, hsh >> 22) & 1u) {
+            ws.surv[h * 32 + lane] = static_cast<uint16_t>(m);
+            ++h;
+          }
+        }
+        if (__any_sync(0xffffffffu, h >= slots)) {
           __syncwarp();
-          process(min(qcount, 64u));
+          flush();
         }
-        __syncwarp();
-        down_cnt = ws.cnt[lane];
-        if (live) ws.cnt[lane] = down_cnt + 1;
-        __syncwarp();
       }
-      const bool app = live && ((s & s_mask[m]) == s_need[m]);
-      const uint32_t bits = __ballot_sync(0xffffffffu, app);
-      if (app) ws.queue[(qhead + qcount + __popc(bits & lt_mask)) & (kFxQueue - 1)] = static_cast<uint16_t>((m << 5) | lane);
-      qcount += __popc(bits);
-      if (qcount >= 64) {
-        __syncwarp();
-        process(64);
-      }
-    }
-    while (qcount > 0) {
       __syncwarp();
-      process(min(qcount, 64u));
+      flush();
     }
-    __syncwarp();
-    if (a.n_down >= a.n_moves && overflow_from == a.n_moves) {  // no positive-delta move: diagonal goes last
-      down_cnt = ws.cnt[lane];
-      if (live) ws.cnt[lane] = down_cnt + 1;
-      __syncwarp();
-    }
-    // lane-per-row fallback for the moves the hit list could not take: count now, write later
-    const uint32_t listed_cnt = ws.cnt[lane];
-    uint32_t my_cnt = listed_cnt;
-    if (overflow_from < a.n_moves) {
-      if (live) {
-        for (int m = overflow_from; m < a.n_moves; ++m) {
-          if (m == a.n_down) down_cnt = my_cnt++;
-          if ((s & s_mask[m]) != s_need[m]) continue;
-          if (search_one(a, s ^ s_flip[m]) >= 0) ++my_cnt;
-        }
-        if (a.n_down >= a.n_moves) down_cnt = my_cnt++;
-      }
-    }
+    const uint32_t packed_cnt = ws.cnt[lane];
+    const uint32_t my_cnt = (packed_cnt & 0xFFFFu) + (live ? 1u : 0u);
+    const uint32_t down_cnt = packed_cnt >> 16;
 
-    // =========================== tile offset by decoupled look-back ==========================
+    // =========================== D: tile offset by decoupled look-back =======================
     uint32_t incl = my_cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -363,7 +391,7 @@ __global__ void __launch_bounds__(kFxThreads) extract_csr_kernel(const FusedArgs
     __syncthreads();
     const uint64_t tile_base = s_tile_base;
 
-    // =========================== phase 2: write the tile's CSR rows ==========================
+    // =========================== write the tile's CSR rows ===================================
     const uint32_t my_off = warp_base + incl - my_cnt;  // row start relative to the tile
     const double a_i = live ? fabs(a.psi[row]) : 0.0;
     ws.row_off[lane] = my_off;
@@ -371,8 +399,8 @@ __global__ void __launch_bounds__(kFxThreads) extract_csr_kernel(const FusedArgs
     if (live) a.indptr[r] = static_cast<int64_t>(tile_base + my_off);
     __syncwarp();
     for (uint32_t k = lane; k < list_count; k += 32) {
-      const uint32_t tag = ws.list_tag[k], pos = ws.list_pos[k];
-      const uint32_t m = tag & 0xFFFFu, src = (tag >> 16) & 31u, rank = tag >> 21;
+      const uint2 entry = my_list[k];
+      const uint32_t pos = entry.x, m = entry.y & 0x7FFu, src = (entry.y >> 11) & 31u, rank = entry.y >> 16;
       const uint64_t dest = tile_base + ws.row_off[src] + rank;
       if (dest < a.capacity) {
         a.indices[dest] = static_cast<int32_t>(pos);
@@ -380,31 +408,11 @@ __global__ void __launch_bounds__(kFxThreads) extract_csr_kernel(const FusedArgs
       }
     }
     if (live) {
-      double d = 0.0;
-      for (int k = 0; k < a.n_diag; ++k) {
-        const DiagBond db = s_diag[k];
-        const int idx = static_cast<int>(((s >> db.i) & 1) * 2 + ((s >> db.j) & 1));
-        d += db.d[idx];
-      }
+      const double d = diagonal_element(s, s_diag, a.n_diag);
       const uint64_t dest = tile_base + my_off + down_cnt;
       if (dest < a.capacity) {
         a.indices[dest] = static_cast<int32_t>(row);
         a.data[dest] = d * (a_i * a_i);
-      }
-      if (overflow_from < a.n_moves) {  // redo the fallback moves, now writing in place
-        uint32_t c = listed_cnt;
-        for (int m = overflow_from; m < a.n_moves; ++m) {
-          if (m == a.n_down) ++c;
-          if ((s & s_mask[m]) != s_need[m]) continue;
-          const int32_t pos = search_one(a, s ^ s_flip[m]);
-          if (pos < 0) continue;
-          const uint64_t at = tile_base + my_off + c;
-          if (at < a.capacity) {
-            a.indices[at] = pos;
-            a.data[at] = s_coef[m] * (a_i * fabs(__ldg(&a.psi[pos])));
-          }
-          ++c;
-        }
       }
     }
   }
@@ -414,26 +422,41 @@ constexpr int kFxMaxChunks = kFusedMaxChunks;  // row chunks of one pipelined ho
 
 struct FusedWorkspace {
   uint32_t *starts;
+  uint2 *filter;
   unsigned long long *status;  // [num_tiles + kFxMaxChunks]: every row chunk has its own slice
   unsigned int *tickets;       // [kFxMaxChunks] one per chunk, 64 B apart
   unsigned long long *totals;  // [kFxMaxChunks] running totals
-  uint64_t num_buckets;
-  int shift;
+  uint2 *scratch;
+  uint64_t num_buckets, num_words;
+  int tshift, fshift;
+  uint32_t scratch_per_warp, scratch_ctas;
   size_t bytes, zero_offset, zero_bytes;
 };
+
+static int g_surv_entries_override = 0;
+static int g_filter_bits_delta = 0, g_table_bits_delta = 0, g_stage_a_mode = 0;
 
 static FusedWorkspace carve_fused(void *base, const asp_operator *op, uint64_t n_total, uint64_t num_rows) {
   FusedWorkspace w;
   int lg = 0;
   while ((1ull << lg) < n_total) ++lg;
-  int bits = lg;  // about one key per bucket
-  if (bits < 4) bits = 4;
-  if (bits > 26) bits = 26;
   const int key_bits = static_cast<int>(op->number_spins);
-  if (bits > key_bits) bits = key_bits;
-  w.shift = key_bits - bits;
-  w.num_buckets = 1ull << bits;
+  int tbits = lg - 1 + g_table_bits_delta;  // about two slots per key: most buckets hold 0 or 1 keys
+  tbits = std::max(4, std::min(tbits, 26));
+  tbits = std::min(tbits, key_bits);
+  w.tshift = key_bits - tbits;
+  w.num_buckets = 1ull << tbits;
+  int fbits = lg - 3 + g_filter_bits_delta;  // 8 bytes per 8 keys
+  fbits = std::max(4, std::min(fbits, 27));
+  fbits = std::min(fbits, key_bits);
+  w.fshift = key_bits - fbits;
+  w.num_words = 1ull << fbits;
   const uint64_t tiles = (num_rows + kFxTileRows - 1) / kFxTileRows + kFxMaxChunks;
+  w.scratch_per_warp = std::max<uint32_t>(32u * static_cast<uint32_t>(op->moves.size()), 32u);
+  const size_t per_cta = static_cast<size_t>(w.scratch_per_warp) * kFxWarps * sizeof(uint2);
+  uint64_t ctas = std::min<uint64_t>(static_cast<uint64_t>(kNumSMs) * kFxMaxCtasPerSM, std::max<uint64_t>(tiles, 1));
+  ctas = std::min<uint64_t>(ctas, std::max<uint64_t>(kFxScratchBudget / per_cta, kNumSMs));
+  w.scratch_ctas = static_cast<uint32_t>(ctas);
   size_t off = 0;
   auto take = [&](size_t bytes) {
     void *p = base ? static_cast<char *>(base) + off : nullptr;
@@ -441,7 +464,9 @@ static FusedWorkspace carve_fused(void *base, const asp_operator *op, uint64_t n
     return p;
   };
   w.starts = static_cast<uint32_t *>(take((w.num_buckets + 1) * sizeof(uint32_t)));
+  w.scratch = static_cast<uint2 *>(take(per_cta * ctas));
   w.zero_offset = off;
+  w.filter = static_cast<uint2 *>(take(w.num_words * sizeof(uint2)));
   w.status = static_cast<unsigned long long *>(take(tiles * sizeof(unsigned long long)));
   w.tickets = static_cast<unsigned int *>(take(kFxMaxChunks * 64));
   w.totals = static_cast<unsigned long long *>(take(kFxMaxChunks * sizeof(unsigned long long)));
@@ -449,8 +474,6 @@ static FusedWorkspace carve_fused(void *base, const asp_operator *op, uint64_t n
   w.bytes = off;
   return w;
 }
-
-static int g_list_cap_override = 0;
 
 size_t fused_workspace_bytes(const asp_operator *op, uint64_t n_total, uint64_t num_rows) {
   return carve_fused(nullptr, op, n_total, num_rows).bytes;
@@ -475,7 +498,8 @@ int fused_prepare(const asp_operator *op, uint64_t n_total, const uint64_t *d_sp
     return ASP_ERR_WORKSPACE;
   }
   ASP_CUDA_CHECK(cudaMemsetAsync(static_cast<char *>(d_workspace) + w.zero_offset, 0, w.zero_bytes, s));
-  build_starts_kernel<<<static_cast<unsigned>((n_total + 255) / 256), 256, 0, s>>>(d_spins, static_cast<uint32_t>(n_total), w.shift, w.num_buckets, w.starts);
+  build_index_kernel<<<static_cast<unsigned>((n_total + 255) / 256), 256, 0, s>>>(d_spins, static_cast<uint32_t>(n_total), op->state_mask, w.tshift,
+                                                                                 w.num_buckets, w.starts, w.fshift, w.filter);
   ASP_LAUNCH_CHECK();
   return ASP_OK;
 }
@@ -493,19 +517,30 @@ int fused_launch(const asp_operator *op, uint64_t n_total, const uint64_t *d_spi
   FusedWorkspace w = carve_fused(d_workspace, op, n_total, num_rows);
   FusedArgs a{};
   a.spins = d_spins;
-  a.starts = w.starts;
-  a.num_buckets = w.num_buckets;
-  a.shift = w.shift;
-  a.n_total = static_cast<uint32_t>(n_total);
   a.psi = d_psi;
+  a.starts = w.starts;
+  a.tshift = w.tshift;
+  a.filter = w.filter;
+  a.fshift = w.fshift;
+  a.state_mask = op->state_mask;
+  a.n_total = static_cast<uint32_t>(n_total);
   a.row_begin = row_begin + chunk_begin;
   a.num_rows = chunk_rows;
   a.num_tiles = (chunk_rows + kFxTileRows - 1) / kFxTileRows;
   a.moves = op->d_moves;
   a.n_moves = static_cast<int>(op->moves.size());
   a.n_down = static_cast<int>(op->n_down);
+  a.n_words = (a.n_moves + 31) / 32;
   a.diag = op->d_diag;
   a.n_diag = static_cast<int>(op->diag.size());
+  int slots = kFxSurvSlotsDefault;
+  if (g_surv_entries_override > 0) slots = std::max(1, g_surv_entries_override / 32);
+  a.surv_slots = slots;
+  bool two_bit = true;
+  for (const Move &mv : op->moves) two_bit = two_bit && __builtin_popcountll(mv.mask) == 2;
+  a.planes_ok = (two_bit && g_stage_a_mode != 1) ? 1 : 0;
+  a.scratch = w.scratch;
+  a.scratch_per_warp = w.scratch_per_warp;
   a.status = w.status + chunk_begin / kFxTileRows + chunk;
   a.ticket = w.tickets + 16 * chunk;
   a.capacity = capacity;
@@ -515,23 +550,15 @@ int fused_launch(const asp_operator *op, uint64_t n_total, const uint64_t *d_spi
   a.nnz_out = w.totals + chunk;
   a.nnz_mirror = nnz_mirror;
   a.base_in = chunk == 0 ? nullptr : w.totals + (chunk - 1);
-  // hit list: room for every candidate of 32 rows when that is small, else 40 per row (more is
-  // handled by the in-kernel fallback)
-  int cap = static_cast<int>(std::min<uint64_t>(32ull * op->max_candidates(), 1280));
-  if (g_list_cap_override > 0) cap = g_list_cap_override;
-  if (cap < 96) cap = 96;
-  cap = (cap + 31) / 32 * 32;
-  a.list_cap = cap;
-  const size_t tables = op->moves.size() * 32 + op->diag.size() * sizeof(DiagBond);
-  const size_t per_warp = static_cast<size_t>(cap) * 8 + kFxQueue * 2 + 32 * 4 + 32 * 8 + 32 * 4;
-  const size_t smem = align_up(tables, 16) + per_warp * kFxWarps + 16;
+  const size_t tables = op->moves.size() * 32 + op->diag.size() * sizeof(DiagBond) + static_cast<size_t>(a.n_words) * 128;
+  const size_t smem = align_up(tables, 16) + fx_per_warp_bytes(a.n_words, slots) * kFxWarps + 16;
   ASP_REQUIRE(smem <= 200 * 1024, "operator too large for the fused kernel's shared-memory tables");
   ASP_CUDA_CHECK(cudaFuncSetAttribute(extract_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int per_sm = 0;
   ASP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, extract_csr_kernel, kFxThreads, smem));
   ASP_REQUIRE(per_sm >= 1, "fused extraction kernel does not fit on an SM");
-  const uint64_t resident = static_cast<uint64_t>(kNumSMs) * per_sm;
-  const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(a.num_tiles, resident));
+  const uint64_t resident = static_cast<uint64_t>(kNumSMs) * std::min(per_sm, kFxMaxCtasPerSM);
+  const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(std::min<uint64_t>(a.num_tiles, resident), w.scratch_ctas));
   extract_csr_kernel<<<grid, kFxThreads, smem, s>>>(a);
   ASP_LAUNCH_CHECK();
   return ASP_OK;
@@ -547,7 +574,13 @@ using namespace asp;
 
 extern "C" {
 
-void asp_debug_set_hit_list_capacity(int entries_per_warp) { g_list_cap_override = entries_per_warp; }
+void asp_debug_set_hit_list_capacity(int entries_per_warp) { g_surv_entries_override = entries_per_warp; }
+
+void asp_debug_set_extract_tuning(int filter_bits_delta, int table_bits_delta, int stage_a_mode) {
+  g_filter_bits_delta = filter_bits_delta;
+  g_table_bits_delta = table_bits_delta;
+  g_stage_a_mode = stage_a_mode;
+}
 
 size_t asp_extract_csr_workspace_bytes(asp_operator const *op, uint64_t n_total, uint64_t num_rows) {
   if (!op) return 0;

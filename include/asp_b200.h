@@ -141,9 +141,12 @@ int asp_extract_csr(asp_operator const *op, uint64_t n_total, uint64_t const *d_
                     double const *d_psi, uint64_t row_begin, uint64_t num_rows, void *d_workspace,
                     size_t workspace_bytes, uint64_t capacity, int64_t *d_indptr,
                     int32_t *d_indices, double *d_data, uint64_t *h_nnz, void *stream);
-/* Test hook: hit-list entries per warp of the single-pass kernel (0 = automatic). Small values
- * force its lane-per-row fallback. */
+/* Test hooks.  Survivor-list entries per warp of the single-pass kernel (0 = automatic, 512):
+ * small values force many exact-search rounds per tile.  Tuning: change the log2 size of the
+ * Bloom filter / first-position table relative to the automatic choice, stage_a_mode 1 = test
+ * move applicability lane by lane instead of on bit planes. */
 void asp_debug_set_hit_list_capacity(int entries_per_warp);
+void asp_debug_set_extract_tuning(int filter_bits_delta, int table_bits_delta, int stage_a_mode);
 
 /* Canonical CSR of generation-order rows (raw output of asp_build_matrix_dev): inside each
  * row a stable sort by column, duplicates summed in generation order -- what scipy's

@@ -337,14 +337,19 @@ def test_single_pass_kernel_equals_two_pass_bitwise(system, n, seed):
     spins = synthetic.cluster_closed_states(op, n, seed, DEV)
     psi = synthetic.synthetic_amplitudes(spins.shape[0], seed, device=DEV)
     ref = common.extract_csr_two_pass_device(op, spins, psi)
-    for cap in (0, 96, 160):  # automatic hit list; tiny lists force the lane-per-row fallback
+    # automatic survivor lists; tiny ones (1 and 3 slots per lane) force many exact-search rounds per
+    # tile; a coarse filter lets most misses through to the exact search, a fine one almost none;
+    # stage A lane by lane instead of on bit planes
+    for cap, tuning in [(0, (0, 0, 0)), (32, (0, 0, 0)), (96, (-6, -3, 0)), (0, (3, 2, 1)), (0, (-30, -30, 1))]:
         lib().asp_debug_set_hit_list_capacity(cap)
+        lib().asp_debug_set_extract_tuning(*tuning)
         try:
             got = common.extract_csr_device(op, spins, psi)
         finally:
             lib().asp_debug_set_hit_list_capacity(0)
+            lib().asp_debug_set_extract_tuning(0, 0, 0)
         for a, b in zip(got, ref):
-            assert torch.equal(a, b), (system, cap)
+            assert torch.equal(a, b), (system, cap, tuning)
     # row blocks (what each GPU of a sharded run builds)
     m = spins.shape[0]
     lo, hi = m // 3, m - m // 5
