@@ -22,7 +22,8 @@ def lib():
             raise AspError(
                 "libasp_b200.so is not built (run `python annealing-sign-problem_b200/build_extension.py`); "
                 "this package has no CPU fallback")
-        _lib = ffi.dlopen(LIBRARY)
+        # ASP_B200_LIBRARY: development override (kernel variants built side by side)
+        _lib = ffi.dlopen(os.environ.get("ASP_B200_LIBRARY", LIBRARY))
     return _lib
 
 

@@ -56,6 +56,9 @@ struct FusedArgs {
   int n_moves, n_down, n_words;
   const DiagBond *diag;
   int n_diag;
+  const DiagGroup *groups; // closed form of the diagonal (n_groups < 0: use the bond loop)
+  int n_groups, diag_scale;
+  long long diag_c0;
   int surv_slots;          // survivor slots per lane
   int planes_ok;           // every move mask has exactly two bits: stage A on bit planes
   uint2 *scratch;          // [gridDim.x * kFxWarps][scratch_per_warp] hit lists {position, tag}
@@ -80,9 +83,81 @@ __device__ __forceinline__ void st_status(unsigned long long *p, unsigned long l
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Two hashed bit positions (5 bits each) of a key inside its filter word.
-__device__ __forceinline__ uint32_t filter_hash(uint64_t key) {
-  return (static_cast<uint32_t>(key) + static_cast<uint32_t>(key >> 32) * 0x85EBCA6Bu) * 0x9E3779B1u;
+// Two hashed bit positions of a key inside its filter word: bits 0..4 (first half-word) and bits
+// 8..12 (second half-word) of a GF(2)-LINEAR mix, so hash(s ^ flip) = hash(s) ^ hash(flip): the
+// kernel hashes every row once and every move once instead of every candidate.
+__host__ __device__ __forceinline__ uint32_t filter_hash(uint64_t key) {
+  const uint32_t lo = static_cast<uint32_t>(key), hi = static_cast<uint32_t>(key >> 32);
+  uint32_t y = lo ^ ((hi << 7) | (hi >> 25));
+  y ^= y >> 15;
+  y ^= y << 11;
+  y ^= y >> 7;
+  y ^= y << 3;
+  y ^= y >> 17;
+  return y;
+}
+
+// Loads that bypass L1 allocation: filter words, table entries, keys and gathered amplitudes are
+// touched once per SM, while the warp's hit list (written, then read back) should stay in L1.
+#ifndef ASP_FX_STREAM_FILTER
+#define ASP_FX_STREAM_FILTER 0
+#endif
+#ifndef ASP_FX_STREAM_SEARCH
+#define ASP_FX_STREAM_SEARCH 0
+#endif
+#ifndef ASP_FX_STREAM_PSI
+#define ASP_FX_STREAM_PSI 0
+#endif
+__device__ __forceinline__ uint2 ldg_filter_u2(const uint2 *p) {
+#if ASP_FX_STREAM_FILTER
+  uint2 v;
+  asm("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
+__device__ __forceinline__ uint32_t ldg_stream_u32(const uint32_t *p) {
+#if ASP_FX_STREAM_SEARCH
+  uint32_t v;
+  asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
+__device__ __forceinline__ uint64_t ldg_stream_u64(const uint64_t *p) {
+#if ASP_FX_STREAM_SEARCH
+  uint64_t v;
+  asm("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
+__device__ __forceinline__ double ldg_stream_f64(const double *p) {
+#if ASP_FX_STREAM_PSI
+  double v;
+  asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
+// Shared memory through 32-bit addresses (the walk of stage B keeps running addresses).
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint2 lds_table_u2(uint32_t addr) {  // read-only tables: free to schedule
+  uint2 v;
+  asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(static_cast<unsigned short>(v)) : "memory");
 }
 
 // Index of the sorted basis: first-position table + Bloom filter, one thread per key.
@@ -105,24 +180,24 @@ __global__ void __launch_bounds__(256) build_index_kernel(const uint64_t *__rest
   if ((key & ~state_mask) == 0) {
     const uint32_t h = filter_hash(key);
     uint2 *w = filter + (key >> fshift);
-    atomicOr(&w->x, 1u << (h >> 27));
-    atomicOr(&w->y, 1u << ((h >> 22) & 31u));
+    atomicOr(&w->x, 1u << (h & 31u));
+    atomicOr(&w->y, 1u << ((h >> 8) & 31u));
   }
 }
 
 // Position of c (< 2^number_spins) in the sorted basis, or -1.
 __device__ __forceinline__ int32_t search_one(const FusedArgs &a, uint64_t c) {
-  const uint64_t b = c >> a.tshift;
-  uint32_t lo = __ldg(&a.starts[b]), hi = __ldg(&a.starts[b + 1]);
+  const uint32_t *bucket = a.starts + (c >> a.tshift);
+  uint32_t lo = ldg_stream_u32(bucket), hi = ldg_stream_u32(bucket + 1);
   while (hi - lo > 8) {  // pathological bucket: bisect down to a short scan
     const uint32_t mid = lo + ((hi - lo) >> 1);
-    if (__ldg(&a.spins[mid]) < c)
+    if (ldg_stream_u64(&a.spins[mid]) < c)
       lo = mid + 1;
     else
       hi = mid + 1;
   }
   for (; lo < hi; ++lo) {
-    const uint64_t k = __ldg(&a.spins[lo]);
+    const uint64_t k = ldg_stream_u64(&a.spins[lo]);
     if (k >= c) return k == c ? static_cast<int32_t>(lo) : -1;
   }
   return -1;
@@ -150,70 +225,109 @@ __device__ __forceinline__ double diagonal_element(uint64_t s, const DiagBond *s
   return d;
 }
 
-// Per-warp shared-memory state.
-struct WarpSmem {
-  uint32_t *planes;   // [64] bit planes of the 32 keys
-  uint32_t *amask;    // [n_words][32] moves that apply, per lane
-  uint16_t *surv;     // [surv_slots][32] moves whose candidate passed the filter, per lane
-  uint32_t *pre;      // [33] exclusive prefix of survivor counts
-  uint32_t *cnt;      // [32] couplings found so far per row | those below the diagonal << 16
-  uint32_t *row_off;  // [32] row start relative to the tile's first coupling
-  double *abs_psi;    // [32]
+// Same value in closed form (operator.cuh: DiagGroup): exact integer arithmetic, one scaling.
+__device__ __forceinline__ double diagonal_closed_form(uint64_t s, const DiagGroup *s_groups, int n_groups, long long c0, int scale) {
+  long long acc = c0;
+  for (int g = 0; g < n_groups; ++g) {
+    const DiagGroup grp = s_groups[g];
+    acc += static_cast<long long>(grp.weight) * __popcll(s & (s >> grp.shift) & grp.sites);
+  }
+  return scalbn(static_cast<double>(acc), -scale);
+}
+
+// Shared-memory layout.  CTA-wide tables, then one block per warp; inside a warp's block the
+// bit planes (stage A) share their bytes with the survivor slots (stages B/C) and the apply
+// masks (A/B) with the row offsets and amplitudes of the write phase.
+struct FxLayout {
+  uint32_t cand, flip, coef, desc, mask, need, groups, diag;  // byte offsets of the tables
+  uint32_t tables;                                            // bytes of all tables
+  uint32_t w_surv, w_amask, w_pre, w_cnt;                     // byte offsets inside a warp's block
+  uint32_t per_warp;
 };
 
-__host__ __device__ inline size_t fx_per_warp_bytes(int n_words, int surv_slots) {
-  return 32 * 8 + 64 * 4 + static_cast<size_t>(n_words) * 128 + 36 * 4 + 32 * 4 + 32 * 4 + static_cast<size_t>(surv_slots) * 64;
+__host__ __device__ inline FxLayout fx_layout(int n_moves, int n_words, int n_groups, int n_diag, int planes_ok, int surv_slots) {
+  FxLayout L;
+  uint32_t off = 0;
+  auto take = [&](uint32_t bytes) {
+    const uint32_t at = off;
+    off += (bytes + 15u) & ~15u;
+    return at;
+  };
+  L.cand = take(static_cast<uint32_t>(n_words) * 32u * 8u);  // {flip >> fshift, hash(flip)} per move, padded to whole words
+  L.flip = take(static_cast<uint32_t>(n_moves) * 8u);
+  L.coef = take(static_cast<uint32_t>(n_moves) * 8u);
+  L.desc = take(planes_ok ? static_cast<uint32_t>(n_words) * 128u : 0u);
+  L.mask = take(planes_ok ? 0u : static_cast<uint32_t>(n_moves) * 8u);
+  L.need = take(planes_ok ? 0u : static_cast<uint32_t>(n_moves) * 8u);
+  L.groups = take(n_groups >= 0 ? static_cast<uint32_t>(n_groups) * 16u : 0u);
+  L.diag = take(n_groups >= 0 ? 0u : static_cast<uint32_t>(n_diag) * static_cast<uint32_t>(sizeof(DiagBond)));
+  L.tables = off;
+  off = 0;
+  const uint32_t surv_bytes = static_cast<uint32_t>(surv_slots) * 64u;
+  L.w_surv = take(surv_bytes > 256u ? surv_bytes : 256u);                              // | planes u32[64]
+  L.w_amask = take(n_words * 128u > 384u ? static_cast<uint32_t>(n_words) * 128u : 384u);  // | abs_psi f64[32], row_off u32[32]
+  L.w_pre = take(36u * 4u);
+  L.w_cnt = take(32u * 4u);
+  L.per_warp = off;
+  return L;
 }
 
 __global__ void __launch_bounds__(kFxThreads) extract_csr_kernel(const FusedArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // ---- shared memory carve-up: move tables (SoA), diagonal table, per-warp state ------------
-  uint64_t *s_flip = reinterpret_cast<uint64_t *>(smem_raw);
-  double *s_coef = reinterpret_cast<double *>(s_flip + a.n_moves);
-  uint64_t *s_mask = reinterpret_cast<uint64_t *>(s_coef + a.n_moves);
-  uint64_t *s_need = s_mask + a.n_moves;
-  DiagBond *s_diag = reinterpret_cast<DiagBond *>(s_need + a.n_moves);
-  uint32_t *s_desc = reinterpret_cast<uint32_t *>(s_diag + a.n_diag);  // [n_words * 32] site i | site j << 8 | need_i << 16 | need_j << 17 | valid << 18
-  unsigned char *cursor = reinterpret_cast<unsigned char *>(s_desc + a.n_words * 32);
-  cursor = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(cursor) + 15) & ~static_cast<uintptr_t>(15));
+  const FxLayout L = fx_layout(a.n_moves, a.n_words, a.n_groups, a.n_diag, a.planes_ok, a.surv_slots);
+  uint2 *s_cand = reinterpret_cast<uint2 *>(smem_raw + L.cand);
+  uint64_t *s_flip = reinterpret_cast<uint64_t *>(smem_raw + L.flip);
+  double *s_coef = reinterpret_cast<double *>(smem_raw + L.coef);
+  uint32_t *s_desc = reinterpret_cast<uint32_t *>(smem_raw + L.desc);  // site i | site j << 8 | need_i << 16 | need_j << 17 | valid << 18
+  uint64_t *s_mask = reinterpret_cast<uint64_t *>(smem_raw + L.mask);
+  uint64_t *s_need = reinterpret_cast<uint64_t *>(smem_raw + L.need);
+  DiagGroup *s_groups = reinterpret_cast<DiagGroup *>(smem_raw + L.groups);
+  DiagBond *s_diag = reinterpret_cast<DiagBond *>(smem_raw + L.diag);
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
-  WarpSmem ws;
-  {
-    unsigned char *base = cursor + fx_per_warp_bytes(a.n_words, a.surv_slots) * warp;
-    ws.abs_psi = reinterpret_cast<double *>(base);
-    ws.planes = reinterpret_cast<uint32_t *>(base + 32 * 8);
-    ws.amask = ws.planes + 64;
-    ws.pre = ws.amask + a.n_words * 32;
-    ws.cnt = ws.pre + 36;
-    ws.row_off = ws.cnt + 32;
-    ws.surv = reinterpret_cast<uint16_t *>(ws.row_off + 32);
-  }
+  unsigned char *const wbase = smem_raw + L.tables + L.per_warp * warp;
+  uint32_t *const w_planes = reinterpret_cast<uint32_t *>(wbase + L.w_surv);
+  uint16_t *const w_surv = reinterpret_cast<uint16_t *>(wbase + L.w_surv);
+  uint32_t *const w_amask = reinterpret_cast<uint32_t *>(wbase + L.w_amask);
+  double *const w_abs_psi = reinterpret_cast<double *>(wbase + L.w_amask);
+  uint32_t *const w_row_off = reinterpret_cast<uint32_t *>(wbase + L.w_amask + 256);
+  uint32_t *const w_pre = reinterpret_cast<uint32_t *>(wbase + L.w_pre);
+  uint32_t *const w_cnt = reinterpret_cast<uint32_t *>(wbase + L.w_cnt);
   __shared__ unsigned int s_tile;
   __shared__ unsigned int s_warp_total[kFxWarps];
   __shared__ unsigned long long s_tile_base;
 
-  for (int k = threadIdx.x; k < a.n_moves; k += kFxThreads) {
-    const Move mv = a.moves[k];
-    s_flip[k] = mv.flip;
-    s_coef[k] = mv.coef;
-    s_mask[k] = mv.mask;
-    s_need[k] = mv.need;
-  }
   for (int k = threadIdx.x; k < a.n_words * 32; k += kFxThreads) {
+    uint2 cand = make_uint2(0u, 0u);
     uint32_t desc = 0;
     if (k < a.n_moves) {
       const Move mv = a.moves[k];
-      const int i = __ffsll(static_cast<long long>(mv.mask)) - 1;
-      const int j = 63 - __clzll(static_cast<long long>(mv.mask));
-      desc = static_cast<uint32_t>(i) | (static_cast<uint32_t>(j) << 8) | (static_cast<uint32_t>((mv.need >> i) & 1) << 16) |
-             (static_cast<uint32_t>((mv.need >> j) & 1) << 17) | (1u << 18);
+      s_flip[k] = mv.flip;
+      s_coef[k] = mv.coef;
+      cand = make_uint2(static_cast<uint32_t>(mv.flip >> a.fshift), filter_hash(mv.flip));
+      if (a.planes_ok) {
+        const int i = __ffsll(static_cast<long long>(mv.mask)) - 1;
+        const int j = 63 - __clzll(static_cast<long long>(mv.mask));
+        desc = static_cast<uint32_t>(i) | (static_cast<uint32_t>(j) << 8) | (static_cast<uint32_t>((mv.need >> i) & 1) << 16) |
+               (static_cast<uint32_t>((mv.need >> j) & 1) << 17) | (1u << 18);
+      } else {
+        s_mask[k] = mv.mask;
+        s_need[k] = mv.need;
+      }
     }
-    s_desc[k] = desc;
+    s_cand[k] = cand;
+    if (a.planes_ok) s_desc[k] = desc;
   }
-  for (int k = threadIdx.x; k < a.n_diag; k += kFxThreads) s_diag[k] = a.diag[k];
+  if (a.n_groups >= 0) {
+    for (int k = threadIdx.x; k < a.n_groups; k += kFxThreads) s_groups[k] = a.groups[k];
+  } else {
+    for (int k = threadIdx.x; k < a.n_diag; k += kFxThreads) s_diag[k] = a.diag[k];
+  }
   uint2 *const my_list = a.scratch + (static_cast<size_t>(blockIdx.x) * kFxWarps + warp) * a.scratch_per_warp;
   const uint32_t slots = static_cast<uint32_t>(a.surv_slots);
+  const uint32_t cand_base = smem_addr(s_cand);
+  const uint32_t amask_base = smem_addr(w_amask) + lane * 4u;
+  const uint32_t surv_base = smem_addr(w_surv) + lane * 2u;
 
   for (;;) {
     __syncthreads();  // previous tile fully written; tables loaded
@@ -225,23 +339,23 @@ __global__ void __launch_bounds__(kFxThreads) extract_csr_kernel(const FusedArgs
     const uint64_t r = tile * kFxTileRows + threadIdx.x;
     const bool live = r < a.num_rows;
     const uint64_t row = a.row_begin + r;
-    const uint64_t s = live ? a.spins[row] : 0ull;
+    const uint64_t s = live ? ldg_stream_u64(&a.spins[row]) : 0ull;
     const uint32_t s_lo = static_cast<uint32_t>(s), s_hi = static_cast<uint32_t>(s >> 32);
     const bool generates = live && (s & ~a.state_mask) == 0;  // keys wider than the word have no images in the basis
 
     // =========================== A: which moves apply to which row ===========================
     if (a.planes_ok) {
       const uint32_t gen_mask = __ballot_sync(0xffffffffu, generates);
-      ws.planes[lane] = transpose32(s_lo, lane);
-      ws.planes[32 + lane] = transpose32(s_hi, lane);
+      w_planes[lane] = transpose32(s_lo, lane);
+      w_planes[32 + lane] = transpose32(s_hi, lane);
       __syncwarp();
       for (int w = 0; w < a.n_words; ++w) {
         const uint32_t desc = s_desc[w * 32 + lane];
-        const uint32_t pi = ws.planes[desc & 63u], pj = ws.planes[(desc >> 8) & 63u];
+        const uint32_t pi = w_planes[desc & 63u], pj = w_planes[(desc >> 8) & 63u];
         const uint32_t xi = ((desc >> 16) & 1u) - 1u, xj = ((desc >> 17) & 1u) - 1u;  // need 1 -> 0, need 0 -> ~0
         uint32_t app = (pi ^ xi) & (pj ^ xj) & gen_mask;                              // rows this lane's move applies to
         if (!(desc & (1u << 18))) app = 0;
-        ws.amask[w * 32 + lane] = transpose32(app, lane);                             // moves that apply to this lane's row
+        w_amask[w * 32 + lane] = transpose32(app, lane);                              // moves that apply to this lane's row
       }
     } else {
       for (int w = 0; w < a.n_words; ++w) {
@@ -249,18 +363,19 @@ __global__ void __launch_bounds__(kFxThreads) extract_csr_kernel(const FusedArgs
         const int m_end = min(32, a.n_moves - w * 32);
         for (int k = 0; k < m_end; ++k)
           if ((s & s_mask[w * 32 + k]) == s_need[w * 32 + k]) bits |= 1u << k;
-        ws.amask[w * 32 + lane] = generates ? bits : 0u;
+        w_amask[w * 32 + lane] = generates ? bits : 0u;
       }
     }
-    ws.cnt[lane] = 0;
-    __syncwarp();
+    w_cnt[lane] = 0;
+    __syncwarp();  // planes are dead from here: their bytes become the survivor slots
 
     // =========================== B + C: sieve, search, record ================================
-    uint32_t list_count = 0;  // warp-uniform
-    uint32_t h = 0;           // survivors waiting in this lane's slots
+    uint32_t list_count = 0;          // warp-uniform
+    uint32_t surv_addr = surv_base;   // next free survivor slot of this lane
 
     // C: deal the waiting survivors evenly over the lanes, search them exactly, record the hits
     auto flush = [&]() {
+      const uint32_t h = (surv_addr - surv_base) >> 6;
       uint32_t incl = h;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -268,8 +383,8 @@ __global__ void __launch_bounds__(kFxThreads) extract_csr_kernel(const FusedArgs
         if (lane >= o) incl += t;
       }
       const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-      ws.pre[lane] = incl - h;
-      if (lane == 31) ws.pre[32] = total;
+      w_pre[lane] = incl - h;
+      if (lane == 31) w_pre[32] = total;
       __syncwarp();
       for (uint32_t base = 0; base < total; base += 32) {
         const uint32_t e = base + lane;
@@ -277,8 +392,8 @@ __global__ void __launch_bounds__(kFxThreads) extract_csr_kernel(const FusedArgs
         uint32_t src = 0;  // last lane whose first survivor is at or before e
 #pragma unroll
         for (int step = 16; step >= 1; step >>= 1)
-          if (ws.pre[src + step] <= e) src += step;
-        const uint32_t m = valid ? ws.surv[(e - ws.pre[src]) * 32 + src] : 0u;
+          if (w_pre[src + step] <= e) src += step;
+        const uint32_t m = valid ? (static_cast<uint32_t>(w_surv[(e - w_pre[src]) * 32 + src]) - (cand_base >> 3)) & 0xFFFFu : 0u;
         const uint64_t s_src = (static_cast<uint64_t>(__shfl_sync(0xffffffffu, s_hi, src)) << 32) | __shfl_sync(0xffffffffu, s_lo, src);
         int32_t pos = -1;
         if (valid) pos = search_one(a, s_src ^ s_flip[m]);
@@ -289,10 +404,10 @@ __global__ void __launch_bounds__(kFxThreads) extract_csr_kernel(const FusedArgs
           const uint32_t belows = __ballot_sync(0xffffffffu, hit && below);
           if (hit) {
             const uint32_t peers = __match_any_sync(hits, src);  // hits of the same row in this batch (ascending move order by lane)
-            const uint32_t packed = ws.cnt[src];
+            const uint32_t packed = w_cnt[src];
             __syncwarp(hits);
             const uint32_t before = __popc(peers & lt_mask);
-            if (before == 0) ws.cnt[src] = packed + __popc(peers) + (__popc(peers & belows) << 16);
+            if (before == 0) w_cnt[src] = packed + __popc(peers) + (__popc(peers & belows) << 16);
             const uint32_t rank = (packed & 0xFFFFu) + before + (below ? 0u : 1u);  // the diagonal sits after the negative deltas
             my_list[list_count + __popc(hits & lt_mask)] = make_uint2(static_cast<uint32_t>(pos), m | (src << 11) | (rank << 16));
           }
@@ -300,37 +415,48 @@ __global__ void __launch_bounds__(kFxThreads) extract_csr_kernel(const FusedArgs
         }
         __syncwarp();
       }
-      h = 0;
+      surv_addr = surv_base;
     };
 
     {
-      int w = 0;
-      uint32_t cur = a.n_words ? ws.amask[lane] : 0u;
+      // B: every lane walks the set bits of its own mask words.  A candidate needs its filter
+      // word (index = (s >> fshift) ^ (flip >> fshift)) and its hash (= hash(s) ^ hash(flip)):
+      // one 8-byte table read and two XORs.  At most one survivor slot is used per iteration,
+      // so a warp-uniform countdown tells when the slots may be full.
+      const uint32_t s_idx = static_cast<uint32_t>(s >> a.fshift), s_hash = filter_hash(s);
+      uint32_t amask_addr = amask_base, tab_addr = cand_base;
+      int left = a.n_words - 1;  // mask words after the current one
+      uint32_t cur = a.n_words ? lds_u32(amask_addr) : 0u;
+      uint32_t room = slots;
       for (;;) {
-        while (cur == 0 && w + 1 < a.n_words) cur = ws.amask[++w * 32 + lane];
-        const bool act = cur != 0;
-        if (!__any_sync(0xffffffffu, act)) break;
-        if (act) {
-          const uint32_t bit = __ffs(cur) - 1;
-          cur &= cur - 1;
-          const uint32_t m = (w << 5) + bit;
-          const uint64_t c = s ^ s_flip[m];
-          const uint32_t hsh = filter_hash(c);
-          const uint2 word = __ldg(&a.filter[c >> a.fshift]);
-          if (__funnelshift_r(word.x, 0u, hsh >> 27) & __funnelshift_r(word.y, 0u, hsh >> 22) & 1u) {
-            ws.surv[h * 32 + lane] = static_cast<uint16_t>(m);
-            ++h;
-          }
+        if (cur == 0 && left > 0) {  // at most one word per iteration
+          amask_addr += 128;
+          tab_addr += 256;
+          --left;
+          cur = lds_u32(amask_addr);
         }
-        if (__any_sync(0xffffffffu, h >= slots)) {
+        const bool act = cur != 0;
+        if (!__any_sync(0xffffffffu, act || left > 0)) break;
+        const uint32_t entry_addr = tab_addr + ((static_cast<uint32_t>(__ffs(static_cast<int>(cur)) - 1) & 31u) << 3);
+        cur &= cur - 1;
+        const uint2 entry = lds_table_u2(entry_addr);
+        const uint32_t hsh = s_hash ^ entry.y;
+        uint2 word = make_uint2(0u, 0u);
+        if (act) word = ldg_filter_u2(a.filter + (s_idx ^ entry.x));
+        if (__funnelshift_r(word.x, 0u, hsh) & __funnelshift_r(word.y, 0u, hsh >> 8) & 1u) {
+          sts_u16(surv_addr, entry_addr >> 3);
+          surv_addr += 64;
+        }
+        if (--room == 0) {
           __syncwarp();
           flush();
+          room = slots;
         }
       }
       __syncwarp();
       flush();
     }
-    const uint32_t packed_cnt = ws.cnt[lane];
+    const uint32_t packed_cnt = w_cnt[lane];
     const uint32_t my_cnt = (packed_cnt & 0xFFFFu) + (live ? 1u : 0u);
     const uint32_t down_cnt = packed_cnt >> 16;
 
@@ -361,9 +487,7 @@ __global__ void __launch_bounds__(kFxThreads) extract_csr_kernel(const FusedArgs
           const int64_t idx = look - lane;
           unsigned long long st = kFlagPrefix;  // virtual tiles before tile 0: prefix 0
           if (idx >= 0) {
-            do {
-              st = ld_status(&a.status[idx]);
-            } while ((st >> 62) == 0);
+            while (((st = ld_status(&a.status[idx])) >> 62) == 0) __nanosleep(40);
           }
           const uint32_t has_prefix = __ballot_sync(0xffffffffu, (st >> 62) == 2);
           const uint32_t first = has_prefix ? static_cast<uint32_t>(__ffs(has_prefix)) - 1u : 32u;  // nearest tile with a prefix
@@ -392,23 +516,25 @@ __global__ void __launch_bounds__(kFxThreads) extract_csr_kernel(const FusedArgs
     const uint64_t tile_base = s_tile_base;
 
     // =========================== write the tile's CSR rows ===================================
+    // (the apply masks are dead: their bytes now hold the row offsets and amplitudes)
     const uint32_t my_off = warp_base + incl - my_cnt;  // row start relative to the tile
-    const double a_i = live ? fabs(a.psi[row]) : 0.0;
-    ws.row_off[lane] = my_off;
-    ws.abs_psi[lane] = a_i;
+    const double a_i = live ? fabs(ldg_stream_f64(&a.psi[row])) : 0.0;
+    w_row_off[lane] = my_off;
+    w_abs_psi[lane] = a_i;
     if (live) a.indptr[r] = static_cast<int64_t>(tile_base + my_off);
     __syncwarp();
     for (uint32_t k = lane; k < list_count; k += 32) {
       const uint2 entry = my_list[k];
       const uint32_t pos = entry.x, m = entry.y & 0x7FFu, src = (entry.y >> 11) & 31u, rank = entry.y >> 16;
-      const uint64_t dest = tile_base + ws.row_off[src] + rank;
+      const uint64_t dest = tile_base + w_row_off[src] + rank;
       if (dest < a.capacity) {
         a.indices[dest] = static_cast<int32_t>(pos);
-        a.data[dest] = s_coef[m] * (ws.abs_psi[src] * fabs(__ldg(&a.psi[pos])));
+        a.data[dest] = s_coef[m] * (w_abs_psi[src] * fabs(ldg_stream_f64(&a.psi[pos])));
       }
     }
     if (live) {
-      const double d = diagonal_element(s, s_diag, a.n_diag);
+      const double d = a.n_groups >= 0 ? diagonal_closed_form(s, s_groups, a.n_groups, a.diag_c0, a.diag_scale)
+                                       : diagonal_element(s, s_diag, a.n_diag);
       const uint64_t dest = tile_base + my_off + down_cnt;
       if (dest < a.capacity) {
         a.indices[dest] = static_cast<int32_t>(row);
@@ -533,6 +659,11 @@ int fused_launch(const asp_operator *op, uint64_t n_total, const uint64_t *d_spi
   a.n_words = (a.n_moves + 31) / 32;
   a.diag = op->d_diag;
   a.n_diag = static_cast<int>(op->diag.size());
+  const bool closed_form = op->diag_scale >= 0 && g_stage_a_mode != 1;
+  a.groups = op->d_diag_groups;
+  a.n_groups = closed_form ? static_cast<int>(op->diag_groups.size()) : -1;
+  a.diag_scale = op->diag_scale;
+  a.diag_c0 = op->diag_c0;
   int slots = kFxSurvSlotsDefault;
   if (g_surv_entries_override > 0) slots = std::max(1, g_surv_entries_override / 32);
   a.surv_slots = slots;
@@ -550,8 +681,8 @@ int fused_launch(const asp_operator *op, uint64_t n_total, const uint64_t *d_spi
   a.nnz_out = w.totals + chunk;
   a.nnz_mirror = nnz_mirror;
   a.base_in = chunk == 0 ? nullptr : w.totals + (chunk - 1);
-  const size_t tables = op->moves.size() * 32 + op->diag.size() * sizeof(DiagBond) + static_cast<size_t>(a.n_words) * 128;
-  const size_t smem = align_up(tables, 16) + fx_per_warp_bytes(a.n_words, slots) * kFxWarps + 16;
+  const FxLayout layout = fx_layout(a.n_moves, a.n_words, a.n_groups, a.n_diag, a.planes_ok, slots);
+  const size_t smem = layout.tables + static_cast<size_t>(layout.per_warp) * kFxWarps;
   ASP_REQUIRE(smem <= 200 * 1024, "operator too large for the fused kernel's shared-memory tables");
   ASP_CUDA_CHECK(cudaFuncSetAttribute(extract_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int per_sm = 0;

@@ -2,6 +2,7 @@
 // physical_systems/*.yaml) into delta-sorted XOR moves + diagonal table + symmetry-group
 // bit permutations (Benes networks), and mirrors them on the device.
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <functional>
 #include <numeric>
@@ -88,6 +89,76 @@ static bool make_bit_perm(const uint32_t *perm, uint32_t number_spins, BitPerm &
   for (int q = 0; q < 64; ++q)
     if (apply_perm_host(net, 1ull << src[q]) != (1ull << q)) return false;
   return true;
+}
+
+// Closed form of the diagonal (operator.cuh: DiagGroup).  With t[bl][bh] the entry of a bond for
+// bits (bl, bh) at sites lo < hi:  t = t00 + (t10 - t00) bl + (t01 - t00) bh + (t11 - t10 - t01 + t00) bl bh.
+static void build_diag_groups(asp_operator *op) {
+  op->diag_groups.clear();
+  op->diag_scale = -1;
+  int scale = 0;
+  for (const DiagBond &db : op->diag)
+    for (double v : db.d) {
+      if (!std::isfinite(v)) return;
+      while (scale <= 24 && std::ldexp(v, scale) != std::nearbyint(std::ldexp(v, scale))) ++scale;
+      if (scale > 24) return;
+    }
+  // |entries| * 2^scale * 4 (the mixed coefficient) must fit int32 and every sum of <= 2^12 bonds must be exact
+  if (op->diag.size() > 4096) return;
+  for (const DiagBond &db : op->diag)
+    for (double v : db.d)
+      if (std::fabs(std::ldexp(v, scale)) >= static_cast<double>(1 << 26)) return;
+  int64_t c0 = 0;
+  std::vector<int64_t> site_weight(64, 0);
+  struct Pair {
+    uint32_t shift;
+    int64_t weight;
+    uint64_t sites;
+  };
+  std::vector<Pair> pairs;
+  for (const DiagBond &db : op->diag) {
+    const uint32_t lo = std::min(db.i, db.j), hi = std::max(db.i, db.j);
+    auto t = [&](int bl, int bh) {  // entry for bit(lo) = bl, bit(hi) = bh; db.d index is 2 * bit(i) + bit(j)
+      const int bi = db.i == lo ? bl : bh, bj = db.i == lo ? bh : bl;
+      return static_cast<int64_t>(std::ldexp(db.d[2 * bi + bj], scale));
+    };
+    c0 += t(0, 0);
+    site_weight[lo] += t(1, 0) - t(0, 0);
+    site_weight[hi] += t(0, 1) - t(0, 0);
+    const int64_t mixed = t(1, 1) - t(1, 0) - t(0, 1) + t(0, 0);
+    if (mixed == 0) continue;
+    bool placed = false;
+    for (Pair &p : pairs)
+      if (p.shift == hi - lo && p.weight == mixed && !(p.sites & (1ull << lo))) {  // a site pair listed twice opens a new group
+        p.sites |= 1ull << lo;
+        placed = true;
+        break;
+      }
+    if (!placed) pairs.push_back({hi - lo, mixed, 1ull << lo});
+  }
+  std::vector<Pair> singles;
+  for (uint32_t site = 0; site < 64; ++site) {
+    if (site_weight[site] == 0) continue;
+    bool placed = false;
+    for (Pair &p : singles)
+      if (p.weight == site_weight[site]) {
+        p.sites |= 1ull << site;
+        placed = true;
+        break;
+      }
+    if (!placed) singles.push_back({0u, site_weight[site], 1ull << site});
+  }
+  for (const auto *list : {&singles, &pairs})
+    for (const Pair &p : *list) {
+      if (p.weight > INT32_MAX || p.weight < INT32_MIN) return;
+      op->diag_groups.push_back({p.sites, static_cast<int32_t>(p.weight), p.shift});
+    }
+  if (op->diag_groups.size() > 512) {  // no gain over the bond loop
+    op->diag_groups.clear();
+    return;
+  }
+  op->diag_c0 = c0;
+  op->diag_scale = scale;
 }
 
 }  // namespace asp
@@ -193,6 +264,7 @@ int asp_operator_create(asp_operator **out, uint32_t number_spins, int32_t hammi
         break;
       }
     }
+  asp::build_diag_groups(op);
   for (uint32_t g = 0; g < num_perms; ++g) {
     asp::BitPerm net;
     if (!asp::make_bit_perm(perms + static_cast<size_t>(g) * number_spins, number_spins, net)) {
@@ -215,6 +287,7 @@ int asp_operator_create(asp_operator **out, uint32_t number_spins, int32_t hammi
     };
     int rc = upload(op->d_moves, op->moves);
     if (rc == ASP_OK) rc = upload(op->d_diag, op->diag);
+    if (rc == ASP_OK) rc = upload(op->d_diag_groups, op->diag_groups);
     if (rc == ASP_OK) rc = upload(op->d_perms, op->perms);
     if (rc == ASP_OK) rc = upload(op->d_characters, op->characters);
     if (rc != ASP_OK) {
@@ -230,6 +303,7 @@ void asp_operator_destroy(asp_operator *op) {
   if (!op) return;
   if (op->d_moves) cudaFree(op->d_moves);
   if (op->d_diag) cudaFree(op->d_diag);
+  if (op->d_diag_groups) cudaFree(op->d_diag_groups);
   if (op->d_perms) cudaFree(op->d_perms);
   if (op->d_characters) cudaFree(op->d_characters);
   delete op;

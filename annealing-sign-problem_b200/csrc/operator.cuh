@@ -24,6 +24,16 @@ struct DiagBond {
   double d[4];
 };
 
+// Diagonal in closed form, available when every diagonal entry is a dyadic rational small enough
+// that sums over all bonds are exact in any order (then it equals the bond-by-bond f64 sum bit for
+// bit):  d(s) = 2^-scale * (c0 + sum_g weight_g * popcount(s & (s >> shift_g) & sites_g)).
+// shift 0 groups carry the single-site part, shift k > 0 groups the bonds (i, i + k).
+struct DiagGroup {
+  uint64_t sites;
+  int32_t weight;
+  uint32_t shift;
+};
+
 // A permutation of <= 64 bits as a Benes network of delta swaps:
 // x = delta_swap(x, mask[k], shift[k]) for k = 0..stages-1.
 struct BitPerm {
@@ -40,6 +50,9 @@ struct asp_operator {
   std::vector<asp::Move> moves;  // sorted by delta ascending; [0, n_down) have delta < 0
   uint32_t n_down = 0;
   std::vector<asp::DiagBond> diag;  // in (term, bond) order
+  std::vector<asp::DiagGroup> diag_groups;  // closed form of the diagonal (valid when diag_scale >= 0)
+  int64_t diag_c0 = 0;
+  int32_t diag_scale = -1;
   bool distinct_flips = true;
   // symmetry group (non-identity permutations), real characters
   std::vector<asp::BitPerm> perms;
@@ -47,6 +60,7 @@ struct asp_operator {
   // device mirrors (device current at creation)
   asp::Move *d_moves = nullptr;
   asp::DiagBond *d_diag = nullptr;
+  asp::DiagGroup *d_diag_groups = nullptr;
   asp::BitPerm *d_perms = nullptr;
   double *d_characters = nullptr;
   int device = -1;
