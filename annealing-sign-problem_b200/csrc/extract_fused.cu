@@ -19,9 +19,10 @@
 //   C. survivors are re-dealt evenly over the lanes, searched exactly (4-byte first-position
 //      table over the top key bits + a short scan of the keys) and appended, with their in-row
 //      rank, to the warp's hit list (global scratch, L2-resident);
-//   D. a tile (256 rows) publishes its coupling count, obtains its CSR offset by decoupled
-//      look-back over earlier tiles (tiles are handed out by an atomic ticket, so a tile only
-//      waits for tiles that already run) and writes indptr / indices / data in place.
+//   D. a tile (the 32 rows of a warp; warps never synchronise with each other) publishes its
+//      coupling count, obtains its CSR offset by decoupled look-back over earlier tiles (tiles
+//      are handed out by an atomic ticket, so a tile only waits for tiles that already run) and
+//      writes indptr / indices / data in place.
 // Every lane enumerates its moves in ascending key-delta order, so hits get ascending columns;
 // positions are exact indices into the sorted basis (bit-exact CSR) and values are
 // coef * (|psi_i| * |psi_j|) exactly as in extract.cu.
@@ -31,10 +32,10 @@ namespace asp {
 
 constexpr int kFxWarps = 8;
 constexpr int kFxThreads = kFxWarps * 32;
-constexpr int kFxTileRows = kFxThreads;
+constexpr int kFxTileRows = 32;  // a tile is the 32 rows of one warp
 static_assert(kFxTileRows == kFusedTileRows, "fused.cuh out of sync");
 constexpr uint32_t kFxMaxMoves = 2046;  // tag layout: move 11 bits | row lane 5 bits | in-row rank 12 bits
-constexpr int kFxSurvSlotsDefault = 16; // survivor slots per lane between two exact-search rounds
+constexpr int kFxSurvSlotsDefault = 24; // survivor slots per lane between two exact-search rounds
 constexpr int kFxMaxCtasPerSM = 8;
 constexpr size_t kFxScratchBudget = 512ull << 20;  // hit-list scratch never exceeds this
 
@@ -61,7 +62,7 @@ struct FusedArgs {
   long long diag_c0;
   int surv_slots;          // survivor slots per lane
   int planes_ok;           // every move mask has exactly two bits: stage A on bit planes
-  uint2 *scratch;          // [gridDim.x * kFxWarps][scratch_per_warp] hit lists {position, tag}
+  uint2 *scratch;          // [gridDim.x * kFxWarps][2][scratch_per_warp] hit lists {position, tag}
   uint32_t scratch_per_warp;
   unsigned long long *status;  // [num_tiles] look-back words (zeroed)
   unsigned int *ticket;        // zeroed
@@ -189,16 +190,21 @@ __global__ void __launch_bounds__(256) build_index_kernel(const uint64_t *__rest
 __device__ __forceinline__ int32_t search_one(const FusedArgs &a, uint64_t c) {
   const uint32_t *bucket = a.starts + (c >> a.tshift);
   uint32_t lo = ldg_stream_u32(bucket), hi = ldg_stream_u32(bucket + 1);
-  while (hi - lo > 8) {  // pathological bucket: bisect down to a short scan
-    const uint32_t mid = lo + ((hi - lo) >> 1);
-    if (ldg_stream_u64(&a.spins[mid]) < c)
-      lo = mid + 1;
-    else
-      hi = mid + 1;
+  if (hi - lo > 16) {  // pathological bucket: bisect down to a short scan
+    do {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      if (ldg_stream_u64(&a.spins[mid]) < c)
+        lo = mid + 1;
+      else
+        hi = mid + 1;
+    } while (hi - lo > 8);
   }
-  for (; lo < hi; ++lo) {
-    const uint64_t k = ldg_stream_u64(&a.spins[lo]);
-    if (k >= c) return k == c ? static_cast<int32_t>(lo) : -1;
+  for (; lo < hi; lo += 2) {  // two keys per step (independent loads)
+    const uint64_t k0 = ldg_stream_u64(&a.spins[lo]);
+    const bool second = lo + 1 < hi;
+    const uint64_t k1 = second ? ldg_stream_u64(&a.spins[lo + 1]) : 0ull;
+    if (k0 >= c) return k0 == c ? static_cast<int32_t>(lo) : -1;
+    if (second && k1 >= c) return k1 == c ? static_cast<int32_t>(lo + 1) : -1;
   }
   return -1;
 }
@@ -266,13 +272,16 @@ __host__ __device__ inline FxLayout fx_layout(int n_moves, int n_words, int n_gr
   const uint32_t surv_bytes = static_cast<uint32_t>(surv_slots) * 64u;
   L.w_surv = take(surv_bytes > 256u ? surv_bytes : 256u);                              // | planes u32[64]
   L.w_amask = take(n_words * 128u > 384u ? static_cast<uint32_t>(n_words) * 128u : 384u);  // | abs_psi f64[32], row_off u32[32]
-  L.w_pre = take(36u * 4u);
+  L.w_pre = take(64u * 4u);  // exclusive prefix of survivor counts [32] | owner board [32]
   L.w_cnt = take(32u * 4u);
   L.per_warp = off;
   return L;
 }
 
-__global__ void __launch_bounds__(kFxThreads) extract_csr_kernel(const FusedArgs a) {
+#ifndef ASP_FX_MIN_CTAS
+#define ASP_FX_MIN_CTAS 6
+#endif
+__global__ void __launch_bounds__(kFxThreads, ASP_FX_MIN_CTAS) extract_csr_kernel(const FusedArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const FxLayout L = fx_layout(a.n_moves, a.n_words, a.n_groups, a.n_diag, a.planes_ok, a.surv_slots);
   uint2 *s_cand = reinterpret_cast<uint2 *>(smem_raw + L.cand);
@@ -293,9 +302,6 @@ __global__ void __launch_bounds__(kFxThreads) extract_csr_kernel(const FusedArgs
   uint32_t *const w_row_off = reinterpret_cast<uint32_t *>(wbase + L.w_amask + 256);
   uint32_t *const w_pre = reinterpret_cast<uint32_t *>(wbase + L.w_pre);
   uint32_t *const w_cnt = reinterpret_cast<uint32_t *>(wbase + L.w_cnt);
-  __shared__ unsigned int s_tile;
-  __shared__ unsigned int s_warp_total[kFxWarps];
-  __shared__ unsigned long long s_tile_base;
 
   for (int k = threadIdx.x; k < a.n_words * 32; k += kFxThreads) {
     uint2 cand = make_uint2(0u, 0u);
@@ -323,23 +329,36 @@ __global__ void __launch_bounds__(kFxThreads) extract_csr_kernel(const FusedArgs
   } else {
     for (int k = threadIdx.x; k < a.n_diag; k += kFxThreads) s_diag[k] = a.diag[k];
   }
-  uint2 *const my_list = a.scratch + (static_cast<size_t>(blockIdx.x) * kFxWarps + warp) * a.scratch_per_warp;
+  __syncthreads();  // tables loaded; from here on the warps run independently
+  uint2 *const my_lists = a.scratch + (static_cast<size_t>(blockIdx.x) * kFxWarps + warp) * 2 * a.scratch_per_warp;  // two hit lists
   const uint32_t slots = static_cast<uint32_t>(a.surv_slots);
   const uint32_t cand_base = smem_addr(s_cand);
   const uint32_t amask_base = smem_addr(w_amask) + lane * 4u;
   const uint32_t surv_base = smem_addr(w_surv) + lane * 2u;
+  const uint32_t surv_limit = surv_base + (slots >= 8u ? slots - 4u : 0u) * 64u;  // fill level checked every 4 candidates
 
+  // One tile of lag: a warp runs stages A-C of its NEXT tile before it fetches the CSR offset of
+  // the tile it has just counted.  The offset needs every earlier tile's count, and a warp that
+  // finished early would otherwise spin for the slowest of its predecessors; by the time the
+  // next tile is counted they are done.  (Counts are published right after stage C and never
+  // wait for anything, so the scheme cannot deadlock.)
+  bool have_pending = false;
+  uint64_t pend_tile = 0;
+  uint32_t pend_packed = 0, pend_count = 0, parity = 0;
   for (;;) {
-    __syncthreads();  // previous tile fully written; tables loaded
-    if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);
-    __syncthreads();
-    const uint64_t tile = s_tile;
-    if (tile >= a.num_tiles) break;
-
-    const uint64_t r = tile * kFxTileRows + threadIdx.x;
+    // a tile = the 32 rows of one warp; tiles are handed out in order by an atomic ticket
+    uint32_t ticket = 0;
+    if (lane == 0) ticket = atomicAdd(a.ticket, 1u);
+    const uint64_t tile = __shfl_sync(0xffffffffu, ticket, 0);
+    const bool have_tile = tile < a.num_tiles;
+    if (!have_tile && !have_pending) break;
+    uint2 *const my_list = my_lists + static_cast<size_t>(parity) * a.scratch_per_warp;
+    uint32_t packed_cnt = 0, list_count = 0;
+    if (have_tile) {
+    const uint64_t r = tile * kFxTileRows + lane;
     const bool live = r < a.num_rows;
     const uint64_t row = a.row_begin + r;
-    const uint64_t s = live ? ldg_stream_u64(&a.spins[row]) : 0ull;
+    const uint64_t s = live ? __ldg(&a.spins[row]) : 0ull;
     const uint32_t s_lo = static_cast<uint32_t>(s), s_hi = static_cast<uint32_t>(s >> 32);
     const bool generates = live && (s & ~a.state_mask) == 0;  // keys wider than the word have no images in the basis
 
@@ -370,7 +389,6 @@ __global__ void __launch_bounds__(kFxThreads) extract_csr_kernel(const FusedArgs
     __syncwarp();  // planes are dead from here: their bytes become the survivor slots
 
     // =========================== B + C: sieve, search, record ================================
-    uint32_t list_count = 0;          // warp-uniform
     uint32_t surv_addr = surv_base;   // next free survivor slot of this lane
 
     // C: deal the waiting survivors evenly over the lanes, search them exactly, record the hits
@@ -383,16 +401,22 @@ __global__ void __launch_bounds__(kFxThreads) extract_csr_kernel(const FusedArgs
         if (lane >= o) incl += t;
       }
       const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-      w_pre[lane] = incl - h;
-      if (lane == 31) w_pre[32] = total;
-      __syncwarp();
+      const uint32_t excl = incl - h;
+      w_pre[lane] = excl;
+      uint32_t carry = 0;  // lane that owns the survivor just before this batch
       for (uint32_t base = 0; base < total; base += 32) {
+        // the lane whose survivors include number base + lane: lanes that START inside the batch
+        // leave their index at the start position, everyone looks up the nearest start at or below
+        const uint32_t start = excl - base;
+        const bool starts_here = h != 0 && start < 32u;
+        const uint32_t heads = __reduce_or_sync(0xffffffffu, starts_here ? 1u << start : 0u);
+        if (starts_here) w_pre[32 + start] = lane;  // w_pre[32..] doubles as the owner board (entries 32..63)
+        __syncwarp();
         const uint32_t e = base + lane;
         const bool valid = e < total;
-        uint32_t src = 0;  // last lane whose first survivor is at or before e
-#pragma unroll
-        for (int step = 16; step >= 1; step >>= 1)
-          if (w_pre[src + step] <= e) src += step;
+        const uint32_t at_or_below = heads & (0xFFFFFFFFu >> (31u - lane));
+        const uint32_t src = at_or_below ? w_pre[32 + (31 - __clz(at_or_below))] : carry;
+        carry = __shfl_sync(0xffffffffu, src, 31);
         const uint32_t m = valid ? (static_cast<uint32_t>(w_surv[(e - w_pre[src]) * 32 + src]) - (cand_base >> 3)) & 0xFFFFu : 0u;
         const uint64_t s_src = (static_cast<uint64_t>(__shfl_sync(0xffffffffu, s_hi, src)) << 32) | __shfl_sync(0xffffffffu, s_lo, src);
         int32_t pos = -1;
@@ -421,22 +445,18 @@ __global__ void __launch_bounds__(kFxThreads) extract_csr_kernel(const FusedArgs
     {
       // B: every lane walks the set bits of its own mask words.  A candidate needs its filter
       // word (index = (s >> fshift) ^ (flip >> fshift)) and its hash (= hash(s) ^ hash(flip)):
-      // one 8-byte table read and two XORs.  At most one survivor slot is used per iteration,
-      // so a warp-uniform countdown tells when the slots may be full.
+      // one 8-byte table read and two XORs.
       const uint32_t s_idx = static_cast<uint32_t>(s >> a.fshift), s_hash = filter_hash(s);
       uint32_t amask_addr = amask_base, tab_addr = cand_base;
-      int left = a.n_words - 1;  // mask words after the current one
+      const uint32_t amask_last = amask_base + (a.n_words > 0 ? a.n_words - 1 : 0) * 128u;
       uint32_t cur = a.n_words ? lds_u32(amask_addr) : 0u;
-      uint32_t room = slots;
-      for (;;) {
-        if (cur == 0 && left > 0) {  // at most one word per iteration
+      auto step = [&]() {  // harmless for a lane that has run out of moves
+        if (cur == 0 && amask_addr < amask_last) {  // at most one word per step
           amask_addr += 128;
           tab_addr += 256;
-          --left;
           cur = lds_u32(amask_addr);
         }
         const bool act = cur != 0;
-        if (!__any_sync(0xffffffffu, act || left > 0)) break;
         const uint32_t entry_addr = tab_addr + ((static_cast<uint32_t>(__ffs(static_cast<int>(cur)) - 1) & 31u) << 3);
         cur &= cur - 1;
         const uint2 entry = lds_table_u2(entry_addr);
@@ -447,47 +467,72 @@ __global__ void __launch_bounds__(kFxThreads) extract_csr_kernel(const FusedArgs
           sts_u16(surv_addr, entry_addr >> 3);
           surv_addr += 64;
         }
-        if (--room == 0) {
-          __syncwarp();
-          flush();
-          room = slots;
+      };
+      if (slots >= 8u) {
+        // four candidates per lane between two looks at the loop condition and the fill level
+        while (__any_sync(0xffffffffu, cur != 0 || amask_addr < amask_last)) {
+          step();
+          step();
+          step();
+          step();
+          if (__any_sync(0xffffffffu, surv_addr > surv_limit)) {
+            __syncwarp();
+            flush();
+          }
+        }
+      } else {  // tiny survivor lists (tests): flush after every survivor
+        while (__any_sync(0xffffffffu, cur != 0 || amask_addr < amask_last)) {
+          step();
+          if (__any_sync(0xffffffffu, surv_addr != surv_base)) {
+            __syncwarp();
+            flush();
+          }
         }
       }
       __syncwarp();
       flush();
     }
-    const uint32_t packed_cnt = w_cnt[lane];
-    const uint32_t my_cnt = (packed_cnt & 0xFFFFu) + (live ? 1u : 0u);
-    const uint32_t down_cnt = packed_cnt >> 16;
+    packed_cnt = w_cnt[lane] + (live ? 1u : 0u);  // couplings of the row (diagonal included) | those below the diagonal << 16
+    // publish the tile's count (tile 0: its inclusive prefix) -- never waits
+    uint32_t total = packed_cnt & 0xFFFFu;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if (lane == 0) {
+      if (tile == 0)
+        st_status(&a.status[0], kFlagPrefix | ((a.base_in ? *a.base_in : 0ull) + total));
+      else
+        st_status(&a.status[tile], kFlagAggregate | total);
+    }
+    }  // have_tile
 
-    // =========================== D: tile offset by decoupled look-back =======================
-    uint32_t incl = my_cnt;
+    if (have_pending) {
+      // ======================= D: CSR offset of the previous tile by decoupled look-back =====
+      const uint64_t ptile = pend_tile;
+      const uint64_t r = ptile * kFxTileRows + lane;
+      const bool live = r < a.num_rows;
+      const uint64_t row = a.row_begin + r;
+      const uint32_t my_cnt = pend_packed & 0xFFFFu, down_cnt = pend_packed >> 16;
+      uint32_t incl = my_cnt;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    if (lane == 31) s_warp_total[warp] = incl;
-    __syncthreads();
-    uint32_t warp_base = 0, tile_total = 0;
-#pragma unroll
-    for (int w = 0; w < kFxWarps; ++w) {
-      if (w < static_cast<int>(warp)) warp_base += s_warp_total[w];
-      tile_total += s_warp_total[w];
-    }
-    if (warp == 0) {
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const uint32_t tile_total = __shfl_sync(0xffffffffu, incl, 31);
       unsigned long long exclusive = 0;
-      if (tile == 0) {
+      if (ptile == 0) {
         if (a.base_in) exclusive = *a.base_in;
-        if (lane == 0) st_status(&a.status[0], kFlagPrefix | (exclusive + tile_total));
       } else {
-        if (lane == 0) st_status(&a.status[tile], kFlagAggregate | tile_total);
-        int64_t look = static_cast<int64_t>(tile) - 1;  // window [look - 31, look]
+        int64_t look = static_cast<int64_t>(ptile) - 1;  // window [look - 31, look]
         for (;;) {
           const int64_t idx = look - lane;
           unsigned long long st = kFlagPrefix;  // virtual tiles before tile 0: prefix 0
           if (idx >= 0) {
-            while (((st = ld_status(&a.status[idx])) >> 62) == 0) __nanosleep(40);
+            unsigned backoff = 32;
+            while (((st = ld_status(&a.status[idx])) >> 62) == 0) {
+              __nanosleep(backoff);
+              if (backoff < 1024) backoff <<= 1;
+            }
           }
           const uint32_t has_prefix = __ballot_sync(0xffffffffu, (st >> 62) == 2);
           const uint32_t first = has_prefix ? static_cast<uint32_t>(__ffs(has_prefix)) - 1u : 32u;  // nearest tile with a prefix
@@ -498,49 +543,53 @@ __global__ void __launch_bounds__(kFxThreads) extract_csr_kernel(const FusedArgs
           if (has_prefix) break;
           look -= 32;
         }
-        if (lane == 0) st_status(&a.status[tile], kFlagPrefix | (exclusive + tile_total));
+        if (lane == 0) st_status(&a.status[ptile], kFlagPrefix | (exclusive + tile_total));
       }
-      if (lane == 0) {
-        s_tile_base = exclusive;
-        if (tile == a.num_tiles - 1) {
-          a.indptr[a.num_rows] = static_cast<int64_t>(exclusive + tile_total);
-          *a.nnz_out = exclusive + tile_total;
-          if (a.nnz_mirror) {
-            *a.nnz_mirror = exclusive + tile_total;
-            __threadfence_system();
-          }
+      if (lane == 0 && ptile == a.num_tiles - 1) {
+        a.indptr[a.num_rows] = static_cast<int64_t>(exclusive + tile_total);
+        *a.nnz_out = exclusive + tile_total;
+        if (a.nnz_mirror) {
+          *a.nnz_mirror = exclusive + tile_total;
+          __threadfence_system();
         }
       }
-    }
-    __syncthreads();
-    const uint64_t tile_base = s_tile_base;
+      const uint64_t tile_base = exclusive;
 
-    // =========================== write the tile's CSR rows ===================================
-    // (the apply masks are dead: their bytes now hold the row offsets and amplitudes)
-    const uint32_t my_off = warp_base + incl - my_cnt;  // row start relative to the tile
-    const double a_i = live ? fabs(ldg_stream_f64(&a.psi[row])) : 0.0;
-    w_row_off[lane] = my_off;
-    w_abs_psi[lane] = a_i;
-    if (live) a.indptr[r] = static_cast<int64_t>(tile_base + my_off);
-    __syncwarp();
-    for (uint32_t k = lane; k < list_count; k += 32) {
-      const uint2 entry = my_list[k];
-      const uint32_t pos = entry.x, m = entry.y & 0x7FFu, src = (entry.y >> 11) & 31u, rank = entry.y >> 16;
-      const uint64_t dest = tile_base + w_row_off[src] + rank;
-      if (dest < a.capacity) {
-        a.indices[dest] = static_cast<int32_t>(pos);
-        a.data[dest] = s_coef[m] * (w_abs_psi[src] * fabs(ldg_stream_f64(&a.psi[pos])));
+      // ======================= write the previous tile's CSR rows ============================
+      // (the apply masks are dead: their bytes now hold the row offsets and amplitudes)
+      const uint2 *const list = my_lists + static_cast<size_t>(parity ^ 1u) * a.scratch_per_warp;
+      const uint32_t my_off = incl - my_cnt;  // row start relative to the tile
+      const uint64_t s = live ? __ldg(&a.spins[row]) : 0ull;
+      const double a_i = live ? fabs(__ldg(&a.psi[row])) : 0.0;
+      w_row_off[lane] = my_off;
+      w_abs_psi[lane] = a_i;
+      if (live) a.indptr[r] = static_cast<int64_t>(tile_base + my_off);
+      __syncwarp();
+      for (uint32_t k = lane; k < pend_count; k += 32) {
+        const uint2 entry = list[k];
+        const uint32_t pos = entry.x, m = entry.y & 0x7FFu, src = (entry.y >> 11) & 31u, rank = entry.y >> 16;
+        const uint64_t dest = tile_base + w_row_off[src] + rank;
+        if (dest < a.capacity) {
+          a.indices[dest] = static_cast<int32_t>(pos);
+          a.data[dest] = s_coef[m] * (w_abs_psi[src] * fabs(ldg_stream_f64(&a.psi[pos])));
+        }
       }
-    }
-    if (live) {
-      const double d = a.n_groups >= 0 ? diagonal_closed_form(s, s_groups, a.n_groups, a.diag_c0, a.diag_scale)
-                                       : diagonal_element(s, s_diag, a.n_diag);
-      const uint64_t dest = tile_base + my_off + down_cnt;
-      if (dest < a.capacity) {
-        a.indices[dest] = static_cast<int32_t>(row);
-        a.data[dest] = d * (a_i * a_i);
+      if (live) {
+        const double d = a.n_groups >= 0 ? diagonal_closed_form(s, s_groups, a.n_groups, a.diag_c0, a.diag_scale)
+                                         : diagonal_element(s, s_diag, a.n_diag);
+        const uint64_t dest = tile_base + my_off + down_cnt;
+        if (dest < a.capacity) {
+          a.indices[dest] = static_cast<int32_t>(row);
+          a.data[dest] = d * (a_i * a_i);
+        }
       }
+      __syncwarp();  // the row offsets are read by all lanes; the next tile overwrites their bytes
     }
+    have_pending = have_tile;
+    pend_tile = tile;
+    pend_packed = packed_cnt;
+    pend_count = list_count;
+    parity ^= 1u;
   }
 }
 
@@ -579,7 +628,7 @@ static FusedWorkspace carve_fused(void *base, const asp_operator *op, uint64_t n
   w.num_words = 1ull << fbits;
   const uint64_t tiles = (num_rows + kFxTileRows - 1) / kFxTileRows + kFxMaxChunks;
   w.scratch_per_warp = std::max<uint32_t>(32u * static_cast<uint32_t>(op->moves.size()), 32u);
-  const size_t per_cta = static_cast<size_t>(w.scratch_per_warp) * kFxWarps * sizeof(uint2);
+  const size_t per_cta = static_cast<size_t>(w.scratch_per_warp) * 2 * kFxWarps * sizeof(uint2);  // two hit lists per warp
   uint64_t ctas = std::min<uint64_t>(static_cast<uint64_t>(kNumSMs) * kFxMaxCtasPerSM, std::max<uint64_t>(tiles, 1));
   ctas = std::min<uint64_t>(ctas, std::max<uint64_t>(kFxScratchBudget / per_cta, kNumSMs));
   w.scratch_ctas = static_cast<uint32_t>(ctas);

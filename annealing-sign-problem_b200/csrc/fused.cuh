@@ -5,7 +5,7 @@
 
 namespace asp {
 
-constexpr int kFusedTileRows = 256;  // rows per tile; row chunks start at multiples of this
+constexpr int kFusedTileRows = 32;   // rows per tile; row chunks start at multiples of this
 constexpr int kFusedMaxChunks = 32;
 
 size_t fused_workspace_bytes(const asp_operator *op, uint64_t n_total, uint64_t num_rows);

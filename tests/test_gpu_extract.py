@@ -337,10 +337,10 @@ def test_single_pass_kernel_equals_two_pass_bitwise(system, n, seed):
     spins = synthetic.cluster_closed_states(op, n, seed, DEV)
     psi = synthetic.synthetic_amplitudes(spins.shape[0], seed, device=DEV)
     ref = common.extract_csr_two_pass_device(op, spins, psi)
-    # automatic survivor lists; tiny ones (1 and 3 slots per lane) force many exact-search rounds per
+    # automatic survivor lists; tiny ones (1, 3 and 8 slots per lane) force many exact-search rounds per
     # tile; a coarse filter lets most misses through to the exact search, a fine one almost none;
     # stage A lane by lane instead of on bit planes
-    for cap, tuning in [(0, (0, 0, 0)), (32, (0, 0, 0)), (96, (-6, -3, 0)), (0, (3, 2, 1)), (0, (-30, -30, 1))]:
+    for cap, tuning in [(0, (0, 0, 0)), (32, (0, 0, 0)), (96, (-6, -3, 0)), (256, (-4, 0, 0)), (0, (3, 2, 1)), (0, (-30, -30, 1))]:
         lib().asp_debug_set_hit_list_capacity(cap)
         lib().asp_debug_set_extract_tuning(*tuning)
         try:
