@@ -43,7 +43,18 @@ constexpr unsigned long long kFlagAggregate = 1ull << 62;
 constexpr unsigned long long kFlagPrefix = 2ull << 62;
 constexpr unsigned long long kValueMask = (1ull << 62) - 1;
 
+// Shared-memory layout.  CTA-wide tables, then one block per warp; inside a warp's block the
+// bit planes (stage A) share their bytes with the survivor slots (stages B/C) and the apply
+// masks (A/B) with the row offsets and amplitudes of the write phase.
+struct FxLayout {
+  uint32_t cand, flip, coef, desc, mask, need, groups, diag;  // byte offsets of the tables
+  uint32_t tables;                                            // bytes of all tables
+  uint32_t w_surv, w_amask, w_pre, w_cnt;                     // byte offsets inside a warp's block
+  uint32_t per_warp;
+};
+
 struct FusedArgs {
+  FxLayout layout;         // computed on the host: the kernel reads the offsets from constant memory
   const uint64_t *spins;   // [n_total] ascending, unique
   const double *psi;
   const uint32_t *starts;  // [2^tbits + 1] first position with key >= bucket << tshift
@@ -149,7 +160,7 @@ __device__ __forceinline__ double ldg_stream_f64(const double *p) {
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));  // ordered with the other volatile asm, transparent to plain loads
   return v;
 }
 __device__ __forceinline__ uint2 lds_table_u2(uint32_t addr) {  // read-only tables: free to schedule
@@ -158,7 +169,7 @@ __device__ __forceinline__ uint2 lds_table_u2(uint32_t addr) {  // read-only tab
   return v;
 }
 __device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
-  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(static_cast<unsigned short>(v)) : "memory");
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(static_cast<unsigned short>(v)));
 }
 
 // Index of the sorted basis: first-position table + Bloom filter, one thread per key.
@@ -241,16 +252,6 @@ __device__ __forceinline__ double diagonal_closed_form(uint64_t s, const DiagGro
   return scalbn(static_cast<double>(acc), -scale);
 }
 
-// Shared-memory layout.  CTA-wide tables, then one block per warp; inside a warp's block the
-// bit planes (stage A) share their bytes with the survivor slots (stages B/C) and the apply
-// masks (A/B) with the row offsets and amplitudes of the write phase.
-struct FxLayout {
-  uint32_t cand, flip, coef, desc, mask, need, groups, diag;  // byte offsets of the tables
-  uint32_t tables;                                            // bytes of all tables
-  uint32_t w_surv, w_amask, w_pre, w_cnt;                     // byte offsets inside a warp's block
-  uint32_t per_warp;
-};
-
 __host__ __device__ inline FxLayout fx_layout(int n_moves, int n_words, int n_groups, int n_diag, int planes_ok, int surv_slots) {
   FxLayout L;
   uint32_t off = 0;
@@ -283,7 +284,7 @@ __host__ __device__ inline FxLayout fx_layout(int n_moves, int n_words, int n_gr
 #endif
 __global__ void __launch_bounds__(kFxThreads, ASP_FX_MIN_CTAS) extract_csr_kernel(const FusedArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const FxLayout L = fx_layout(a.n_moves, a.n_words, a.n_groups, a.n_diag, a.planes_ok, a.surv_slots);
+  const FxLayout &L = a.layout;
   uint2 *s_cand = reinterpret_cast<uint2 *>(smem_raw + L.cand);
   uint64_t *s_flip = reinterpret_cast<uint64_t *>(smem_raw + L.flip);
   double *s_coef = reinterpret_cast<double *>(smem_raw + L.coef);
@@ -450,31 +451,48 @@ __global__ void __launch_bounds__(kFxThreads, ASP_FX_MIN_CTAS) extract_csr_kerne
       uint32_t amask_addr = amask_base, tab_addr = cand_base;
       const uint32_t amask_last = amask_base + (a.n_words > 0 ? a.n_words - 1 : 0) * 128u;
       uint32_t cur = a.n_words ? lds_u32(amask_addr) : 0u;
-      auto step = [&]() {  // harmless for a lane that has run out of moves
+      // first half of a step: next set bit -> table entry -> filter word on its way
+      auto fetch = [&](uint32_t &entry_addr, uint32_t &hsh, uint2 &word) {  // harmless for a lane that has run out of moves
         if (cur == 0 && amask_addr < amask_last) {  // at most one word per step
           amask_addr += 128;
           tab_addr += 256;
           cur = lds_u32(amask_addr);
         }
         const bool act = cur != 0;
-        const uint32_t entry_addr = tab_addr + ((static_cast<uint32_t>(__ffs(static_cast<int>(cur)) - 1) & 31u) << 3);
+        entry_addr = tab_addr + ((static_cast<uint32_t>(__ffs(static_cast<int>(cur)) - 1) & 31u) << 3);
         cur &= cur - 1;
         const uint2 entry = lds_table_u2(entry_addr);
-        const uint32_t hsh = s_hash ^ entry.y;
-        uint2 word = make_uint2(0u, 0u);
+        hsh = s_hash ^ entry.y;
+        word = make_uint2(0u, 0u);
         if (act) word = ldg_filter_u2(a.filter + (s_idx ^ entry.x));
+      };
+      // second half: both hashed bits set -> the candidate survives into this lane's slots
+      auto sieve = [&](uint32_t entry_addr, uint32_t hsh, uint2 word) {
         if (__funnelshift_r(word.x, 0u, hsh) & __funnelshift_r(word.y, 0u, hsh >> 8) & 1u) {
           sts_u16(surv_addr, entry_addr >> 3);
           surv_addr += 64;
         }
       };
+      auto step = [&]() {
+        uint32_t e0, h0;
+        uint2 w0;
+        fetch(e0, h0, w0);
+        sieve(e0, h0, w0);
+      };
       if (slots >= 8u) {
-        // four candidates per lane between two looks at the loop condition and the fill level
+        // four candidates per lane between two looks at the loop condition and the fill level,
+        // their four filter words in flight together
         while (__any_sync(0xffffffffu, cur != 0 || amask_addr < amask_last)) {
-          step();
-          step();
-          step();
-          step();
+          uint32_t e0, e1, e2, e3, h0, h1, h2, h3;
+          uint2 w0, w1, w2, w3;
+          fetch(e0, h0, w0);
+          fetch(e1, h1, w1);
+          fetch(e2, h2, w2);
+          fetch(e3, h3, w3);
+          sieve(e0, h0, w0);
+          sieve(e1, h1, w1);
+          sieve(e2, h2, w2);
+          sieve(e3, h3, w3);
           if (__any_sync(0xffffffffu, surv_addr > surv_limit)) {
             __syncwarp();
             flush();
@@ -536,10 +554,16 @@ __global__ void __launch_bounds__(kFxThreads, ASP_FX_MIN_CTAS) extract_csr_kerne
           }
           const uint32_t has_prefix = __ballot_sync(0xffffffffu, (st >> 62) == 2);
           const uint32_t first = has_prefix ? static_cast<uint32_t>(__ffs(has_prefix)) - 1u : 32u;  // nearest tile with a prefix
-          unsigned long long contrib = lane <= first ? (st & kValueMask) : 0ull;
+          // counts of the tiles in front of it (each < 2^16) add up in 32 bits; the prefix itself is 64-bit
+          uint32_t counts = lane < first ? static_cast<uint32_t>(st) : 0u;
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-          exclusive += contrib;
+          for (int o = 16; o > 0; o >>= 1) counts += __shfl_xor_sync(0xffffffffu, counts, o);
+          exclusive += counts;
+          if (has_prefix) {
+            const uint32_t p_lo = __shfl_sync(0xffffffffu, static_cast<uint32_t>(st), first);
+            const uint32_t p_hi = __shfl_sync(0xffffffffu, static_cast<uint32_t>(st >> 32), first);
+            exclusive += ((static_cast<unsigned long long>(p_hi) << 32) | p_lo) & kValueMask;
+          }
           if (has_prefix) break;
           look -= 32;
         }
@@ -621,7 +645,7 @@ static FusedWorkspace carve_fused(void *base, const asp_operator *op, uint64_t n
   tbits = std::min(tbits, key_bits);
   w.tshift = key_bits - tbits;
   w.num_buckets = 1ull << tbits;
-  int fbits = lg - 3 + g_filter_bits_delta;  // 8 bytes per 8 keys
+  int fbits = lg - 1 + g_filter_bits_delta;  // 8 bytes per 2 keys: ~1 % false positives
   fbits = std::max(4, std::min(fbits, 27));
   fbits = std::min(fbits, key_bits);
   w.fshift = key_bits - fbits;
@@ -731,6 +755,7 @@ int fused_launch(const asp_operator *op, uint64_t n_total, const uint64_t *d_spi
   a.nnz_mirror = nnz_mirror;
   a.base_in = chunk == 0 ? nullptr : w.totals + (chunk - 1);
   const FxLayout layout = fx_layout(a.n_moves, a.n_words, a.n_groups, a.n_diag, a.planes_ok, slots);
+  a.layout = layout;
   const size_t smem = layout.tables + static_cast<size_t>(layout.per_warp) * kFxWarps;
   ASP_REQUIRE(smem <= 200 * 1024, "operator too large for the fused kernel's shared-memory tables");
   ASP_CUDA_CHECK(cudaFuncSetAttribute(extract_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));

@@ -23,7 +23,7 @@ def main():
     p = argparse.ArgumentParser()
     p.add_argument("--states", type=int, default=10_000_000)
     p.add_argument("--system", default="heisenberg_kagome_36")
-    p.add_argument("--combos", default="0,0,0,0;0,0,1,0;-1,0,0,0;1,0,0,0;2,0,0,0;0,-1,0,0;0,1,0,0;0,0,0,256;0,0,0,1024")
+    p.add_argument("--combos", default="0,0,0,0;0,0,1,0;-2,0,0,0;-1,0,0,0;1,0,0,0;0,-1,0,0;0,1,0,0;0,0,0,256;0,0,0,512;0,0,0,1024")
     args = p.parse_args()
     dev = torch.device("cuda", 0)
     cfg = asp.ls.load_config(asp.ls.system_path(args.system))
