@@ -37,7 +37,14 @@ static_assert(kFxTileRows == kFusedTileRows, "fused.cuh out of sync");
 constexpr uint32_t kFxMaxMoves = 2046;  // tag layout: move 11 bits | row lane 5 bits | in-row rank 12 bits
 constexpr int kFxSurvSlotsDefault = 24; // survivor slots per lane between two exact-search rounds
 constexpr int kFxMaxCtasPerSM = 8;
-constexpr size_t kFxScratchBudget = 512ull << 20;  // hit-list scratch never exceeds this
+#ifndef ASP_FX_LAG
+#define ASP_FX_LAG 1
+#endif
+#ifndef ASP_FX_SCRATCH_MB
+#define ASP_FX_SCRATCH_MB 512
+#endif
+constexpr int kFxLag = ASP_FX_LAG;  // tiles a warp counts ahead of the tile whose CSR offset it fetches
+constexpr size_t kFxScratchBudget = static_cast<size_t>(ASP_FX_SCRATCH_MB) << 20;  // hit-list scratch never exceeds this
 
 constexpr unsigned long long kFlagAggregate = 1ull << 62;
 constexpr unsigned long long kFlagPrefix = 2ull << 62;
@@ -49,7 +56,7 @@ constexpr unsigned long long kValueMask = (1ull << 62) - 1;
 struct FxLayout {
   uint32_t cand, flip, coef, desc, mask, need, groups, diag;  // byte offsets of the tables
   uint32_t tables;                                            // bytes of all tables
-  uint32_t w_surv, w_amask, w_pre, w_cnt;                     // byte offsets inside a warp's block
+  uint32_t w_surv, w_amask, w_pre, w_cnt, w_pend;             // byte offsets inside a warp's block
   uint32_t per_warp;
 };
 
@@ -73,7 +80,7 @@ struct FusedArgs {
   long long diag_c0;
   int surv_slots;          // survivor slots per lane
   int planes_ok;           // every move mask has exactly two bits: stage A on bit planes
-  uint2 *scratch;          // [gridDim.x * kFxWarps][2][scratch_per_warp] hit lists {position, tag}
+  uint2 *scratch;          // [gridDim.x * kFxWarps][kFxLag + 1][scratch_per_warp] hit lists {position, tag}
   uint32_t scratch_per_warp;
   unsigned long long *status;  // [num_tiles] look-back words (zeroed)
   unsigned int *ticket;        // zeroed
@@ -275,6 +282,7 @@ __host__ __device__ inline FxLayout fx_layout(int n_moves, int n_words, int n_gr
   L.w_amask = take(n_words * 128u > 384u ? static_cast<uint32_t>(n_words) * 128u : 384u);  // | abs_psi f64[32], row_off u32[32]
   L.w_pre = take(64u * 4u);  // exclusive prefix of survivor counts [32] | owner board [32]
   L.w_cnt = take(32u * 4u);
+  L.w_pend = take(static_cast<uint32_t>(kFxLag) * 36u * 4u);  // per waiting tile: packed row counts [32], tile lo/hi, list length
   L.per_warp = off;
   return L;
 }
@@ -303,6 +311,7 @@ __global__ void __launch_bounds__(kFxThreads, ASP_FX_MIN_CTAS) extract_csr_kerne
   uint32_t *const w_row_off = reinterpret_cast<uint32_t *>(wbase + L.w_amask + 256);
   uint32_t *const w_pre = reinterpret_cast<uint32_t *>(wbase + L.w_pre);
   uint32_t *const w_cnt = reinterpret_cast<uint32_t *>(wbase + L.w_cnt);
+  uint32_t *const w_pend = reinterpret_cast<uint32_t *>(wbase + L.w_pend);
 
   for (int k = threadIdx.x; k < a.n_words * 32; k += kFxThreads) {
     uint2 cand = make_uint2(0u, 0u);
@@ -331,29 +340,29 @@ __global__ void __launch_bounds__(kFxThreads, ASP_FX_MIN_CTAS) extract_csr_kerne
     for (int k = threadIdx.x; k < a.n_diag; k += kFxThreads) s_diag[k] = a.diag[k];
   }
   __syncthreads();  // tables loaded; from here on the warps run independently
-  uint2 *const my_lists = a.scratch + (static_cast<size_t>(blockIdx.x) * kFxWarps + warp) * 2 * a.scratch_per_warp;  // two hit lists
+  uint2 *const my_lists = a.scratch + (static_cast<size_t>(blockIdx.x) * kFxWarps + warp) * (kFxLag + 1) * a.scratch_per_warp;  // kFxLag + 1 hit lists
   const uint32_t slots = static_cast<uint32_t>(a.surv_slots);
   const uint32_t cand_base = smem_addr(s_cand);
   const uint32_t amask_base = smem_addr(w_amask) + lane * 4u;
   const uint32_t surv_base = smem_addr(w_surv) + lane * 2u;
   const uint32_t surv_limit = surv_base + (slots >= 8u ? slots - 4u : 0u) * 64u;  // fill level checked every 4 candidates
 
-  // One tile of lag: a warp runs stages A-C of its NEXT tile before it fetches the CSR offset of
-  // the tile it has just counted.  The offset needs every earlier tile's count, and a warp that
-  // finished early would otherwise spin for the slowest of its predecessors; by the time the
-  // next tile is counted they are done.  (Counts are published right after stage C and never
-  // wait for anything, so the scheme cannot deadlock.)
-  bool have_pending = false;
-  uint64_t pend_tile = 0;
-  uint32_t pend_packed = 0, pend_count = 0, parity = 0;
+  // Lag: a warp runs stages A-C of its next kFxLag tiles before it fetches the CSR offset of a
+  // tile it has counted.  The offset needs every earlier tile's count, and a warp that finished
+  // early would otherwise spin for the slowest of its predecessors (the SM's warp arbiter is not
+  // fair, so some warps ARE much slower); by the time the next tiles are counted they are done.
+  // (Counts are published right after stage C and never wait for anything, so the scheme cannot
+  // deadlock.)  Waiting tiles keep their hit list in one of kFxLag + 1 scratch lists and their row
+  // counts in shared memory.
+  uint32_t taken = 0, waiting = 0;  // tiles this warp has counted / of those, not yet written (warp-uniform)
   for (;;) {
     // a tile = the 32 rows of one warp; tiles are handed out in order by an atomic ticket
     uint32_t ticket = 0;
     if (lane == 0) ticket = atomicAdd(a.ticket, 1u);
     const uint64_t tile = __shfl_sync(0xffffffffu, ticket, 0);
     const bool have_tile = tile < a.num_tiles;
-    if (!have_tile && !have_pending) break;
-    uint2 *const my_list = my_lists + static_cast<size_t>(parity) * a.scratch_per_warp;
+    if (!have_tile && waiting == 0) break;
+    uint2 *const my_list = my_lists + static_cast<size_t>(taken % (kFxLag + 1)) * a.scratch_per_warp;
     uint32_t packed_cnt = 0, list_count = 0;
     if (have_tile) {
     const uint64_t r = tile * kFxTileRows + lane;
@@ -523,9 +532,12 @@ __global__ void __launch_bounds__(kFxThreads, ASP_FX_MIN_CTAS) extract_csr_kerne
     }
     }  // have_tile
 
-    if (have_pending) {
-      // ======================= D: CSR offset of the previous tile by decoupled look-back =====
-      const uint64_t ptile = pend_tile;
+    if (waiting == kFxLag || (!have_tile && waiting != 0)) {
+      // ======================= D: CSR offset of the oldest waiting tile by decoupled look-back
+      const uint32_t oldest = taken - waiting;
+      const uint32_t *const pend = w_pend + (oldest % kFxLag) * 36;
+      const uint32_t pend_packed = pend[lane], pend_count = pend[34];
+      const uint64_t ptile = (static_cast<uint64_t>(pend[33]) << 32) | pend[32];
       const uint64_t r = ptile * kFxTileRows + lane;
       const bool live = r < a.num_rows;
       const uint64_t row = a.row_begin + r;
@@ -563,8 +575,8 @@ __global__ void __launch_bounds__(kFxThreads, ASP_FX_MIN_CTAS) extract_csr_kerne
             const uint32_t p_lo = __shfl_sync(0xffffffffu, static_cast<uint32_t>(st), first);
             const uint32_t p_hi = __shfl_sync(0xffffffffu, static_cast<uint32_t>(st >> 32), first);
             exclusive += ((static_cast<unsigned long long>(p_hi) << 32) | p_lo) & kValueMask;
+            break;
           }
-          if (has_prefix) break;
           look -= 32;
         }
         if (lane == 0) st_status(&a.status[ptile], kFlagPrefix | (exclusive + tile_total));
@@ -581,7 +593,7 @@ __global__ void __launch_bounds__(kFxThreads, ASP_FX_MIN_CTAS) extract_csr_kerne
 
       // ======================= write the previous tile's CSR rows ============================
       // (the apply masks are dead: their bytes now hold the row offsets and amplitudes)
-      const uint2 *const list = my_lists + static_cast<size_t>(parity ^ 1u) * a.scratch_per_warp;
+      const uint2 *const list = my_lists + static_cast<size_t>(oldest % (kFxLag + 1)) * a.scratch_per_warp;
       const uint32_t my_off = incl - my_cnt;  // row start relative to the tile
       const uint64_t s = live ? __ldg(&a.spins[row]) : 0ull;
       const double a_i = live ? fabs(__ldg(&a.psi[row])) : 0.0;
@@ -608,12 +620,20 @@ __global__ void __launch_bounds__(kFxThreads, ASP_FX_MIN_CTAS) extract_csr_kerne
         }
       }
       __syncwarp();  // the row offsets are read by all lanes; the next tile overwrites their bytes
+      --waiting;
     }
-    have_pending = have_tile;
-    pend_tile = tile;
-    pend_packed = packed_cnt;
-    pend_count = list_count;
-    parity ^= 1u;
+    if (have_tile) {  // the tile just counted joins the queue
+      uint32_t *const pend = w_pend + (taken % kFxLag) * 36;
+      pend[lane] = packed_cnt;
+      if (lane == 0) {
+        pend[32] = static_cast<uint32_t>(tile);
+        pend[33] = static_cast<uint32_t>(tile >> 32);
+        pend[34] = list_count;
+      }
+      __syncwarp();
+      ++taken;
+      ++waiting;
+    }
   }
 }
 
@@ -633,6 +653,9 @@ struct FusedWorkspace {
 };
 
 static int g_surv_entries_override = 0;
+// optional CUDA-event bracket around the extraction kernel alone (bench.py's roofline figure)
+static bool g_time_kernel = false;
+static cudaEvent_t g_ev_begin = nullptr, g_ev_end = nullptr;
 static int g_filter_bits_delta = 0, g_table_bits_delta = 0, g_stage_a_mode = 0;
 
 static FusedWorkspace carve_fused(void *base, const asp_operator *op, uint64_t n_total, uint64_t num_rows) {
@@ -652,7 +675,7 @@ static FusedWorkspace carve_fused(void *base, const asp_operator *op, uint64_t n
   w.num_words = 1ull << fbits;
   const uint64_t tiles = (num_rows + kFxTileRows - 1) / kFxTileRows + kFxMaxChunks;
   w.scratch_per_warp = std::max<uint32_t>(32u * static_cast<uint32_t>(op->moves.size()), 32u);
-  const size_t per_cta = static_cast<size_t>(w.scratch_per_warp) * 2 * kFxWarps * sizeof(uint2);  // two hit lists per warp
+  const size_t per_cta = static_cast<size_t>(w.scratch_per_warp) * (kFxLag + 1) * kFxWarps * sizeof(uint2);  // kFxLag + 1 hit lists per warp
   uint64_t ctas = std::min<uint64_t>(static_cast<uint64_t>(kNumSMs) * kFxMaxCtasPerSM, std::max<uint64_t>(tiles, 1));
   ctas = std::min<uint64_t>(ctas, std::max<uint64_t>(kFxScratchBudget / per_cta, kNumSMs));
   w.scratch_ctas = static_cast<uint32_t>(ctas);
@@ -764,8 +787,16 @@ int fused_launch(const asp_operator *op, uint64_t n_total, const uint64_t *d_spi
   ASP_REQUIRE(per_sm >= 1, "fused extraction kernel does not fit on an SM");
   const uint64_t resident = static_cast<uint64_t>(kNumSMs) * std::min(per_sm, kFxMaxCtasPerSM);
   const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(std::min<uint64_t>(a.num_tiles, resident), w.scratch_ctas));
+  if (g_time_kernel) {
+    if (!g_ev_begin) {
+      ASP_CUDA_CHECK(cudaEventCreate(&g_ev_begin));
+      ASP_CUDA_CHECK(cudaEventCreate(&g_ev_end));
+    }
+    ASP_CUDA_CHECK(cudaEventRecord(g_ev_begin, s));
+  }
   extract_csr_kernel<<<grid, kFxThreads, smem, s>>>(a);
   ASP_LAUNCH_CHECK();
+  if (g_time_kernel) ASP_CUDA_CHECK(cudaEventRecord(g_ev_end, s));
   return ASP_OK;
 }
 
@@ -785,6 +816,15 @@ void asp_debug_set_extract_tuning(int filter_bits_delta, int table_bits_delta, i
   g_filter_bits_delta = filter_bits_delta;
   g_table_bits_delta = table_bits_delta;
   g_stage_a_mode = stage_a_mode;
+}
+
+void asp_debug_time_extract_kernel(int enable) { g_time_kernel = enable != 0; }
+
+float asp_debug_last_extract_kernel_ms(void) {
+  float ms = -1.0f;
+  if (!g_ev_begin || cudaEventSynchronize(g_ev_end) != cudaSuccess) return -1.0f;
+  if (cudaEventElapsedTime(&ms, g_ev_begin, g_ev_end) != cudaSuccess) return -1.0f;
+  return ms;
 }
 
 size_t asp_extract_csr_workspace_bytes(asp_operator const *op, uint64_t n_total, uint64_t num_rows) {

@@ -47,12 +47,17 @@ def all_gather_blocks(local: torch.Tensor, total: int) -> torch.Tensor:
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return local
     world = dist.get_world_size()
-    longest = max(block(total, r, world)[1] for r in range(world))
+    sizes = [block(total, r, world)[1] for r in range(world)]
+    longest = max(sizes)
+    if min(sizes) == longest:  # equal blocks: gather straight into place, no padding, no copy
+        gathered = torch.empty(total, dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(gathered, local.contiguous())
+        return gathered
     padded = torch.zeros(longest, dtype=local.dtype, device=local.device)
     padded[: local.shape[0]] = local
     gathered = torch.empty(world * longest, dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(gathered, padded)
-    parts = [gathered[r * longest: r * longest + block(total, r, world)[1]] for r in range(world)]
+    parts = [gathered[r * longest: r * longest + sizes[r]] for r in range(world)]
     return torch.cat(parts)
 
 

@@ -9,8 +9,9 @@ heisenberg_kagome_36-shaped U(1) basis (36 spins, 72 bonds), 10^7 sampled states
 (weak scaling: the global sorted basis has N x 10^7 states and every rank builds the CSR
 rows of its contiguous row block against the full basis), synthetic log-normal amplitudes,
 cluster-closed sampled subset (about a tenth of all candidates are hits).  A step is one
-pass: [N>1: all-gather of basis words + amplitudes] -> bucket index -> single-pass extraction
-kernel (search once, decoupled look-back, CSR written in place).
+pass: [N>1: all-gather of basis words + amplitudes] -> index (first-position table + Bloom
+filter) -> single-pass extraction kernel (bit-plane applicability, filter pre-sieve, exact search
+of the survivors, decoupled look-back, CSR written in place).
 The annealing stage is timed separately on the same extracted model and reported under the
 "anneal" key.  One JSON line on stdout (rank 0).
 """
@@ -91,7 +92,7 @@ class ClockSampler:
             except Exception as exc:  # pragma: no cover
                 self.error = repr(exc)
                 return
-            time.sleep(0.005)
+            time.sleep(0.001)
 
     def stop(self):
         self.stop_flag.set()
@@ -273,6 +274,7 @@ def run_ours(args):
         if ev:
             ev[1].record()
             timers.append(ev)
+            kernel_only.append(float(lib().asp_debug_last_extract_kernel_ms()))
         m = int(nnz[0])
         return indptr, indices[:m], data[:m]
 
@@ -285,7 +287,8 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     launches0 = int(lib().asp_kernel_launch_count())
-    timers = []
+    timers, kernel_only = [], []
+    lib().asp_debug_time_extract_kernel(1)  # CUDA events around extract_csr_kernel alone, on its own stream
     D.barrier()
     torch.cuda.synchronize()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -298,7 +301,9 @@ def run_ours(args):
     total_ms = D.max_over_ranks(start.elapsed_time(end), dev)
     launches = int(lib().asp_kernel_launch_count()) - launches0
     clocks = sampler.stop() if rank == 0 else None
-    kernel_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in timers]))  # index + single-pass kernel + count read-back
+    lib().asp_debug_time_extract_kernel(0)
+    call_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in timers]))  # memset + index kernel + extraction kernel + count read-back
+    kernel_ms = float(np.mean(kernel_only))                                 # extract_csr_kernel alone
     nnz_total = D.sum_over_ranks(float(nnz_mine), dev)
     candidates_mine = None
     value = nnz_total * args.steps / (total_ms * 1e-3)
@@ -306,9 +311,12 @@ def run_ours(args):
     roofline = {
         "bound": "hbm", "kernel": "extract_csr_kernel", "achieved": algo_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peak,
         "unit": "GB/s", "frac": algo_bytes / (kernel_ms * 1e-3) / 1e9 / peak, "traffic": TRAFFIC_BYTES, "peak_source": peak_src,
-        "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": kernel_ms,
-        "note": "CUDA events around asp_extract_csr on the launching stream: build_starts_kernel (index) + extract_csr_kernel "
-                "(single pass) + the 8-byte count read-back; algorithmic bytes = 24 B/row + 20 B/coupling (SURVEY.md 8d)",
+        "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": kernel_ms, "call_ms": call_ms,
+        "frac_whole_call": algo_bytes / (call_ms * 1e-3) / 1e9 / peak,
+        "note": "kernel_ms: CUDA events around extract_csr_kernel alone on its launching stream (asp_debug_time_extract_kernel); "
+                "call_ms: events around the whole asp_extract_csr call (memset + build_index_kernel + extract_csr_kernel + 8-byte "
+                "count read-back); algorithmic bytes = 24 B/row + 20 B/coupling (SURVEY.md 8d); the kernel is bound by instruction "
+                "issue, not by HBM (DESIGN.md 4.1, profiles/)",
     }
     indptr, indices, data = out
 

@@ -147,6 +147,11 @@ int asp_extract_csr(asp_operator const *op, uint64_t n_total, uint64_t const *d_
  * move applicability lane by lane instead of on bit planes. */
 void asp_debug_set_hit_list_capacity(int entries_per_warp);
 void asp_debug_set_extract_tuning(int filter_bits_delta, int table_bits_delta, int stage_a_mode);
+/* Measurement hook: when enabled, every launch of the single-pass extraction kernel is bracketed by
+ * CUDA events on its own stream; the second call returns the device time of the LAST such launch
+ * (milliseconds; synchronises on it; -1 if none). */
+void asp_debug_time_extract_kernel(int enable);
+float asp_debug_last_extract_kernel_ms(void);
 
 /* Canonical CSR of generation-order rows (raw output of asp_build_matrix_dev): inside each
  * row a stable sort by column, duplicates summed in generation order -- what scipy's
