@@ -257,15 +257,20 @@ def test_symmetrised_kagome_36_extraction_vs_oracle():
     _assert_same_matrix((0.5 * (ours + ours.T)).tocsr(), ref)
 
 
-def test_properties_at_scale():
-    """Size-independent properties on a 2e6-state kagome_36-shaped U(1) subset: rows sorted and
+@pytest.mark.parametrize("system,states", [
+    ("heisenberg_kagome_36", 10_000_000),       # BASELINE.json configs[3] at full size (one GPU's row block)
+    ("heisenberg_pyrochlore_2x2x2", 10_000_000),  # configs[4]
+    ("sk_32_1", 1_000_000),                      # configs[2]
+])
+def test_properties_at_scale(system, states):
+    """Size-independent properties at BASELINE.json's full sizes (U(1) bases): rows sorted and
     duplicate-free, one diagonal per row, structurally symmetric, values symmetric bitwise,
     random rows equal to the oracle's."""
-    cfg = asp.ls.load_config(asp.ls.system_path("heisenberg_kagome_36"))
+    cfg = asp.ls.load_config(asp.ls.system_path(system))
     cfg["basis"]["symmetries"], cfg["basis"]["spin_inversion"] = [], None
     op = asp.ls.Operator.load_from_yaml(cfg["hamiltonian"], asp.ls.SpinBasis.load_from_yaml(cfg["basis"]))
     op_np = OperatorNP.from_config(cfg)
-    spins = synthetic.cluster_closed_states(op, 2_000_000, 21, DEV)
+    spins = synthetic.cluster_closed_states(op, states, 21, DEV)
     n = spins.shape[0]
     psi = synthetic.synthetic_amplitudes(n, 21, device=DEV)
     indptr, indices, data = common.extract_csr_device(op, spins, psi)

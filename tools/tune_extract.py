@@ -39,7 +39,7 @@ def main():
         lib().asp_debug_set_hit_list_capacity(slots)
         need = int(lib().asp_extract_csr_workspace_bytes(op.handle, n, n))
         ws = torch.empty(need, dtype=torch.uint8, device=dev)
-        cap = 8 * n
+        cap = max(8 * n, min(n * op.max_candidates, 400_000_000))
         indptr = torch.empty(n + 1, dtype=torch.int64, device=dev)
         indices = torch.empty(cap, dtype=torch.int32, device=dev)
         data = torch.empty(cap, dtype=torch.float64, device=dev)
