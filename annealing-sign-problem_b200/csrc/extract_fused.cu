@@ -37,6 +37,12 @@ static_assert(kFxTileRows == kFusedTileRows, "fused.cuh out of sync");
 constexpr uint32_t kFxMaxMoves = 2046;  // tag layout: move 11 bits | row lane 5 bits | in-row rank 12 bits
 constexpr int kFxSurvSlotsDefault = 24; // survivor slots per lane between two exact-search rounds
 constexpr int kFxMaxCtasPerSM = 8;
+#ifndef ASP_FX_IN_FLIGHT
+#define ASP_FX_IN_FLIGHT 4  // filter words a lane has in flight in the candidate walk (4 or 2)
+#endif
+#ifndef ASP_FX_BACKOFF_NS
+#define ASP_FX_BACKOFF_NS 32  // first sleep of a look-back that finds an unpublished tile
+#endif
 #ifndef ASP_FX_LAG
 #define ASP_FX_LAG 1
 #endif
@@ -492,6 +498,7 @@ __global__ void __launch_bounds__(kFxThreads, ASP_FX_MIN_CTAS) extract_csr_kerne
         // four candidates per lane between two looks at the loop condition and the fill level,
         // their four filter words in flight together
         while (__any_sync(0xffffffffu, cur != 0 || amask_addr < amask_last)) {
+#if ASP_FX_IN_FLIGHT == 4
           uint32_t e0, e1, e2, e3, h0, h1, h2, h3;
           uint2 w0, w1, w2, w3;
           fetch(e0, h0, w0);
@@ -502,6 +509,18 @@ __global__ void __launch_bounds__(kFxThreads, ASP_FX_MIN_CTAS) extract_csr_kerne
           sieve(e1, h1, w1);
           sieve(e2, h2, w2);
           sieve(e3, h3, w3);
+#else
+          uint32_t e0, e1, h0, h1;
+          uint2 w0, w1;
+          fetch(e0, h0, w0);
+          fetch(e1, h1, w1);
+          sieve(e0, h0, w0);
+          sieve(e1, h1, w1);
+          fetch(e0, h0, w0);
+          fetch(e1, h1, w1);
+          sieve(e0, h0, w0);
+          sieve(e1, h1, w1);
+#endif
           if (__any_sync(0xffffffffu, surv_addr > surv_limit)) {
             __syncwarp();
             flush();
@@ -558,10 +577,10 @@ __global__ void __launch_bounds__(kFxThreads, ASP_FX_MIN_CTAS) extract_csr_kerne
           const int64_t idx = look - lane;
           unsigned long long st = kFlagPrefix;  // virtual tiles before tile 0: prefix 0
           if (idx >= 0) {
-            unsigned backoff = 32;
+            unsigned backoff = ASP_FX_BACKOFF_NS;
             while (((st = ld_status(&a.status[idx])) >> 62) == 0) {
               __nanosleep(backoff);
-              if (backoff < 1024) backoff <<= 1;
+              if (backoff < 32 * ASP_FX_BACKOFF_NS) backoff <<= 1;
             }
           }
           const uint32_t has_prefix = __ballot_sync(0xffffffffu, (st >> 62) == 2);
