@@ -120,10 +120,12 @@ def default_betas(hamiltonian: Hamiltonian, number_sweeps: int, beta0: Optional[
 
 
 def energy_scale(hamiltonian: Hamiltonian) -> float:
-    """Power of two that maps every reachable energy difference into int64 with headroom."""
+    """Power of two that turns energy differences into integers: every single-flip change stays
+    below 2^50 (the kernel rounds with the 1.5 * 2^52 trick, exact below 2^51) and every running sum
+    well inside int64."""
     _, _, data, fld = hamiltonian.device_csr()
     w = float(data.abs().sum()) + (float(fld.abs().sum()) if fld is not None else 0.0)
-    return float(2.0 ** np.floor(np.log2(2.0 ** 60 / (2.0 * w + 1.0))))
+    return float(2.0 ** np.floor(np.log2(2.0 ** 50 / (2.0 * w + 1.0))))
 
 
 class AnnealPlan:

@@ -46,6 +46,7 @@ struct asp_sa_plan {
   int64_t *d_class_ptr = nullptr; // [num_classes + 1]
   std::vector<int64_t> class_ptr;
   double diag_sum = 0.0;          // sum_i J_ii of the original model (constant part of the energy)
+  double max_de = 0.0;            // max_p (4 sum_j |J_pj| + 2 |h_p|): bound on any single-flip energy change
 };
 
 namespace asp {
@@ -146,28 +147,35 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   return c;
 }
 
-__device__ __forceinline__ double exp_neg(double x) {
-  const double t = __dmul_rn(x, 1.4426950408889634);
-  const double kf = floor(t);
-  const double z = __dmul_rn(__dadd_rn(__dadd_rn(t, -kf), -0.5), 0.6931471805599453);
-  const double w = -z;
-  double p = 1.0 / 6227020800.0;
-  p = __fma_rn(p, w, 1.0 / 479001600.0);
-  p = __fma_rn(p, w, 1.0 / 39916800.0);
-  p = __fma_rn(p, w, 1.0 / 3628800.0);
-  p = __fma_rn(p, w, 1.0 / 362880.0);
-  p = __fma_rn(p, w, 1.0 / 40320.0);
-  p = __fma_rn(p, w, 1.0 / 5040.0);
-  p = __fma_rn(p, w, 1.0 / 720.0);
-  p = __fma_rn(p, w, 1.0 / 120.0);
-  p = __fma_rn(p, w, 1.0 / 24.0);
-  p = __fma_rn(p, w, 1.0 / 6.0);
-  p = __fma_rn(p, w, 0.5);
-  p = __fma_rn(p, w, 1.0);
-  p = __fma_rn(p, w, 1.0);
-  p = __dmul_rn(p, 0.7071067811865476);
-  const double scale = __longlong_as_double((1023ll - static_cast<long long>(kf)) << 52);
-  return __dmul_rn(p, scale);
+// exp(-x), 0 < x < 23, binary32, the operation sequence of oracle/anneal_port.c:exp_neg_f32
+// (explicit _rn intrinsics: nothing is contracted or reassociated).
+__device__ __forceinline__ float exp_neg_f32(float x) {
+  const float t = __fmul_rn(x, 1.44269502f);
+  const float r = __fadd_rn(t, 12582912.0f);
+  const int k = __float_as_int(r) - 0x4B400000;
+  const float g = __fadd_rn(t, -__fadd_rn(r, -12582912.0f));
+  const float w = __fmul_rn(g, -0.693147182f);
+  float p = 1.0f / 5040.0f;
+  p = __fmaf_rn(p, w, 1.0f / 720.0f);
+  p = __fmaf_rn(p, w, 1.0f / 120.0f);
+  p = __fmaf_rn(p, w, 1.0f / 24.0f);
+  p = __fmaf_rn(p, w, 1.0f / 6.0f);
+  p = __fmaf_rn(p, w, 0.5f);
+  p = __fmaf_rn(p, w, 1.0f);
+  p = __fmaf_rn(p, w, 1.0f);
+  return __int_as_float(__float_as_int(p) - (k << 23));
+}
+
+// Metropolis test for an uphill move, 0 < x = beta dE < 23 (oracle: accept_uphill).
+__device__ __forceinline__ bool accept_uphill(double x, uint32_t rnd) {
+  const float u = __fmaf_rn(__uint2float_rn(rnd), 2.32830644e-10f, 1.16415322e-10f);
+  return u < exp_neg_f32(__double2float_rn(x));
+}
+
+// llrint(v) for |v| < 2^51 without a conversion instruction: adding 1.5 * 2^52 leaves the
+// integer, rounded to nearest-even, in the low mantissa bits (asp_sa_anneal checks the bound).
+__device__ __forceinline__ long long round_to_ll(double v) {
+  return __double_as_longlong(__dadd_rn(v, 6755399441055744.0)) - 0x4338000000000000ll;
 }
 
 constexpr double kRejectAbove = 23.0;  // exp(-23) < 2^-33, the smallest uniform variate
@@ -257,9 +265,9 @@ struct __align__(16) StagedEntry {
   uint32_t pad;
 };
 
-// +val when bit `lane` of `word` is set, -val otherwise (sign-bit XOR: exact)
-__device__ __forceinline__ double signed_by_bit(double val, uint32_t word, uint32_t lane) {
-  const uint32_t flip = (((~word) >> lane) & 1u) << 31;
+// +val when bit `lane` of `word` is set, -val otherwise (sign-bit XOR: exact); up = 31 - lane
+__device__ __forceinline__ double signed_by_bit(double val, uint32_t word, uint32_t up) {
+  const uint32_t flip = ~(word << up) & 0x80000000u;
   return __hiloint2double(__double2hiint(val) ^ static_cast<int>(flip), __double2loint(val));
 }
 
@@ -295,12 +303,14 @@ __device__ __forceinline__ void accumulate_rows(const TaskRows &rows, int64_t e_
     se.pad = 0;
     stage[lane] = se;
     __syncwarp();
+    const uint32_t up = 31u - lane;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int32_t lo = max(rows.b[j], cb) - cb, hi = min(rows.b[j + 1], cb + 32) - cb;
+#pragma unroll 1  // rows hold ~4 entries: a tight loop beats an unrolled one with its remainder code
       for (int32_t k = lo; k < hi; ++k) {
         const StagedEntry x = stage[k];
-        acc[j] = __dadd_rn(acc[j], signed_by_bit(x.val, x.word, lane));
+        acc[j] = __dadd_rn(acc[j], signed_by_bit(x.val, x.word, up));
       }
     }
   }
@@ -405,11 +415,10 @@ __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm) sa_sweep_kernel(cons
               if (x >= kRejectAbove) {
                 accept = false;
               } else {
-                const double u = __dmul_rn(__dadd_rn(static_cast<double>(rnd[j]), 0.5), 2.3283064365386963e-10);
-                accept = u < exp_neg(x);
+                accept = accept_uphill(x, rnd[j]);
               }
             }
-            if (accept) rel_delta += __double2ll_rn(__dmul_rn(dE[j], a.escale));
+            if (accept) rel_delta += round_to_ll(__dmul_rn(dE[j], a.escale));
             new_w[j] = cur_w[j] ^ __ballot_sync(0xffffffffu, accept);
           }
           if (lane == 0) __stcg(reinterpret_cast<uint4 *>(words + p0), make_uint4(new_w[0], new_w[1], new_w[2], new_w[3]));
@@ -497,6 +506,18 @@ __global__ void __launch_bounds__(256) energy_sliced_final_kernel(const double *
     const uint32_t r = g * 32 + lane;
     if (r < num_replicas) out[r] = __dadd_rn(total, diag_sum);
   }
+}
+
+// largest possible single-flip energy change: max over rows of 4 sum |J| + 2 |h| (non-negative
+// doubles order like their bit patterns, so an integer atomicMax does the reduction)
+__global__ void __launch_bounds__(256) max_de_kernel(uint64_t n_padded, const int64_t *__restrict__ indptr, const double *__restrict__ data,
+                                                     const double *__restrict__ field, unsigned long long *__restrict__ out) {
+  const uint64_t p = static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (p >= n_padded) return;
+  double sum = 0.0;
+  for (int64_t k = indptr[p]; k < indptr[p + 1]; ++k) sum += fabs(data[k]);
+  const double bound = 4.0 * sum + 2.0 * fabs(field[p]);
+  atomicMax(out, static_cast<unsigned long long>(__double_as_longlong(bound)));
 }
 
 // sum of the diagonal of the ORIGINAL model (dropped from the relabelled CSR): block partials
@@ -702,6 +723,10 @@ int asp_sa_plan_create(asp_sa_plan **out, uint64_t n, int64_t const *d_indptr, i
     diag_final_kernel<<<1, 256, 0, s>>>(d_part, dblocks, d_part + dblocks);
     ASP_LAUNCH_CHECK();
     ASP_CUDA_CHECK(cudaMemcpyAsync(&plan->diag_sum, d_part + dblocks, sizeof(double), cudaMemcpyDeviceToHost, s));
+    ASP_CUDA_CHECK(cudaMemsetAsync(d_part, 0, sizeof(double), s));
+    max_de_kernel<<<pblocks, 256, 0, s>>>(np, plan->d_indptr, plan->d_data, plan->d_field, reinterpret_cast<unsigned long long *>(d_part));
+    ASP_LAUNCH_CHECK();
+    ASP_CUDA_CHECK(cudaMemcpyAsync(&plan->max_de, d_part, sizeof(double), cudaMemcpyDeviceToHost, s));
     ASP_CUDA_CHECK(cudaStreamSynchronize(s));
     cudaFree(d_part);
   }
@@ -741,6 +766,7 @@ int asp_sa_anneal(asp_sa_plan *plan, uint32_t num_replicas, uint32_t replica_off
   ASP_REQUIRE(num_sweeps == 0 || h_betas != nullptr, "h_betas is NULL");
   ASP_REQUIRE(d_best_bits != nullptr, "d_best_bits is NULL");
   ASP_REQUIRE(energy_scale > 0.0, "energy_scale must be positive");
+  ASP_REQUIRE(energy_scale * plan->max_de < 2251799813685248.0, "energy_scale too large: |dE| * energy_scale must stay below 2^51");
   ASP_REQUIRE(replica_offset % 32 == 0, "replica_offset must be a multiple of 32");
   const uint32_t groups = (num_replicas + 31) / 32;
   const uint64_t np = plan->n_padded;

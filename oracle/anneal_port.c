@@ -20,9 +20,10 @@
  * remembers its configuration if its energy is the lowest seen so far.
  *
  * Determinism contract shared with the CUDA kernel (DESIGN.md "SA chain definition"):
- * every floating-point operation below is a single correctly-rounded IEEE-754 binary64
- * add / mul / fma, so a GPU that performs the same sequence reproduces every accept
- * decision bit for bit.  Compile with -ffp-contract=off.
+ * every floating-point operation below is a single correctly-rounded IEEE-754 add / mul /
+ * fma (binary64 for energies, binary32 for the acceptance probability), so a GPU that
+ * performs the same sequence reproduces every accept decision bit for bit.  Compile with
+ * -ffp-contract=off.
  */
 #include <math.h>
 #include <pthread.h>
@@ -63,35 +64,42 @@ static inline uint32_t draw(uint64_t seed, uint32_t r, uint32_t t, uint64_t p) {
   return out[p & 3];
 }
 
-/* exp(-x) for 0 < x < 23 from IEEE add/mul/fma only (no libm call on the decision path):
- * x*log2(e) = k + f, exp(-x) = 2^-k * 2^-1/2 * exp(-(f - 1/2) ln 2), degree-13 Taylor. */
-static inline double exp_neg(double x) {
-  double const t = x * 1.4426950408889634;
-  double const kf = floor(t);
-  double const z = (t - kf - 0.5) * 0.6931471805599453; /* |z| <= 0.3466 */
-  double const w = -z;
-  double p = 1.0 / 6227020800.0;            /* 1/13! */
-  p = fma(p, w, 1.0 / 479001600.0);         /* 1/12! */
-  p = fma(p, w, 1.0 / 39916800.0);
-  p = fma(p, w, 1.0 / 3628800.0);
-  p = fma(p, w, 1.0 / 362880.0);
-  p = fma(p, w, 1.0 / 40320.0);
-  p = fma(p, w, 1.0 / 5040.0);
-  p = fma(p, w, 1.0 / 720.0);
-  p = fma(p, w, 1.0 / 120.0);
-  p = fma(p, w, 1.0 / 24.0);
-  p = fma(p, w, 1.0 / 6.0);
-  p = fma(p, w, 0.5);
-  p = fma(p, w, 1.0);
-  p = fma(p, w, 1.0);
-  p = p * 0.7071067811865476;               /* 2^-1/2 */
-  uint64_t const bits = (uint64_t)(1023 - (int64_t)kf) << 52; /* 2^-k, exact */
-  double scale;
-  memcpy(&scale, &bits, sizeof scale);
-  return p * scale;
+/* exp(-x) for 0 < x < 23 in IEEE binary32 from add / mul / fma only (no libm call on the
+ * decision path), relative error < 2e-7 -- far below anything an acceptance rate can resolve:
+ * t = x log2(e) = k + g with k the nearest integer (magic-number rounding, no conversion) and
+ * |g| <= 1/2;  exp(-x) = 2^-k exp(-g ln 2), degree-7 Taylor, 2^-k applied to the exponent bits. */
+static inline float exp_neg_f32(float x) {
+  float const t = x * 1.44269502f;
+  float const r = t + 12582912.0f; /* 1.5 * 2^23: r's low mantissa bits hold round(t) */
+  uint32_t rbits;
+  memcpy(&rbits, &r, sizeof rbits);
+  int32_t const k = (int32_t)(rbits - 0x4B400000u);
+  float const kf = r - 12582912.0f;
+  float const g = t - kf; /* exact, |g| <= 1/2 */
+  float const w = g * -0.693147182f;
+  float p = 1.0f / 5040.0f;
+  p = fmaf(p, w, 1.0f / 720.0f);
+  p = fmaf(p, w, 1.0f / 120.0f);
+  p = fmaf(p, w, 1.0f / 24.0f);
+  p = fmaf(p, w, 1.0f / 6.0f);
+  p = fmaf(p, w, 0.5f);
+  p = fmaf(p, w, 1.0f);
+  p = fmaf(p, w, 1.0f);
+  uint32_t pbits;
+  memcpy(&pbits, &p, sizeof pbits);
+  pbits -= (uint32_t)k << 23; /* p in [0.70, 1.42], k <= 34: stays a normal number */
+  memcpy(&p, &pbits, sizeof p);
+  return p;
 }
 
-double oracle_exp_neg(double x) { return exp_neg(x); }
+/* Metropolis test for an uphill move with 0 < x = beta dE < 23 and the 32-bit variate rnd:
+ * u = (rnd + 1/2) 2^-32 (binary32) < exp(-x). */
+static inline int accept_uphill(double x, uint32_t rnd) {
+  float const u = fmaf((float)rnd, 2.32830644e-10f, 1.16415322e-10f);
+  return u < exp_neg_f32((float)x);
+}
+
+double oracle_exp_neg(double x) { return (double)exp_neg_f32((float)x); }
 
 #define ORACLE_REJECT_ABOVE 23.0 /* exp(-23) < 2^-33 = smallest uniform variate */
 
@@ -128,8 +136,7 @@ static int64_t anneal_one(uint64_t n, int64_t const *indptr, int32_t const *cols
         if (x >= ORACLE_REJECT_ABOVE) {
           accept = 0;
         } else {
-          double const u = ((double)draw(seed, r, t, i) + 0.5) * 2.3283064365386963e-10;
-          accept = u < exp_neg(x);
+          accept = accept_uphill(x, draw(seed, r, t, i));
         }
       }
       if (accept) {

@@ -172,7 +172,8 @@ def test_philox_known_answers(oracle_capi):
 
 def test_exp_neg_accuracy(oracle_capi):
     for x in np.concatenate([np.linspace(1e-9, 22.99, 4001), [1e-300, 0.5, 1.0, 22.999999]]):
-        assert abs(oracle_capi.exp_neg(x) / math.exp(-x) - 1.0) < 4e-15  # x*log2(e) rounds once: error grows like x * 2^-53
+        # binary32: the argument, x*log2(e) and the degree-7 polynomial round at 2^-24 each; error grows like x * 2^-24
+        assert abs(oracle_capi.exp_neg(x) / math.exp(-float(np.float32(x))) - 1.0) < 3e-7 + 1.5e-7 * x
 
 
 def _random_model(n, density, rng):
