@@ -235,7 +235,10 @@ struct SaArgs {
 
 constexpr int kSaThreads = 256;
 constexpr int kSaWarps = kSaThreads / 32;
-constexpr int kSaCtasPerSm = 3;  // 24 warps/SM: hides the indptr -> entries -> spin-word load chain
+#ifndef ASP_SA_CTAS_PER_SM
+#define ASP_SA_CTAS_PER_SM 3
+#endif
+constexpr int kSaCtasPerSm = ASP_SA_CTAS_PER_SM;  // 24 warps/SM: hides the indptr -> entries -> spin-word load chain
 
 struct TeamBarrier {
   unsigned long long *counter;
@@ -307,17 +310,18 @@ __device__ __forceinline__ void accumulate_rows(const TaskRows &rows, int64_t e_
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int32_t lo = max(rows.b[j], cb) - cb, hi = min(rows.b[j + 1], cb + 32) - cb;
-#pragma unroll 1  // rows hold ~4 entries: a tight loop beats an unrolled one with its remainder code
-      for (int32_t k = lo; k < hi; ++k) {
-        const StagedEntry x = stage[k];
-        acc[j] = __dadd_rn(acc[j], signed_by_bit(x.val, x.word, up));
+#pragma unroll 1  // rows hold ~4 entries: a tight loop (two entries per trip, the second one predicated) beats an unrolled one
+      for (int32_t k = lo; k < hi; k += 2) {
+        const StagedEntry x0 = stage[k], x1 = stage[k + 1];  // stage has a 33rd slot
+        acc[j] = __dadd_rn(acc[j], signed_by_bit(x0.val, x0.word, up));
+        if (k + 1 < hi) acc[j] = __dadd_rn(acc[j], signed_by_bit(x1.val, x1.word, up));
       }
     }
   }
 }
 
 __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm) sa_sweep_kernel(const SaArgs a) {
-  __shared__ StagedEntry s_stage[kSaWarps][32];
+  __shared__ StagedEntry s_stage[kSaWarps][33];
   const uint32_t lane = threadIdx.x & 31, warp_in_cta = threadIdx.x >> 5;
   const uint32_t team = blockIdx.x / a.team_size;
   if (team >= a.num_teams) return;
@@ -451,7 +455,7 @@ constexpr int kEnWarps = 8;
 __global__ void __launch_bounds__(kEnWarps * 32) energy_sliced_kernel(uint64_t n_padded, const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                                                                       const double *__restrict__ data, const double *__restrict__ field,
                                                                       const uint32_t *__restrict__ all_words, double *__restrict__ partial) {
-  __shared__ StagedEntry s_stage[kEnWarps][32];
+  __shared__ StagedEntry s_stage[kEnWarps][33];
   const uint32_t lane = threadIdx.x & 31, warp_in_cta = threadIdx.x >> 5;
   const uint32_t g = blockIdx.y;
   const uint32_t *words = all_words + static_cast<uint64_t>(g) * n_padded;

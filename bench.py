@@ -41,7 +41,7 @@ def parse_args():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--states", type=int, default=10_000_000, help="sampled basis states per GPU")
     p.add_argument("--replicas", type=int, default=64, help="annealing replicas per GPU")
-    p.add_argument("--sweeps", type=int, default=4, help="annealing sweeps per step")
+    p.add_argument("--sweeps", type=int, default=16, help="annealing sweeps per step")
     p.add_argument("--cpu-sample", type=int, default=200_000, help="states of the bounded CPU-baseline sample")
     p.add_argument("--skip-anneal", action="store_true")
     p.add_argument("--skip-cpu", action="store_true")
