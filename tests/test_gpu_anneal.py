@@ -196,3 +196,58 @@ def test_energy_and_overlap_reductions_vs_oracle(oracle_capi):
                 assert abs(acc[r] - a_ref) <= 1e-12 and abs(ov[r] - o_ref) <= 1e-12
         with pytest.raises(ValueError):
             asp.compute_accuracy_and_overlap(bits[0], exact)
+
+
+def test_config_kagome_18_symmetrised_1024_replicas(golden_dir):
+    """BASELINE.json configs[1]: heisenberg_kagome_18, full symmetrised basis (24 310 inversion
+    representatives), 1024 SA replicas on one GPU.  The ground level is doubly degenerate inside the
+    sector, so the gate is the ENERGY: best-of-R reaches E0 to 1e-10 and no
+    replica goes below it (variational bound); overlap is not gated."""
+    table = json.load(open(os.path.join(golden_dir, "known_answers.json")))["heisenberg_kagome_18"]
+    name = "heisenberg_kagome_18"
+    op_np = OperatorNP.load(asp.ls.system_path(name))
+    e0, psi, _ = ground_state(op_np)
+    assert abs(e0 - table["E0"]) < 1e-9
+    op = asp.load_hamiltonian(asp.ls.system_path(name))
+    assert op.basis.states.shape[0] == table["n"]
+    with np.errstate(divide="ignore"):
+        model = asp.make_ising_model(op.basis.states, op, log_psi=np.log(psi.astype(np.complex128)))
+    # explicit zeros are dropped by the symmetrisation (common.py:195): at most T entries, at least the diagonal
+    assert table["n"] <= model.ising_hamiltonian.exchange.nnz <= table["T"]
+    exact = model.ising_hamiltonian.energy(model.initial_signs)
+    assert abs(exact - e0) <= 1e-10  # KAT-1: E(sign psi) = E0
+    xs, es = asp.sa.anneal(model.ising_hamiltonian, seed=0, number_sweeps=1600, repetitions=1024, only_best=False)
+    assert xs.shape == (1024, (table["n"] + 63) // 64)
+    assert np.all(es >= e0 - 1e-10)
+    assert abs(es.min() - e0) <= 1e-10
+    assert (np.abs((es - e0) / e0) <= 1e-12).mean() > 0.2
+
+
+def test_config_sk_32_shaped_4096_replicas(oracle_capi):
+    """BASELINE.json configs[2] in shape (sk_32_1 operator, sampled subset, 4096 replicas), sized so
+    the CPU oracle finishes in seconds: 20 000 states.  32 of the 4096 replicas (the first and the
+    last group) are compared bit for bit with the oracle run on the same relabelled model."""
+    from annealing_sign_problem_b200 import synthetic
+
+    cfg = asp.ls.load_config(asp.ls.system_path("sk_32_1"))
+    cfg["basis"]["symmetries"], cfg["basis"]["spin_inversion"] = [], None
+    op = asp.ls.Operator.load_from_yaml(cfg["hamiltonian"], asp.ls.SpinBasis.load_from_yaml(cfg["basis"]))
+    spins = synthetic.cluster_closed_states(op, 20000, 3, DEV)
+    n = int(spins.shape[0])
+    psi = synthetic.synthetic_amplitudes(n, 3, device=DEV)
+    indptr, indices, data = common.extract_csr_device(op, spins, psi)
+    csr = scipy.sparse.csr_matrix((data.cpu().numpy(), indices.cpu().numpy(), indptr.cpu().numpy()), shape=(n, n))
+    ham = asp.sa.Hamiltonian(csr, np.zeros(n), _device_csr=(indptr, indices, data, None))
+    plan = asp.sa.AnnealPlan(ham)
+    ex, pos = check_plan(plan, csr, np.zeros(n))
+    betas = asp.sa.default_betas(ham, 12)
+    escale = asp.sa.energy_scale(ham)
+    bits, energies = plan.anneal_device(4096, betas, 11, escale=escale)
+    assert bits.shape[0] == 4096 and bool(torch.isfinite(energies).all())
+    ref_first, _ = oracle_best(ex, pos, n, oracle_capi, 32, betas, 11, escale)
+    assert np.array_equal(bits[:32].cpu().numpy().view(np.uint64), ref_first)
+    # replicas 4064..4095 as their own launch with replica_offset: same random streams, same result
+    tail_bits, tail_e = plan.anneal_device(32, betas, 11, escale=escale, replica_offset=4064)
+    assert torch.equal(tail_bits, bits[4064:]) and torch.equal(tail_e, energies[4064:])
+    e_ref = oracle_capi.energy(csr.indptr, csr.indices, csr.data, None, bits[0].cpu().numpy().view(np.uint64))
+    assert abs(float(energies[0]) - e_ref) < 1e-10 * max(1.0, abs(e_ref))

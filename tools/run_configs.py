@@ -1,0 +1,91 @@
+#!/usr/bin/env python
+"""Times the BASELINE.json configurations other than the headline one (development tool; the
+numbers quoted in DESIGN.md 6 come from here).  python tools/run_configs.py [cfg2 cfg3 cfg5]"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import annealing_sign_problem_b200 as asp  # noqa: E402
+from annealing_sign_problem_b200 import common, synthetic  # noqa: E402
+
+DEV = torch.device("cuda", 0)
+
+
+def u1(system):
+    cfg = asp.ls.load_config(asp.ls.system_path(system))
+    cfg["basis"]["symmetries"], cfg["basis"]["spin_inversion"] = [], None
+    return asp.ls.Operator.load_from_yaml(cfg["hamiltonian"], asp.ls.SpinBasis.load_from_yaml(cfg["basis"]))
+
+
+def timed(fn, reps=3):
+    fn()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        out = fn()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / reps, out
+
+
+def sampled(system, states, replicas, sweeps):
+    op = u1(system)
+    spins = synthetic.cluster_closed_states(op, states, 5, DEV)
+    n = int(spins.shape[0])
+    psi = synthetic.synthetic_amplitudes(n, 5, device=DEV)
+    dt, (indptr, indices, data) = timed(lambda: common.extract_csr_device(op, spins, psi, nnz_hint=None))
+    nnz = int(indices.numel())
+    print("%s: n=%d nnz=%d  extraction %.2f ms (%.3g couplings/s, %.3g candidates/s)" % (
+        system, n, nnz, 1e3 * dt, nnz / dt, n * (op.max_candidates / 4.0 + 1) / dt), flush=True)
+
+    class _Shape:
+        shape = (n, n)
+
+    ham = asp.sa.Hamiltonian(_Shape(), np.zeros(n), _device_csr=(indptr, indices, data, None))
+    t0 = time.perf_counter()
+    plan = asp.sa.AnnealPlan(ham)
+    torch.cuda.synchronize()
+    plan_s = time.perf_counter() - t0
+    betas = asp.sa.default_betas(ham, max(64, sweeps * 8))[:sweeps]
+    escale = asp.sa.energy_scale(ham)
+    dt, (bits, energies) = timed(lambda: plan.anneal_device(replicas, betas, 1, escale=escale), reps=2)
+    print("   SA: %d replicas x %d sweeps: %.1f ms = %.3g proposals/s (plan %.0f ms, %d colour classes), best E %.6f" % (
+        replicas, sweeps, 1e3 * dt, replicas * sweeps * n / dt, 1e3 * plan_s, plan.num_classes, float(energies.min())), flush=True)
+
+
+def cfg2():
+    from oracle.operator_np import OperatorNP, ground_state  # checker only: exact eigenvector for the model
+
+    name = "heisenberg_kagome_18"
+    e0, psi, _ = ground_state(OperatorNP.load(asp.ls.system_path(name)))
+    op = asp.load_hamiltonian(asp.ls.system_path(name))
+    with np.errstate(divide="ignore"):
+        t0 = time.perf_counter()
+        model = asp.make_ising_model(op.basis.states, op, log_psi=np.log(psi.astype(np.complex128)))
+        dt_model = time.perf_counter() - t0
+    ham = model.ising_hamiltonian
+    for sweeps in (100, 1600):
+        t0 = time.perf_counter()
+        xs, es = asp.sa.anneal(ham, seed=0, number_sweeps=sweeps, repetitions=1024, only_best=False)
+        dt = time.perf_counter() - t0
+        ok = np.abs((es - e0) / e0) <= 1e-12
+        print("kagome_18 symmetrised: n=%d nnz=%d make_ising_model %.0f ms; SA 1024 x %d sweeps %.1f ms = %.3g proposals/s; "
+              "best E - E0 = %.2e, replicas at E0: %.3f" % (model.size, ham.exchange.nnz, 1e3 * dt_model, sweeps, 1e3 * dt,
+                                                            1024 * sweeps * model.size / dt, es.min() - e0, ok.mean()), flush=True)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["cfg2", "cfg3", "cfg5"]
+    if "cfg2" in which:
+        cfg2()
+    if "cfg3" in which:
+        sampled("sk_32_1", 1_000_000, 4096, 4)
+    if "cfg5" in which:
+        sampled("heisenberg_pyrochlore_2x2x2", 10_000_000, 64, 16)
+    if "cfg4" in which:
+        sampled("heisenberg_kagome_36", 10_000_000, 64, 16)
