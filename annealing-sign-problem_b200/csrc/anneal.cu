@@ -594,20 +594,6 @@ __global__ void __launch_bounds__(256) sa_unpermute_kernel(uint64_t n, uint64_t 
 
 using namespace asp;
 
-// The stream-ordered allocations of a call are returned to the default pool at its end; keep
-// them cached there instead of handing them back to the driver at every synchronisation.
-static cudaError_t keep_pool_memory(int device) {
-  static bool done[64] = {};
-  if (device < 0 || device >= 64 || done[device]) return cudaSuccess;
-  cudaMemPool_t pool;
-  cudaError_t e = cudaDeviceGetDefaultMemPool(&pool, device);
-  if (e != cudaSuccess) return e;
-  uint64_t threshold = UINT64_MAX;
-  e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
-  if (e == cudaSuccess) done[device] = true;
-  return e;
-}
-
 extern "C" {
 
 void asp_sa_plan_destroy(asp_sa_plan *plan) {
@@ -622,6 +608,7 @@ void asp_sa_plan_destroy(asp_sa_plan *plan) {
 int asp_sa_plan_create(asp_sa_plan **out, uint64_t n, int64_t const *d_indptr, int32_t const *d_indices,
                        double const *d_data, double const *d_field, void *stream) {
   auto s = static_cast<cudaStream_t>(stream);
+  ASP_CUDA_CHECK(asp::keep_pool_memory());
   ASP_REQUIRE(out != nullptr, "out is NULL");
   ASP_REQUIRE(n > 0 && n < (1ull << 31), "n must be in [1, 2^31)");
   ASP_REQUIRE(d_indptr && d_indices && d_data, "NULL CSR arrays");
@@ -777,7 +764,7 @@ int asp_sa_anneal(asp_sa_plan *plan, uint32_t num_replicas, uint32_t replica_off
 
   int device = 0, sms = 0, per_sm = 0, coop = 0;
   ASP_CUDA_CHECK(cudaGetDevice(&device));
-  ASP_CUDA_CHECK(keep_pool_memory(device));
+  ASP_CUDA_CHECK(asp::keep_pool_memory());
   ASP_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   ASP_CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
   ASP_REQUIRE(coop != 0, "device does not support cooperative launches");

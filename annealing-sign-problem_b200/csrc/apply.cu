@@ -23,10 +23,18 @@ __device__ __forceinline__ uint64_t delta_swap(uint64_t x, uint64_t m, int d) {
 }
 
 __device__ __forceinline__ uint64_t permute(const BitPerm &p, uint64_t x) {
+  // the masks are the same for every lane (one group element at a time), so skipping the empty
+  // stages of a network is a uniform branch
 #pragma unroll
-  for (int k = 0; k < 6; ++k) x = delta_swap(x, p.mask[k], 32 >> k);
+  for (int k = 0; k < 6; ++k) {
+    const uint64_t m = p.mask[k];
+    if (m) x = delta_swap(x, m, 32 >> k);
+  }
 #pragma unroll
-  for (int k = 6; k < 11; ++k) x = delta_swap(x, p.mask[k], 2 << (k - 6));
+  for (int k = 6; k < 11; ++k) {
+    const uint64_t m = p.mask[k];
+    if (m) x = delta_swap(x, m, 2 << (k - 6));
+  }
   return x;
 }
 
@@ -129,6 +137,108 @@ __global__ void __launch_bounds__(kApplyThreads) apply_kernel(const ApplyArgs a)
   if (!kFill) a.counts[r] = cnt;
 }
 
+// ---- symmetrised operators whose characters are all +1 (every shipped system: sectors 0, spin
+// inversion +1): norm(x)^2 = |stabiliser| / |G| never vanishes, so the number of candidates of a row
+// is known without visiting a single orbit, and only the fill pass pays for the group.
+__global__ void __launch_bounds__(256) apply_count_plain_kernel(uint64_t num_rows, const uint64_t *__restrict__ spins, const Move *__restrict__ moves,
+                                                                int n_moves, int64_t *__restrict__ counts) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t *s_mask = reinterpret_cast<uint64_t *>(smem_raw);
+  uint64_t *s_need = s_mask + n_moves;
+  for (int k = threadIdx.x; k < n_moves; k += blockDim.x) {
+    s_mask[k] = moves[k].mask;
+    s_need[k] = moves[k].need;
+  }
+  __syncthreads();
+  const uint64_t r = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= num_rows) return;
+  const uint64_t s = spins[r];
+  int cnt = 1;  // the diagonal
+  for (int m = 0; m < n_moves; ++m) cnt += (s & s_mask[m]) == s_need[m];
+  counts[r] = cnt;
+}
+
+// orbit representative, multiplicity of the stabiliser (characters all +1)
+__device__ __forceinline__ void orbit_info(const SymmetryView &g, const BitPerm *s_perms, uint64_t c, uint64_t &rep, uint32_t &stab) {
+  rep = c;
+  stab = 1;  // the identity
+  if (g.spin_inversion) {
+    const uint64_t y1 = ~c & g.state_mask;
+    rep = min(rep, y1);  // y1 != c always
+  }
+  for (int e = 0; e < g.num_perms; ++e) {
+    const uint64_t y0 = permute(s_perms[e], c);
+    stab += y0 == c;
+    rep = min(rep, y0);
+    if (g.spin_inversion) {
+      const uint64_t y1 = ~y0 & g.state_mask;
+      stab += y1 == c;
+      rep = min(rep, y1);
+    }
+  }
+}
+
+// Fill pass: every lane finds ITS next applicable move by itself (cheap, divergent) and then all
+// lanes walk the group together on their own candidate (expensive, converged): the orbit loop runs
+// with ~90 % of the lanes busy instead of the ~25 % of a move-by-move loop.
+__global__ void __launch_bounds__(kApplyThreads) apply_fill_positive_kernel(const ApplyArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Move *s_moves = reinterpret_cast<Move *>(smem_raw);
+  DiagBond *s_diag = reinterpret_cast<DiagBond *>(s_moves + a.n_moves);
+  BitPerm *s_perms = reinterpret_cast<BitPerm *>(s_diag + a.n_diag);
+  for (int k = threadIdx.x; k < a.n_moves; k += blockDim.x) s_moves[k] = a.moves[k];
+  for (int k = threadIdx.x; k < a.n_diag; k += blockDim.x) s_diag[k] = a.diag[k];
+  for (int k = threadIdx.x; k < a.sym.num_perms; k += blockDim.x) s_perms[k] = a.sym.perms[k];
+  __syncthreads();
+  const uint64_t r = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool live = r < a.num_rows;
+  const uint64_t s = live ? a.spins[r] : 0ull;
+  uint64_t rep;
+  uint32_t stab_s = 1;
+  orbit_info(a.sym, s_perms, s, rep, stab_s);  // converged: dead lanes walk the orbit of 0
+  int64_t out = live ? a.offsets[r] : 0;
+  int m = 0;
+  bool diag_done = !live;
+  if (!live) m = a.n_moves;
+  for (;;) {
+    uint64_t c = 0;
+    double coef = 0.0;
+    bool have = false;
+    while (!have && (m < a.n_moves || !diag_done)) {
+      if (!diag_done && m >= a.n_down) {  // the diagonal sits between the negative and the positive deltas
+        double d = 0.0;
+        for (int k = 0; k < a.n_diag; ++k) {
+          const DiagBond db = s_diag[k];
+          d += db.d[((s >> db.i) & 1) * 2 + ((s >> db.j) & 1)];
+        }
+        c = s;
+        coef = d;
+        diag_done = true;
+        have = true;
+      } else {
+        const Move mv = s_moves[m++];
+        if ((s & mv.mask) == mv.need) {
+          c = s ^ mv.flip;
+          coef = mv.coef;
+          have = true;
+        }
+      }
+    }
+    if (!__any_sync(0xffffffffu, have)) break;
+    uint32_t stab_c = 1;
+    orbit_info(a.sym, s_perms, c, rep, stab_c);
+    if (have) {
+      // coef * (chi * norm(c)) / norm(s) with chi = 1 and norm = sqrt(stabiliser / |G|): the operation
+      // sequence of apply_kernel<true>, so both kernels agree bit for bit
+      const double norm_c = sqrt(fmax(static_cast<double>(stab_c), 0.0) / a.sym.group_order);
+      const double norm_s = sqrt(fmax(static_cast<double>(stab_s), 0.0) / a.sym.group_order);
+      a.other_spins[out] = rep;
+      a.other_coeffs[out] = coef * ((1.0 * norm_c) / norm_s);
+      ++out;
+    }
+  }
+}
+
 // ---- canonicalisation: one warp per row, bitonic sort of (col, seq) keys in smem --------
 constexpr int kCanonThreads = 128;
 constexpr int kCanonMaxRow = 1024;
@@ -223,11 +333,16 @@ __global__ void __launch_bounds__(256) compact_rows_kernel(uint64_t num_rows, co
 
 using namespace asp;
 
+static int g_apply_mode = 0;  // test hook: 1 = always the general kernels
+
 extern "C" {
+
+void asp_debug_set_apply_mode(int mode) { g_apply_mode = mode; }
 
 int asp_operator_apply_dev(asp_operator const *op, uint64_t num_rows, uint64_t const *d_spins, uint64_t *d_other_spins,
                            double *d_other_coeffs, int64_t *d_counts, uint64_t capacity, uint64_t *h_total, void *stream) {
   auto s = static_cast<cudaStream_t>(stream);
+  ASP_CUDA_CHECK(asp::keep_pool_memory());
   ASP_REQUIRE(op != nullptr && op->d_moves != nullptr, "operator is NULL or has no device mirror");
   ASP_REQUIRE(h_total != nullptr, "h_total is NULL");
   *h_total = 0;
@@ -254,7 +369,16 @@ int asp_operator_apply_dev(asp_operator const *op, uint64_t num_rows, uint64_t c
   const unsigned blocks = static_cast<unsigned>((num_rows + kApplyThreads - 1) / kApplyThreads);
   ASP_CUDA_CHECK(cudaFuncSetAttribute(apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   ASP_CUDA_CHECK(cudaFuncSetAttribute(apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  apply_kernel<false><<<blocks, kApplyThreads, smem, s>>>(a);
+  // all characters +1 (and no odd spin-inversion sector): the fast pair of kernels
+  bool positive = a.symmetrised && op->spin_inversion >= 0 && g_apply_mode != 1;
+  for (double chi : op->characters) positive = positive && chi == 1.0;
+  if (positive) {
+    const size_t csmem = op->moves.size() * 16 + 16;
+    ASP_CUDA_CHECK(cudaFuncSetAttribute(apply_count_plain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(csmem)));
+    apply_count_plain_kernel<<<static_cast<unsigned>((num_rows + 255) / 256), 256, csmem, s>>>(num_rows, d_spins, op->d_moves, a.n_moves, d_counts);
+  } else {
+    apply_kernel<false><<<blocks, kApplyThreads, smem, s>>>(a);
+  }
   ASP_LAUNCH_CHECK();
   int64_t *d_offsets = nullptr;
   void *d_tmp = nullptr;
@@ -275,7 +399,12 @@ int asp_operator_apply_dev(asp_operator const *op, uint64_t num_rows, uint64_t c
   a.offsets = d_offsets;
   a.other_spins = d_other_spins;
   a.other_coeffs = d_other_coeffs;
-  apply_kernel<true><<<blocks, kApplyThreads, smem, s>>>(a);
+  if (positive) {
+    ASP_CUDA_CHECK(cudaFuncSetAttribute(apply_fill_positive_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    apply_fill_positive_kernel<<<blocks, kApplyThreads, smem, s>>>(a);
+  } else {
+    apply_kernel<true><<<blocks, kApplyThreads, smem, s>>>(a);
+  }
   ASP_LAUNCH_CHECK();
   ASP_CUDA_CHECK(cudaFreeAsync(d_offsets, s));
   ASP_CUDA_CHECK(cudaFreeAsync(d_tmp, s));
@@ -286,6 +415,7 @@ int asp_csr_canonicalize(uint64_t num_rows, uint32_t max_row_len, int64_t const 
                          double const *d_vals, uint64_t nnz_in, int64_t *d_indptr, int32_t *d_indices, double *d_data,
                          uint64_t *h_nnz, void *stream) {
   auto s = static_cast<cudaStream_t>(stream);
+  ASP_CUDA_CHECK(asp::keep_pool_memory());
   ASP_REQUIRE(h_nnz != nullptr && d_indptr != nullptr, "NULL output");
   *h_nnz = 0;
   if (num_rows == 0) {

@@ -99,6 +99,11 @@ __device__ __forceinline__ int64_t block_exclusive_scan_i64(int64_t v, int64_t *
   return base + incl - v;
 }
 
+// The stream-ordered allocations (cudaMallocAsync) of a call are returned to the default pool at
+// its end; keep them cached there instead of handing them back to the driver at every
+// synchronisation.  Call once at the top of every entry point that allocates.
+cudaError_t keep_pool_memory();
+
 // Internal scan entry (extract.cu) reused by other translation units.
 int scan_exclusive_i64(const int64_t *d_in, int64_t *d_out, uint64_t m, void *d_tmp, cudaStream_t s);
 size_t scan_tmp_bytes(uint64_t m);

@@ -91,6 +91,7 @@ static int legacy_build_dev(uint64_t n_total, const Key *d_spins, uint64_t row_b
                             int64_t *d_row_offsets, uint32_t *d_row_indices, uint32_t *d_col_indices,
                             double *d_elements, double *d_field, uint64_t capacity, uint64_t *h_nnz, cudaStream_t s) {
   ASP_REQUIRE(h_nnz != nullptr && d_row_offsets != nullptr, "NULL output");
+  ASP_CUDA_CHECK(asp::keep_pool_memory());
   if (num_rows == 0) {
     *h_nnz = 0;
     ASP_CUDA_CHECK(cudaMemsetAsync(d_row_offsets, 0, sizeof(int64_t), s));

@@ -21,6 +21,21 @@ void set_error(const char *fmt, ...) {
   va_end(ap);
 }
 
+cudaError_t keep_pool_memory() {
+  static bool done[64] = {};
+  int device = 0;
+  cudaError_t e = cudaGetDevice(&device);
+  if (e != cudaSuccess) return e;
+  if (device < 0 || device >= 64 || done[device]) return cudaSuccess;
+  cudaMemPool_t pool;
+  e = cudaDeviceGetDefaultMemPool(&pool, device);
+  if (e != cudaSuccess) return e;
+  uint64_t threshold = UINT64_MAX;
+  e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+  if (e == cudaSuccess) done[device] = true;
+  return e;
+}
+
 // ---- Benes network construction (looping algorithm) ---------------------------------
 // Stages: k = 0..5 swap distance 32 >> k (input side), k = 6..10 distance 2 << (k-6)
 // (output side).  out bit q = in bit src[q].

@@ -146,6 +146,7 @@ extern "C" {
 int asp_energy(uint64_t n, int64_t const *d_indptr, int32_t const *d_indices, double const *d_data,
                double const *d_field, uint32_t num_replicas, uint64_t const *d_bits, double *d_energy, void *stream) {
   auto s = static_cast<cudaStream_t>(stream);
+  ASP_CUDA_CHECK(asp::keep_pool_memory());
   if (num_replicas == 0) return ASP_OK;
   ASP_REQUIRE(d_energy && d_bits, "NULL buffer");
   if (n == 0) {
@@ -168,6 +169,7 @@ int asp_energy(uint64_t n, int64_t const *d_indptr, int32_t const *d_indices, do
 int asp_accuracy_overlap(uint64_t n, uint32_t num_replicas, uint64_t const *d_predicted, uint64_t const *d_exact,
                          double const *d_weights, double *d_accuracy, double *d_overlap, void *stream) {
   auto s = static_cast<cudaStream_t>(stream);
+  ASP_CUDA_CHECK(asp::keep_pool_memory());
   if (num_replicas == 0) return ASP_OK;
   ASP_REQUIRE(n > 0, "n must be positive");
   ASP_REQUIRE(d_predicted && d_exact && d_accuracy && d_overlap, "NULL buffer");
@@ -187,6 +189,7 @@ int asp_accuracy_overlap(uint64_t n, uint32_t num_replicas, uint64_t const *d_pr
 int asp_csr_symmetrize(uint64_t n, int64_t const *d_indptr, int32_t const *d_indices, double *d_data,
                        uint64_t *h_asymmetric, void *stream) {
   auto s = static_cast<cudaStream_t>(stream);
+  ASP_CUDA_CHECK(asp::keep_pool_memory());
   ASP_REQUIRE(h_asymmetric != nullptr, "h_asymmetric is NULL");
   *h_asymmetric = 0;
   if (n == 0) return ASP_OK;

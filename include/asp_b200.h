@@ -150,6 +150,7 @@ void asp_debug_set_extract_tuning(int filter_bits_delta, int table_bits_delta, i
 /* Measurement hook: when enabled, every launch of the single-pass extraction kernel is bracketed by
  * CUDA events on its own stream; the second call returns the device time of the LAST such launch
  * (milliseconds; synchronises on it; -1 if none). */
+void asp_debug_set_apply_mode(int mode); /* 1 = asp_operator_apply_dev always takes its general kernels */
 void asp_debug_time_extract_kernel(int enable);
 float asp_debug_last_extract_kernel_ms(void);
 

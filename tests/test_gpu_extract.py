@@ -237,6 +237,26 @@ def test_batched_apply_device_matches_oracle_including_symmetry_groups():
             np.testing.assert_allclose(got, exp, rtol=1e-12, atol=1e-300)
 
 
+def test_symmetrised_apply_fast_kernels_equal_the_general_ones_bitwise():
+    """All characters +1: counts without visiting orbits + the converged orbit walk
+    (apply_fill_positive_kernel) against the general move-by-move kernels."""
+    for system, m in [("heisenberg_kagome_36", 20000), ("heisenberg_pyrochlore_2x2x2", 5000), ("heisenberg_kagome_18", 24310)]:
+        op = asp.load_hamiltonian(asp.ls.system_path(system))
+        rows = op.basis.states if system == "heisenberg_kagome_18" else None
+        if rows is None:
+            rows = synthetic.cluster_closed_states(op, m, 9, DEV)
+        else:
+            rows = torch.from_numpy(np.ascontiguousarray(rows).view(np.int64)).to(DEV)
+        fast = op.batched_apply_device(rows)
+        lib().asp_debug_set_apply_mode(1)
+        try:
+            general = op.batched_apply_device(rows)
+        finally:
+            lib().asp_debug_set_apply_mode(0)
+        for a, b in zip(fast, general):
+            assert torch.equal(a, b), system
+
+
 def test_symmetrised_kagome_36_extraction_vs_oracle():
     """Full symmetrised path (orbit representatives + canonicalisation) on a subset of
     representatives of the 36-spin kagome basis."""

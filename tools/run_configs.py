@@ -33,14 +33,14 @@ def timed(fn, reps=3):
     return (time.perf_counter() - t0) / reps, out
 
 
-def sampled(system, states, replicas, sweeps):
-    op = u1(system)
+def sampled(system, states, replicas, sweeps, symmetrised=False):
+    op = asp.load_hamiltonian(asp.ls.system_path(system)) if symmetrised else u1(system)
     spins = synthetic.cluster_closed_states(op, states, 5, DEV)
     n = int(spins.shape[0])
     psi = synthetic.synthetic_amplitudes(n, 5, device=DEV)
     dt, (indptr, indices, data) = timed(lambda: common.extract_csr_device(op, spins, psi, nnz_hint=None))
     nnz = int(indices.numel())
-    print("%s: n=%d nnz=%d  extraction %.2f ms (%.3g couplings/s, %.3g candidates/s)" % (
+    print(("symmetrised " if symmetrised else "") + "%s: n=%d nnz=%d  extraction %.2f ms (%.3g couplings/s, %.3g candidates/s)" % (
         system, n, nnz, 1e3 * dt, nnz / dt, n * (op.max_candidates / 4.0 + 1) / dt), flush=True)
 
     class _Shape:
@@ -87,5 +87,7 @@ if __name__ == "__main__":
         sampled("sk_32_1", 1_000_000, 4096, 4)
     if "cfg5" in which:
         sampled("heisenberg_pyrochlore_2x2x2", 10_000_000, 64, 16)
+    if "cfg4sym" in which:  # symmetrised kagome_36 (|G| = 144 x spin inversion): integer-ALU-bound orbit representatives
+        sampled("heisenberg_kagome_36", 1_000_000, 64, 16, symmetrised=True)
     if "cfg4" in which:
         sampled("heisenberg_kagome_36", 10_000_000, 64, 16)
