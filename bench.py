@@ -255,9 +255,15 @@ def run_ours(args):
     del first
 
     def one_pass(timers=None):
+        ex = [torch.cuda.Event(enable_timing=True) for _ in range(2)] if (timers is not None and world > 1) else None
         if world > 1:  # X1: the exchange step of the path
+            if ex:
+                ex[0].record()
             full_spins = D.all_gather_blocks(my_spins, n_total)
             full_psi = D.all_gather_blocks(my_psi, n_total)
+            if ex:
+                ex[1].record()
+                exchange.append(ex)
         else:
             full_spins, full_psi = spins, psi
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)] if timers is not None else None
@@ -287,7 +293,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     launches0 = int(lib().asp_kernel_launch_count())
-    timers, kernel_only = [], []
+    timers, kernel_only, exchange = [], [], []
     lib().asp_debug_time_extract_kernel(1)  # CUDA events around extract_csr_kernel alone, on its own stream
     D.barrier()
     torch.cuda.synchronize()
@@ -312,10 +318,11 @@ def run_ours(args):
         "bound": "hbm", "kernel": "extract_csr_kernel", "achieved": algo_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peak,
         "unit": "GB/s", "frac": algo_bytes / (kernel_ms * 1e-3) / 1e9 / peak, "traffic": TRAFFIC_BYTES, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": kernel_ms, "call_ms": call_ms,
+        "exchange_ms": float(np.mean([e[0].elapsed_time(e[1]) for e in exchange])) if exchange else 0.0,
         "frac_whole_call": algo_bytes / (call_ms * 1e-3) / 1e9 / peak,
         "note": "kernel_ms: CUDA events around extract_csr_kernel alone on its launching stream (asp_debug_time_extract_kernel); "
                 "call_ms: events around the whole asp_extract_csr call (memset + build_index_kernel + extract_csr_kernel + 8-byte "
-                "count read-back); algorithmic bytes = 24 B/row + 20 B/coupling (SURVEY.md 8d); the kernel is bound by instruction "
+                "count read-back); exchange_ms: the two NCCL all-gathers of X1 (N > 1; includes waiting for the slowest rank); algorithmic bytes = 24 B/row + 20 B/coupling (SURVEY.md 8d); the kernel is bound by instruction "
                 "issue, not by HBM (DESIGN.md 4.1, profiles/)",
     }
     indptr, indices, data = out
