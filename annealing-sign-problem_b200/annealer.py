@@ -158,6 +158,16 @@ class AnnealPlan:
         return dict(order=order, class_ptr=class_ptr, indptr=indptr, indices=indices[:self.nnz],
                     data=data[:self.nnz], field=field)
 
+    def greedy_device(self):
+        """-> (bits [ceil(n/64)] int64 CUDA, energy f64 0-d CUDA, merge rounds, descent sweeps)."""
+        dev = require_cuda()
+        n = self.hamiltonian.size
+        bits = torch.zeros((n + 63) // 64, dtype=torch.int64, device=dev)
+        energy = torch.zeros(1, dtype=torch.float64, device=dev)
+        rounds, sweeps = ffi.new("uint32_t *"), ffi.new("uint32_t *")
+        check(lib().asp_greedy_solve(self.handle, ptr(bits, "uint64_t *"), ptr(energy, "double *"), rounds, sweeps, stream()))
+        return bits, energy[0], int(rounds[0]), int(sweeps[0])
+
     def anneal_device(self, repetitions: int, betas: np.ndarray, seed: int, x0: Optional[torch.Tensor] = None,
                       escale: Optional[float] = None, replica_offset: int = 0, want_energies: bool = True):
         """-> (best_bits [R, ceil(n/64)] int64 CUDA, energies [R] f64 CUDA)."""
@@ -199,4 +209,13 @@ def anneal(hamiltonian: Hamiltonian, x0=None, seed: Optional[int] = None, number
 
 
 def greedy_solve(hamiltonian: Hamiltonian):
-    raise NotImplementedError("sa.greedy_solve is the next row of the scope table (SURVEY.md 8f N1)")
+    """``sa.greedy_solve`` (common.py:249-250) -> (bits, energy): strongest couplings first (clusters
+    merge with the joining edge satisfied), then local descent until no flip lowers the energy
+    (asp_greedy_solve; algorithm and its two deviations from common.py:298-438 in csrc/greedy.cu)."""
+    dev = require_cuda()
+    plan = getattr(hamiltonian, "_plan", None)
+    if plan is None:
+        plan = AnnealPlan(hamiltonian)
+        hamiltonian._plan = plan
+    bits, energy, _, _ = plan.greedy_device()
+    return bits.cpu().numpy().view(np.uint64), float(energy)

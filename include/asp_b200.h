@@ -227,6 +227,18 @@ int asp_sa_plan_export(asp_sa_plan const *plan, int32_t *h_order, int64_t *h_cla
 int asp_sa_anneal(asp_sa_plan *plan, uint32_t num_replicas, uint32_t replica_offset,
                   uint32_t num_sweeps, double const *h_betas, uint64_t seed, uint64_t const *d_x0,
                   double energy_scale, uint64_t *d_best_bits, double *d_best_energy, void *stream);
+/* ------------------------------------------------------------------------------------
+ * 5. Greedy solver (replaces ising_glass_annealer.greedy_solve as called at common.py:249-250;
+ *    algorithm restated from the Python preserved at common.py:298-438, see csrc/greedy.cu):
+ *    strongest couplings first -- clusters merge with the joining edge satisfied (= maximum
+ *    spanning forest by |J|, built with Boruvka rounds) -- then local-descent sweeps in the
+ *    plan's position order until no flip lowers the energy.  Deterministic.
+ *    d_bits [ceil(n/64)] packed signs in ORIGINAL spin order; d_energy (may be NULL) the exact
+ *    energy; *h_rounds / *h_sweeps (may be NULL) merge rounds and descent sweeps performed.
+ * ---------------------------------------------------------------------------------- */
+int asp_greedy_solve(asp_sa_plan *plan, uint64_t *d_bits, double *d_energy, uint32_t *h_rounds,
+                     uint32_t *h_sweeps, void *stream);
+
 /* Number of kernel launches the library has issued in this process (bench accounting). */
 uint64_t asp_kernel_launch_count(void);
 

@@ -1,6 +1,6 @@
 """ctypes bindings of the CPU oracle libraries (TEST INFRASTRUCTURE ONLY).
 
-* ``oracle/_lib/liboracle.so``          -- extract_port.c + anneal_port.c (our restatements)
+* ``oracle/_lib/liboracle.so``          -- extract_port.c + anneal_port.c + greedy_port.c (our restatements)
 * ``oracle/_ref/libref_build_matrix.so`` -- the reference's cbits/build_matrix.c, compiled
   where it lies by ``oracle/Makefile``; exports the two symbols of cbits/build_matrix.h:7-14.
 """
@@ -58,6 +58,8 @@ def port():
         lib.oracle_philox4x32_10.argtypes = [_p, _p, _p]
         lib.oracle_exp_neg.restype = _f64
         lib.oracle_exp_neg.argtypes = [_f64]
+        lib.oracle_greedy.restype = _u32
+        lib.oracle_greedy.argtypes = [_u64, _p, _p, _p, _p, _p]
         lib.oracle_anneal.restype = None
         lib.oracle_anneal.argtypes = [_u64, _p, _p, _p, _p, _u32, _u32, _p, _u64, _p, _f64, _p, _p, _p, _u32]
         _port = lib
@@ -154,6 +156,18 @@ def energy(indptr, indices, data, field, bits) -> float:
     field = None if field is None else np.ascontiguousarray(field, dtype=np.float64)
     n = indptr.shape[0] - 1
     return float(port().oracle_energy(n, _ptr(indptr), _ptr(indices), _ptr(data), _ptr(field), _ptr(bits)))
+
+
+def greedy(indptr, indices, data, field):
+    """oracle/greedy_port.c on a CSR model (diagonal ignored) -> (spins int8 [+1/-1], sweeps)."""
+    indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+    indices = np.ascontiguousarray(indices, dtype=np.int32)
+    data = np.ascontiguousarray(data, dtype=np.float64)
+    field = None if field is None else np.ascontiguousarray(field, dtype=np.float64)
+    n = indptr.shape[0] - 1
+    spin = np.zeros(n, dtype=np.int8)
+    sweeps = int(port().oracle_greedy(n, _ptr(indptr), _ptr(indices), _ptr(data), _ptr(field), _ptr(spin)))
+    return spin, sweeps
 
 
 def philox(ctr, key):

@@ -236,3 +236,74 @@ def test_accuracy_and_overlap_restatement():
     assert abs(ov - abs(np.dot(a * b, w / w.sum()))) < 1e-15
     acc2, ov2 = live_path.compute_accuracy_and_overlap(live_path.signs_to_bits(-b), live_path.signs_to_bits(a), w)
     assert abs(acc2 - acc) < 1e-15 and abs(ov2 - ov) < 1e-15  # global-flip invariant
+
+
+def _python_greedy_reference(j, h):
+    """Plain-Python restatement of the same definition (Kruskal by |J| with edge-satisfying signs,
+    cluster normalisation, index-order descent) used to pin oracle/greedy_port.c on small cases."""
+    n = j.shape[0]
+    coo = j.tocoo()
+    edges = sorted(((-abs(v), int(r), int(c), v) for r, c, v in zip(coo.row, coo.col, coo.data) if r < c and v != 0.0))
+    cluster = list(range(n))
+    sign = [1] * n
+    members = {i: [i] for i in range(n)}
+    for _, a, b, v in edges:
+        ca, cb = cluster[a], cluster[b]
+        if ca == cb:
+            continue
+        if sign[a] * sign[b] * v > 0:  # frustrated: flip the second cluster
+            for q in members[cb]:
+                sign[q] = -sign[q]
+        for q in members[cb]:
+            cluster[q] = ca
+        members[ca] += members.pop(cb)
+    for c, ms in members.items():
+        if sign[min(ms)] < 0:
+            for q in ms:
+                sign[q] = -sign[q]
+    dense = j.toarray()
+    np.fill_diagonal(dense, 0.0)
+    csr = scipy.sparse.csr_matrix(j)
+    sweeps = 0
+    while True:
+        flips = 0
+        for i in range(n):
+            acc = 0.0
+            for k in range(csr.indptr[i], csr.indptr[i + 1]):
+                c = csr.indices[k]
+                if c != i:
+                    acc = acc + (csr.data[k] if sign[c] > 0 else -csr.data[k])
+            g = 4.0 * acc + 2.0 * h[i]
+            de = -g if sign[i] > 0 else g
+            if de < 0.0:
+                sign[i] = -sign[i]
+                flips += 1
+        sweeps += 1
+        if not flips:
+            break
+    return np.array(sign, dtype=np.int8), sweeps
+
+
+def test_greedy_port_matches_plain_python_and_is_a_local_minimum(oracle_capi):
+    """oracle/greedy_port.c (restated from the reference's preserved Python, common.py:298-438)
+    against a dictionary-based Python version of the same definition; the result is a local
+    minimum of E(s) = s^T J s + h^T s and, on a tree, the exact ground state."""
+    for seed, n, density, with_field in [(0, 12, 0.5, False), (1, 40, 0.2, True), (2, 200, 0.05, False), (3, 64, 0.0, False)]:
+        rng = np.random.default_rng(seed)
+        j = _random_model(n, density, rng)
+        h = rng.standard_normal(n) * 0.3 if with_field else np.zeros(n)
+        spin, sweeps = oracle_capi.greedy(j.indptr, j.indices, j.data, h)
+        ref, ref_sweeps = _python_greedy_reference(j, h)
+        assert np.array_equal(spin, ref) and sweeps == ref_sweeps
+        dense = j.toarray()
+        off = dense - np.diag(np.diag(dense))
+        s = spin.astype(np.float64)
+        de = -s * (4.0 * off @ s + 2.0 * h)
+        assert np.all(de >= 0.0)  # no single flip lowers the energy
+    # a tree (path with random couplings, no field): every edge can be satisfied -> global minimum
+    n = 50
+    w = np.random.default_rng(9).standard_normal(n - 1)
+    j = scipy.sparse.diags([w, w], [1, -1], shape=(n, n)).tocsr()
+    spin, _ = oracle_capi.greedy(j.indptr, j.indices, j.data, None)
+    s = spin.astype(np.float64)
+    assert abs(s @ (j @ s) + 2.0 * np.abs(w).sum()) < 1e-12 and spin[0] == 1
