@@ -54,8 +54,8 @@ def sampled(system, states, replicas, sweeps, symmetrised=False):
     betas = asp.sa.default_betas(ham, max(64, sweeps * 8))[:sweeps]
     escale = asp.sa.energy_scale(ham)
     dt, (bits, energies) = timed(lambda: plan.anneal_device(replicas, betas, 1, escale=escale), reps=2)
-    dt, (gbits, genergy, rounds, gsweeps) = timed(lambda: plan.greedy_device(), reps=2)
-    print("   greedy: %.1f ms (%d merge rounds, %d descent sweeps), E %.6f" % (1e3 * dt, rounds, gsweeps, float(genergy)), flush=True)
+    gdt, (gbits, genergy, rounds, gsweeps) = timed(lambda: plan.greedy_device(), reps=2)
+    print("   greedy: %.1f ms (%d merge rounds, %d descent sweeps), E %.6f" % (1e3 * gdt, rounds, gsweeps, float(genergy)), flush=True)
     print("   SA: %d replicas x %d sweeps: %.1f ms = %.3g proposals/s (plan %.0f ms, %d colour classes), best E %.6f" % (
         replicas, sweeps, 1e3 * dt, replicas * sweeps * n / dt, 1e3 * plan_s, plan.num_classes, float(energies.min())), flush=True)
 
