@@ -8,9 +8,12 @@ from .common import (  # noqa: F401
     IsingModel,
     binary_search,
     compute_accuracy_and_overlap,
+    get_strongest_off_diag,
     load_hamiltonian,
+    make_hamiltonian_extension,
     make_ising_model,
     solve_ising_model,
+    sparsify_using_global_cutoff,
 )
 from . import annealer as sa  # noqa: F401  (plays the role of `import ising_glass_annealer as sa`)
 from . import symmetries as ls  # noqa: F401  (plays the role of `import lattice_symmetries as ls`)

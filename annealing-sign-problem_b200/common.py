@@ -334,6 +334,94 @@ def binary_search(haystack, needles):  # common.py:544-548
     return indices
 
 
+# ---------------------------------------------------------------------------------------
+# Cluster extension and sparsification -- the callers around the extraction
+# (common.py:516-541, 621-692; experiments/sampled_connected_components.py:737-749)
+# ---------------------------------------------------------------------------------------
+def make_hamiltonian_extension(model: IsingModel, log_psi_fn: Callable) -> IsingModel:
+    """common.py:516-522: one batched_apply shell around the model's states, unique, new model."""
+    dev = require_cuda()
+    op = model.quantum_hamiltonian
+    if isinstance(op, ls.Operator):
+        d_spins = torch.from_numpy(np.ascontiguousarray(model.spins).view(np.int64)).to(dev)
+        other, _, _ = op.batched_apply_device(d_spins)
+        spins = _sort_unique_device(other)[0].cpu().numpy().view(np.uint64)
+    else:  # a foreign operator: chunks of 10 000 rows exactly as common.py:85-106
+        parts = []
+        for start in range(0, model.size, 10000):
+            x = np.zeros((min(start + 10000, model.size) - start, 8), dtype=np.uint64)
+            x[:, 0] = model.spins[start:start + 10000]
+            s, c, _ = op.batched_apply(x)
+            if not np.allclose(c.imag, 0, atol=1e-6):
+                raise ValueError("expected all Hamiltonian matrix elements to be real")
+            parts.append(np.ascontiguousarray(s[:, 0]))
+        spins = np.unique(np.hstack(parts))
+    return make_ising_model(spins, op, log_psi_fn=log_psi_fn)
+
+
+def _device_csr_of(matrix_or_hamiltonian):
+    if isinstance(matrix_or_hamiltonian, sa.Hamiltonian):
+        return matrix_or_hamiltonian.device_csr()[:3]
+    dev = require_cuda()
+    m = scipy.sparse.csr_matrix(matrix_or_hamiltonian)
+    m.sort_indices()
+    return (torch.from_numpy(m.indptr.astype(np.int64)).to(dev), torch.from_numpy(m.indices.astype(np.int32)).to(dev),
+            torch.from_numpy(np.ascontiguousarray(m.data, dtype=np.float64)).to(dev))
+
+
+def get_strongest_off_diag(matrix) -> np.ndarray:
+    """common.py:539-541: max_{j != i} |J_ij| per row (0 for rows without off-diagonal entries).
+    Accepts a scipy matrix or a :class:`sa.Hamiltonian` (then the device copy is used)."""
+    indptr, indices, data = _device_csr_of(matrix)
+    n = int(indptr.shape[0]) - 1
+    out = torch.zeros(n, dtype=torch.float64, device=indptr.device)
+    check(lib().asp_csr_strongest_offdiag(n, ptr(indptr, "int64_t *"), ptr(indices, "int32_t *"), ptr(data, "double *"),
+                                          ptr(out, "double *"), stream()))
+    return out.cpu().numpy()
+
+
+def sparsify_using_global_cutoff(model: IsingModel, reltol: float, frozen_spins) -> IsingModel:
+    """common.py:634-692: couplings below ``reltol * max|J|`` are dropped unless both spins are frozen;
+    the connected component that holds the frozen spins survives, with the ORIGINAL couplings among
+    its members (common.py:671)."""
+    dev = require_cuda()
+    frozen_indices = binary_search(model.spins, frozen_spins)
+    n = model.size
+    ham = model.ising_hamiltonian
+    indptr, indices, data, fld = ham.device_csr()
+    original_nnz = int(data.shape[0])
+    frozen = torch.zeros(n, dtype=torch.uint8, device=dev)
+    frozen[torch.from_numpy(np.asarray(frozen_indices, dtype=np.int64)).to(dev)] = 1
+    labels = torch.empty(n, dtype=torch.int32, device=dev)
+    check(lib().asp_cutoff_components(n, ptr(indptr, "int64_t *"), ptr(indices, "int32_t *"), ptr(data, "double *"), original_nnz,
+                                      float(reltol), ptr(frozen, "unsigned char *"), ptr(labels, "int32_t *"), stream()))
+    frozen_labels = labels[frozen.bool()]
+    magic = int(labels[int(frozen_indices[0])])
+    assert bool((frozen_labels == magic).all())  # common.py:667
+    keep_spin = labels == magic
+    new_index = torch.cumsum(keep_spin.to(torch.int64), 0) - 1
+    rows = torch.repeat_interleave(torch.arange(n, device=dev), indptr[1:] - indptr[:-1])
+    cols = indices.to(torch.int64)
+    keep = keep_spin[rows] & keep_spin[cols]
+    m = int(keep_spin.sum())
+    new_rows = new_index[rows[keep]]
+    new_indices = new_index[cols[keep]].to(torch.int32).contiguous()
+    new_data = data[keep].contiguous()
+    new_indptr = torch.zeros(m + 1, dtype=torch.int64, device=dev)
+    new_indptr[1:] = torch.cumsum(torch.bincount(new_rows, minlength=m), 0)
+    h_keep = keep_spin.cpu().numpy()
+    spins = model.spins[h_keep]
+    initial_signs = sa.signs_to_bits(sa.bits_to_signs(model.initial_signs, n)[h_keep])
+    matrix = scipy.sparse.csr_matrix((new_data.cpu().numpy(), new_indices.cpu().numpy(), new_indptr.cpu().numpy().astype(np.int32)),
+                                     shape=(m, m))
+    field = (fld.cpu().numpy() if fld is not None else np.zeros(n))[h_keep]
+    new_field = None if fld is None else fld[keep_spin].contiguous()
+    new_model = IsingModel(spins, model.quantum_hamiltonian,
+                           sa.Hamiltonian(matrix, field, _device_csr=(new_indptr, new_indices, new_data, new_field)), initial_signs)
+    logger.info("number of spins: {} -> {}; number of connections: {} -> {}", n, new_model.size, original_nnz, int(new_data.shape[0]))
+    return new_model
+
+
 def solve_ising_model(
     model: IsingModel,
     mode: str = "sa",

@@ -4,6 +4,8 @@
 //   asp_accuracy_overlap  replaces compute_accuracy_and_overlap (common.py:211-229)
 //   asp_csr_symmetrize    replaces 0.5*(M + M.T) (common.py:194) for structurally symmetric J
 // All reductions are two-stage with a fixed tree, so results do not depend on scheduling.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace asp {
@@ -137,6 +139,74 @@ __global__ void __launch_bounds__(kRedThreads) symmetrize_kernel(uint64_t n, con
   }
 }
 
+
+// ---- cluster sparsification helpers -----------------------------------------------
+// strongest off-diagonal coupling of every row (common.py:525-541)
+__global__ void __launch_bounds__(kRedThreads) strongest_offdiag_kernel(uint64_t n, const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                                                                        const double *__restrict__ data, double *__restrict__ out) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kRedThreads + threadIdx.x;
+  if (i >= n) return;
+  double best = 0.0;
+  for (int64_t k = indptr[i]; k < indptr[i + 1]; ++k)
+    if (static_cast<uint64_t>(indices[k]) != i) best = fmax(best, fabs(data[k]));
+  out[i] = best;
+}
+
+// max |data| (non-negative doubles order like their bit patterns)
+__global__ void __launch_bounds__(kRedThreads) max_abs_kernel(uint64_t m, const double *__restrict__ data, unsigned long long *__restrict__ out) {
+  unsigned long long best = 0;
+  for (uint64_t k = static_cast<uint64_t>(blockIdx.x) * kRedThreads + threadIdx.x; k < m; k += static_cast<uint64_t>(gridDim.x) * kRedThreads)
+    best = max(best, static_cast<unsigned long long>(__double_as_longlong(fabs(data[k]))));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if ((threadIdx.x & 31) == 0 && best) atomicMax(out, best);
+}
+
+// an entry survives the global cutoff (common.py:621-631) when it is non-zero and either not below
+// reltol * max|J| or between two frozen spins
+__device__ __forceinline__ bool survives_cutoff(double v, double cutoff, bool both_frozen) { return v != 0.0 && (both_frozen || !(fabs(v) < cutoff)); }
+
+// connected components of the surviving couplings: minimum-label propagation + pointer jumping;
+// labels only ever decrease and stay inside the component, so unsynchronised updates are benign.
+// Converges to label = smallest vertex of the component.
+__global__ void __launch_bounds__(kRedThreads) cc_propagate_kernel(uint64_t n, const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                                                                   const double *__restrict__ data, const unsigned long long *__restrict__ max_bits,
+                                                                   double reltol, const unsigned char *__restrict__ frozen, int32_t *labels,
+                                                                   unsigned int *__restrict__ changed) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kRedThreads + threadIdx.x;
+  if (i >= n) return;
+  const double cutoff = reltol * __longlong_as_double(static_cast<long long>(*max_bits));
+  const int32_t mine = labels[i];
+  int32_t best = mine;
+  const bool fi = frozen && frozen[i];
+  for (int64_t k = indptr[i]; k < indptr[i + 1]; ++k) {
+    const int32_t j = indices[k];
+    if (survives_cutoff(data[k], cutoff, fi && frozen[j])) best = min(best, labels[j]);
+  }
+  if (best < mine) {
+    atomicMin(&labels[i], best);
+    atomicMin(&labels[mine], best);  // hook the old representative as well
+    *changed = 1u;
+  }
+}
+
+__global__ void __launch_bounds__(kRedThreads) cc_jump_kernel(uint64_t n, int32_t *labels) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kRedThreads + threadIdx.x;
+  if (i >= n) return;
+  int32_t l = labels[i];
+  for (;;) {
+    const int32_t up = labels[l];
+    if (up == l) break;
+    l = up;
+  }
+  labels[i] = l;
+}
+
+__global__ void __launch_bounds__(kRedThreads) iota_kernel(uint64_t n, int32_t *labels) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kRedThreads + threadIdx.x;
+  if (i < n) labels[i] = static_cast<int32_t>(i);
+}
+
 }  // namespace asp
 
 using namespace asp;
@@ -209,5 +279,54 @@ int asp_csr_symmetrize(uint64_t n, int64_t const *d_indptr, int32_t const *d_ind
   ASP_LAUNCH_CHECK();
   return ASP_OK;
 }
+
+int asp_csr_strongest_offdiag(uint64_t n, int64_t const *d_indptr, int32_t const *d_indices, double const *d_data,
+                              double *d_out, void *stream) {
+  auto s = static_cast<cudaStream_t>(stream);
+  if (n == 0) return ASP_OK;
+  ASP_REQUIRE(d_indptr && d_out, "NULL buffer");
+  strongest_offdiag_kernel<<<static_cast<unsigned>((n + kRedThreads - 1) / kRedThreads), kRedThreads, 0, s>>>(n, d_indptr, d_indices, d_data, d_out);
+  ASP_LAUNCH_CHECK();
+  return ASP_OK;
+}
+
+int asp_cutoff_components(uint64_t n, int64_t const *d_indptr, int32_t const *d_indices, double const *d_data, uint64_t nnz,
+                          double reltol, unsigned char const *d_frozen, int32_t *d_labels, void *stream) {
+  auto s = static_cast<cudaStream_t>(stream);
+  ASP_CUDA_CHECK(asp::keep_pool_memory());
+  if (n == 0) return ASP_OK;
+  ASP_REQUIRE(d_indptr && d_labels, "NULL buffer");
+  ASP_REQUIRE(n < (1ull << 31), "labels are int32");
+  unsigned long long *scratch = nullptr;  // [0] max |J| bits, [1] changed flag
+  ASP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&scratch), 2 * sizeof(unsigned long long), s));
+  ASP_CUDA_CHECK(cudaMemsetAsync(scratch, 0, 2 * sizeof(unsigned long long), s));
+  const unsigned blocks = static_cast<unsigned>((n + kRedThreads - 1) / kRedThreads);
+  if (nnz) {
+    max_abs_kernel<<<static_cast<unsigned>(std::min<uint64_t>((nnz + kRedThreads - 1) / kRedThreads, 4 * 148)), kRedThreads, 0, s>>>(nnz, d_data, scratch);
+    ASP_LAUNCH_CHECK();
+  }
+  iota_kernel<<<blocks, kRedThreads, 0, s>>>(n, d_labels);
+  ASP_LAUNCH_CHECK();
+  unsigned int *changed = reinterpret_cast<unsigned int *>(scratch + 1);
+  for (int round = 0;; ++round) {
+    ASP_CUDA_CHECK(cudaMemsetAsync(changed, 0, sizeof(unsigned int), s));
+    cc_propagate_kernel<<<blocks, kRedThreads, 0, s>>>(n, d_indptr, d_indices, d_data, scratch, reltol, d_frozen, d_labels, changed);
+    ASP_LAUNCH_CHECK();
+    cc_jump_kernel<<<blocks, kRedThreads, 0, s>>>(n, d_labels);
+    ASP_LAUNCH_CHECK();
+    unsigned int h = 0;
+    ASP_CUDA_CHECK(cudaMemcpyAsync(&h, changed, sizeof(h), cudaMemcpyDeviceToHost, s));
+    ASP_CUDA_CHECK(cudaStreamSynchronize(s));
+    if (!h) break;
+    if (round > 100000) {
+      cudaFreeAsync(scratch, s);
+      asp::set_error("connected components did not converge");
+      return ASP_ERR_CUDA;
+    }
+  }
+  ASP_CUDA_CHECK(cudaFreeAsync(scratch, s));
+  return ASP_OK;
+}
+
 
 }  // extern "C"

@@ -239,6 +239,20 @@ int asp_sa_anneal(asp_sa_plan *plan, uint32_t num_replicas, uint32_t replica_off
 int asp_greedy_solve(asp_sa_plan *plan, uint64_t *d_bits, double *d_energy, uint32_t *h_rounds,
                      uint32_t *h_sweeps, void *stream);
 
+/* ------------------------------------------------------------------------------------
+ * 6. Cluster sparsification helpers (callers around the extraction).
+ *    asp_csr_strongest_offdiag: out[i] = max_{j != i} |J_ij| (get_strongest_off_diag,
+ *    common.py:525-541).  asp_cutoff_components: connected components of the couplings that
+ *    survive the global cutoff of sparsify_using_global_cutoff (common.py:621-662): an entry
+ *    survives when it is non-zero and (|J_ij| >= reltol * max|J| or both spins are frozen;
+ *    d_frozen [n] bytes, may be NULL); d_labels[i] = smallest vertex of i's component.
+ * ---------------------------------------------------------------------------------- */
+int asp_csr_strongest_offdiag(uint64_t n, int64_t const *d_indptr, int32_t const *d_indices,
+                              double const *d_data, double *d_out, void *stream);
+int asp_cutoff_components(uint64_t n, int64_t const *d_indptr, int32_t const *d_indices,
+                          double const *d_data, uint64_t nnz, double reltol,
+                          unsigned char const *d_frozen, int32_t *d_labels, void *stream);
+
 /* Number of kernel launches the library has issued in this process (bench accounting). */
 uint64_t asp_kernel_launch_count(void);
 

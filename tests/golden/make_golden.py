@@ -28,7 +28,7 @@ ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
 sys.path.insert(0, ROOT)
 
 from oracle import capi  # noqa: E402
-from oracle.live_path import signs_to_bits  # noqa: E402
+from oracle.live_path import bits_to_signs, signs_to_bits  # noqa: E402
 from oracle.operator_np import OperatorNP, ground_state, system_path  # noqa: E402
 
 
@@ -41,6 +41,7 @@ def import_reference_common():
     sa = types.ModuleType("ising_glass_annealer")
     sa.Hamiltonian = Hamiltonian
     sa.signs_to_bits = signs_to_bits
+    sa.bits_to_signs = bits_to_signs
     ls = types.ModuleType("lattice_symmetries")
     ls.Operator = object
     ls.SpinBasis = object
@@ -122,6 +123,54 @@ def one_case(ref_common, name, n_target, seed, out):
         os.path.basename(out), os.path.getsize(out)))
 
 
+def hashed_log_psi(spins):
+    """Deterministic log-amplitude of a basis state (stands in for the noisy ground-state lookup of
+    sampled_connected_components.py:699-722): log|psi| + i*pi*[psi < 0], a function of the state only."""
+    h = (np.asarray(spins, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)) >> np.uint64(11)
+    u = h.astype(np.float64) / 2.0 ** 53
+    v = ((np.asarray(spins, dtype=np.uint64) * np.uint64(0xC2B2AE3D27D4EB4F)) >> np.uint64(63)).astype(np.float64)
+    return 4.0 * (u - 0.5) + 1j * np.pi * v
+
+
+def extension_case(ref_common, name, n_target, seed, reltol, out):
+    """Row N2 of the scope table, produced by the reference itself: make_hamiltonian_extension
+    (common.py:516-522), get_strongest_off_diag (common.py:539-541) and
+    sparsify_using_global_cutoff (common.py:634-692) on a sampled cluster."""
+    import scipy.sparse
+    from scipy.sparse.csgraph import connected_components
+
+    rng = np.random.default_rng(seed)
+    op = OperatorNP.load(system_path(name))
+    cluster = cluster_closed_subset(op, n_target, rng)
+    model0 = ref_common.make_ising_model(cluster, op, log_psi_fn=hashed_log_psi)
+    model1 = ref_common.make_hamiltonian_extension(model0, hashed_log_psi)
+    strongest = ref_common.get_strongest_off_diag(model1.ising_hamiltonian.exchange)
+    # the reference slices `exchange[mask][:, mask]` (common.py:671): its annealer's Hamiltonian must hold
+    # a sliceable matrix; give the stub's the CSR form of the same COO matrix
+    model1.ising_hamiltonian.exchange = model1.ising_hamiltonian.exchange.tocsr()
+    # frozen spins: members of the original cluster that stay connected under the cutoff
+    m = model1.ising_hamiltonian.exchange.tocsr().copy()
+    big = np.abs(m.data).max()
+    m.data[np.abs(m.data) < reltol * big] = 0
+    m.eliminate_zeros()
+    _, comp = connected_components(m, directed=False)
+    idx = np.searchsorted(model1.spins, cluster)
+    magic = np.bincount(comp[idx]).argmax()
+    frozen = cluster[comp[idx] == magic][:40]
+    model2 = ref_common.sparsify_using_global_cutoff(model1, reltol, frozen)
+    c1 = model1.ising_hamiltonian.exchange.tocoo()
+    c2 = model2.ising_hamiltonian.exchange.tocoo()
+    np.savez_compressed(
+        out, system=name, cluster=cluster, reltol=reltol, frozen=frozen,
+        ext_spins=model1.spins, ext_row=c1.row.astype(np.int32), ext_col=c1.col.astype(np.int32), ext_data=c1.data,
+        ext_x0=model1.initial_signs, strongest=strongest,
+        sp_spins=model2.spins, sp_row=c2.row.astype(np.int32), sp_col=c2.col.astype(np.int32), sp_data=c2.data,
+        sp_x0=model2.initial_signs, sp_field=model2.ising_hamiltonian.field)
+    print("%-28s cluster=%d extension=%d (nnz %d) sparsified=%d (nnz %d) frozen=%d -> %s (%d bytes)" % (
+        name, cluster.shape[0], model1.spins.shape[0], c1.nnz, model2.spins.shape[0], c2.nnz, frozen.shape[0],
+        os.path.basename(out), os.path.getsize(out)))
+
+
 def known_answers(out):
     """Full-basis known-answer table, recomputed by the oracle's ED."""
     table = {}
@@ -146,6 +195,8 @@ def main():
     one_case(ref_common, "heisenberg_kagome_18", 900, 2, os.path.join(HERE, "live_heisenberg_kagome_18.npz"))
     one_case(ref_common, "sk_16_1", 300, 3, os.path.join(HERE, "live_sk_16_1.npz"))
     known_answers(os.path.join(HERE, "known_answers.json"))
+    extension_case(ref_common, "heisenberg_kagome_16", 120, 4, 2e-2, os.path.join(HERE, "n2_heisenberg_kagome_16.npz"))
+    extension_case(ref_common, "j1j2_square_4x4", 80, 5, 5e-2, os.path.join(HERE, "n2_j1j2_square_4x4.npz"))
 
 
 if __name__ == "__main__":

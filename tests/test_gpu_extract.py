@@ -441,3 +441,71 @@ def test_one_call_host_pipeline_with_row_chunks():
         rc = lib().asp_extract_host(op.handle, n, c(h_spins, "uint64_t *"), c(h_psi, "double *"), lo, rows, m // 2,
                                     c(hp, "int64_t *"), c(hi, "int32_t *"), c(hd, "double *"), nnz)
         assert rc == lib().ASP_ERR_WORKSPACE and int(nnz[0]) == m and np.array_equal(hp, indptr.cpu().numpy())
+
+
+def _golden_log_psi(spins):
+    """tests/golden/make_golden.py:hashed_log_psi (the amplitude model the N2 vectors were made with)."""
+    s = np.asarray(spins, dtype=np.uint64)
+    u = ((s * np.uint64(0x9E3779B97F4A7C15)) >> np.uint64(11)).astype(np.float64) / 2.0 ** 53
+    v = ((s * np.uint64(0xC2B2AE3D27D4EB4F)) >> np.uint64(63)).astype(np.float64)
+    return 4.0 * (u - 0.5) + 1j * np.pi * v
+
+
+@pytest.mark.parametrize("name", ["n2_heisenberg_kagome_16", "n2_j1j2_square_4x4"])
+def test_cluster_extension_and_sparsification_match_the_reference(golden_dir, name):
+    """SURVEY 8f N2 against vectors produced by the reference's OWN make_hamiltonian_extension
+    (common.py:516-522), get_strongest_off_diag (:539-541) and sparsify_using_global_cutoff
+    (:634-692): same states, same sparsity pattern, couplings to 1e-12, same packed signs."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    op = asp.load_hamiltonian(asp.ls.system_path(str(g["system"])))
+    model0 = asp.make_ising_model(g["cluster"], op, log_psi_fn=_golden_log_psi)
+    model1 = asp.make_hamiltonian_extension(model0, _golden_log_psi)
+    assert np.array_equal(model1.spins, g["ext_spins"])
+    n1 = model1.size
+    ref1 = scipy.sparse.coo_matrix((g["ext_data"], (g["ext_row"], g["ext_col"])), shape=(n1, n1)).tocsr()
+    _assert_same_matrix(model1.ising_hamiltonian.exchange.tocsr(), ref1)
+    assert np.array_equal(model1.initial_signs, g["ext_x0"])
+    for arg in (model1.ising_hamiltonian, model1.ising_hamiltonian.exchange):
+        np.testing.assert_allclose(asp.get_strongest_off_diag(arg), g["strongest"], rtol=1e-12, atol=0)
+    model2 = asp.sparsify_using_global_cutoff(model1, float(g["reltol"]), g["frozen"])
+    assert np.array_equal(model2.spins, g["sp_spins"])
+    n2 = model2.size
+    ref2 = scipy.sparse.coo_matrix((g["sp_data"], (g["sp_row"], g["sp_col"])), shape=(n2, n2)).tocsr()
+    _assert_same_matrix(model2.ising_hamiltonian.exchange.tocsr(), ref2)
+    assert np.array_equal(model2.initial_signs, g["sp_x0"]) and np.array_equal(model2.ising_hamiltonian.field, g["sp_field"])
+    # the sparsified model is a working Ising model: its device copy anneals
+    x = asp.solve_ising_model(model2, mode="sa", seed=1, number_sweeps=50, repetitions=32)
+    assert x.shape == ((n2 + 63) // 64,)
+    with pytest.raises(AssertionError):  # frozen spins that are not part of the model (common.py:544-548)
+        asp.sparsify_using_global_cutoff(model1, float(g["reltol"]), np.array([int(g["ext_spins"][0]) + 1], dtype=np.uint64))
+
+
+def test_cutoff_components_equal_scipy_on_random_graphs():
+    from scipy.sparse.csgraph import connected_components
+
+    rng = np.random.default_rng(3)
+    for n, density, reltol in [(1, 0.0, 0.5), (500, 0.004, 0.0), (20000, 0.00008, 0.3), (5000, 0.0006, 0.6)]:
+        a = scipy.sparse.random(n, n, density=density, random_state=rng, data_rvs=rng.standard_normal).tocsr()
+        a = (a + a.T).tocsr()
+        a.sort_indices()
+        frozen = (rng.random(n) < 0.05).astype(np.uint8)
+        data = a.data.copy()
+        if data.size:
+            rows = np.repeat(np.arange(n), np.diff(a.indptr))
+            big = np.abs(data).max()
+            drop = (np.abs(data) < reltol * big) & ~((frozen[rows] == 1) & (frozen[a.indices] == 1))
+            data[drop] = 0
+        b = scipy.sparse.csr_matrix((data, a.indices.copy(), a.indptr.copy()), shape=(n, n))  # eliminate_zeros works in place
+        b.eliminate_zeros()
+        _, ref = connected_components(b, directed=False)
+        labels = torch.empty(n, dtype=torch.int32, device=DEV)
+        t = lambda x, dt: torch.from_numpy(np.ascontiguousarray(x, dtype=dt)).to(DEV)  # noqa: E731
+        indptr, indices, vals, fr = t(a.indptr, np.int64), t(a.indices, np.int32), t(a.data, np.float64), t(frozen, np.uint8)
+        common.check(lib().asp_cutoff_components(n, common.ptr(indptr, "int64_t *"), common.ptr(indices, "int32_t *"),
+                                                 common.ptr(vals, "double *"), a.nnz, reltol, common.ptr(fr, "unsigned char *"),
+                                                 common.ptr(labels, "int32_t *"), common.stream()))
+        got = labels.cpu().numpy()
+        # same partition; our label is the smallest vertex of the component
+        smallest = np.full(ref.max() + 1, n, dtype=np.int64)
+        np.minimum.at(smallest, ref, np.arange(n))
+        assert np.array_equal(got, smallest[ref])
