@@ -161,6 +161,23 @@ def extract_csr_device(operator: ls.Operator, spins: torch.Tensor, psi: torch.Te
                                             max_row_len=operator.max_candidates)
 
 
+def extract_csr_indexed_device(operator: ls.Operator, spins: torch.Tensor, psi: torch.Tensor, row_begin: int, num_rows: int,
+                               workspace: torch.Tensor, capacity: int):
+    """Single-pass extraction on a workspace already indexed by asp_gather_index (the sharded path,
+    distributed.PeerBasis.gather_index).  -> (indptr, indices[:nnz], data[:nnz]); raises when
+    ``capacity`` is too small (the caller sized it from an earlier pass, like the C contract)."""
+    dev = require_cuda()
+    indptr = torch.empty(num_rows + 1, dtype=torch.int64, device=dev)
+    indices = torch.empty(capacity, dtype=torch.int32, device=dev)
+    data = torch.empty(capacity, dtype=torch.float64, device=dev)
+    nnz = ffi.new("uint64_t *")
+    check(lib().asp_extract_csr_indexed(operator.handle, int(spins.shape[0]), ptr(spins, "uint64_t *"), ptr(psi, "double *"),
+                                        row_begin, num_rows, ptr(workspace, "void *"), workspace.numel(), capacity,
+                                        ptr(indptr, "int64_t *"), ptr(indices, "int32_t *"), ptr(data, "double *"), nnz, stream()))
+    m = int(nnz[0])
+    return indptr, indices[:m], data[:m]
+
+
 def build_csr_from_candidates_device(spins, psi, row_begin, other_spins, other_coeffs, other_counts, max_row_len=0):
     """Explicit-candidate path (what cbits/build_matrix.c does) + canonical CSR."""
     dev = require_cuda()

@@ -210,6 +210,159 @@ __global__ void __launch_bounds__(256) build_index_kernel(const uint64_t *__rest
   }
 }
 
+// ---- X1 fused with the index build: pull every rank's row block over NVLink peer memory ----------
+// One kernel replaces ncclAllGather(keys) + ncclAllGather(amplitudes) + build_index_kernel: the blocks
+// of the sorted basis live in buffers the other processes of the node have mapped (CUDA IPC);
+// a thread pulls two consecutive keys and amplitudes of one block with 16-byte loads (several in
+// flight), writes the rank's private full copy and indexes the keys (first-position table + Bloom
+// filter) while the next loads travel.  Blocks are visited in ring order rank+1, rank+2, ... so that
+// at any time the ranks pull from different peers.  A CTA waits (system-scope acquire) for the
+// "ready" flag of the blocks it touches; 10 s without it is a dead peer -> trap (never hang the box).
+constexpr int kGxMaxRanks = 16;
+constexpr int kGxThreads = 256;
+constexpr int kGxUnroll = 4;  // key pairs per thread
+
+struct GatherArgs {
+  const uint64_t *shard_spins[kGxMaxRanks];
+  const double *shard_psi[kGxMaxRanks];
+  uint64_t begin[kGxMaxRanks + 1];       // global index of the first key of every block
+  uint64_t unit_begin[kGxMaxRanks + 1];  // first key pair of the k-th VISITED block
+  int order[kGxMaxRanks];                // k-th visited block
+  int world;
+  const unsigned long long *ready;  // local flags [world] (NULL: no waiting)
+  unsigned long long epoch;
+  uint64_t *spins;  // [n] private full copy (out)
+  double *psi;
+  uint32_t n;
+  uint64_t state_mask, num_buckets;
+  int tshift, fshift;
+  uint32_t *starts;
+  uint2 *filter;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void wait_flag_or_trap(const unsigned long long *flag, unsigned long long value) {
+  if (ld_acquire_sys(flag) >= value) return;
+  const unsigned long long t0 = global_timer_ns();
+  unsigned ns = 64;
+  while (ld_acquire_sys(flag) < value) {
+    __nanosleep(ns);
+    if (ns < 2048) ns <<= 1;
+    if (global_timer_ns() - t0 > 10000000000ull) __trap();
+  }
+}
+// Coherent (not .nc) loads: the data was released by another GPU in this very epoch.
+__device__ __forceinline__ ulonglong2 ld_peer_v2(const void *p) {
+  ulonglong2 v;
+  asm volatile("ld.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_peer_u64(const void *p) {
+  unsigned long long v;
+  asm volatile("ld.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ void index_one(const GatherArgs &a, uint64_t i, uint64_t key, bool has_prev, uint64_t pk) {
+  const uint64_t last = a.num_buckets;
+  const uint64_t b = (key & ~a.state_mask) ? last : key >> a.tshift;
+  const uint64_t prev = has_prev ? ((pk & ~a.state_mask) ? last : pk >> a.tshift) + 1 : 0;
+  for (uint64_t k = prev; k <= b && k <= last; ++k) a.starts[k] = static_cast<uint32_t>(i);
+  if (i == a.n - 1)
+    for (uint64_t k = b + 1; k <= last; ++k) a.starts[k] = a.n;
+  if ((key & ~a.state_mask) == 0) {
+    const uint32_t h = filter_hash(key);
+    uint2 *w = a.filter + (key >> a.fshift);
+    atomicOr(&w->x, 1u << (h & 31u));
+    atomicOr(&w->y, 1u << ((h >> 8) & 31u));
+  }
+}
+
+__global__ void __launch_bounds__(kGxThreads) gather_index_kernel(const GatherArgs a) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t units = a.unit_begin[a.world];
+  const uint64_t cta_first = static_cast<uint64_t>(blockIdx.x) * (kGxThreads * kGxUnroll);
+  if (cta_first >= units) return;
+  if (a.ready != nullptr) {
+    if (threadIdx.x == 0) {
+      const uint64_t cta_last = min(cta_first + kGxThreads * kGxUnroll, units) - 1;
+      for (int k = 0; k < a.world; ++k)
+        if (a.unit_begin[k] <= cta_last && a.unit_begin[k + 1] > cta_first) wait_flag_or_trap(a.ready + a.order[k], a.epoch);
+    }
+    __syncthreads();
+  }
+  ulonglong2 keys[kGxUnroll], amps[kGxUnroll];
+  uint64_t g[kGxUnroll];   // global index of the pair's first key (n: none)
+  uint32_t cnt[kGxUnroll]; // keys of the pair (0, 1 or 2)
+  int blk[kGxUnroll];
+  uint64_t loc[kGxUnroll];
+#pragma unroll
+  for (int j = 0; j < kGxUnroll; ++j) {
+    const uint64_t u = cta_first + static_cast<uint64_t>(j) * kGxThreads + threadIdx.x;
+    cnt[j] = 0;
+    g[j] = a.n;
+    blk[j] = 0;
+    loc[j] = 0;
+    keys[j] = make_ulonglong2(0, 0);
+    amps[j] = make_ulonglong2(0, 0);
+    if (u < units) {
+      int k = 0;
+      while (u >= a.unit_begin[k + 1]) ++k;
+      const int q = a.order[k];
+      const uint64_t l = 2 * (u - a.unit_begin[k]), len = a.begin[q + 1] - a.begin[q];
+      blk[j] = q;
+      loc[j] = l;
+      g[j] = a.begin[q] + l;
+      if (l + 1 < len) {
+        cnt[j] = 2;
+        keys[j] = ld_peer_v2(a.shard_spins[q] + l);
+        amps[j] = ld_peer_v2(a.shard_psi[q] + l);
+      } else {
+        cnt[j] = 1;
+        keys[j].x = ld_peer_u64(a.shard_spins[q] + l);
+        amps[j].x = ld_peer_u64(a.shard_psi[q] + l);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kGxUnroll; ++j) {
+    // predecessor of the pair's first key: the neighbouring lane holds it unless this pair opens a
+    // block (then it is the last key of the block before) or the lane is 0
+    const uint64_t up = __shfl_up_sync(0xffffffffu, keys[j].y, 1);
+    if (cnt[j] == 0) continue;
+    uint64_t pk = up;
+    bool has_prev = true;
+    if (loc[j] == 0) {
+      has_prev = g[j] > 0;
+      if (has_prev) {
+        int p = blk[j] - 1;
+        while (a.begin[p + 1] == a.begin[p]) --p;  // skip empty blocks; g > 0 => one is not
+        if (a.ready != nullptr) wait_flag_or_trap(a.ready + p, a.epoch);  // a block this CTA may not have waited for
+        pk = ld_peer_u64(a.shard_spins[p] + (a.begin[p + 1] - a.begin[p] - 1));
+      }
+    } else if (lane == 0) {
+      pk = ld_peer_u64(a.shard_spins[blk[j]] + loc[j] - 1);
+    }
+    a.spins[g[j]] = keys[j].x;
+    reinterpret_cast<unsigned long long *>(a.psi)[g[j]] = amps[j].x;
+    index_one(a, g[j], keys[j].x, has_prev, pk);
+    if (cnt[j] == 2) {
+      a.spins[g[j] + 1] = keys[j].y;
+      reinterpret_cast<unsigned long long *>(a.psi)[g[j] + 1] = amps[j].y;
+      index_one(a, g[j] + 1, keys[j].y, true, keys[j].x);
+    }
+  }
+}
+
 // Position of c (< 2^number_spins) in the sorted basis, or -1.
 __device__ __forceinline__ int32_t search_one(const FusedArgs &a, uint64_t c) {
   const uint32_t *bucket = a.starts + (c >> a.tshift);
@@ -745,6 +898,58 @@ int fused_prepare(const asp_operator *op, uint64_t n_total, const uint64_t *d_sp
   return ASP_OK;
 }
 
+// X1 + index in one kernel: see gather_index_kernel.  Host arrays: shard_begin[world+1],
+// d_shard_spins/d_shard_psi[world] (device pointers valid on this device: own memory or IPC-mapped).
+int fused_prepare_gather(const asp_operator *op, uint32_t world, uint32_t rank, const uint64_t *shard_begin,
+                         const uint64_t *const *d_shard_spins, const double *const *d_shard_psi, const uint64_t *d_ready,
+                         uint64_t epoch, uint64_t *d_spins, double *d_psi, uint64_t num_rows, void *d_workspace,
+                         size_t workspace_bytes, cudaStream_t s) {
+  ASP_REQUIRE(world >= 1 && world <= static_cast<uint32_t>(kGxMaxRanks) && rank < world, "world size must be in 1..16");
+  const uint64_t n_total = shard_begin[world];
+  ASP_REQUIRE(shard_begin[0] == 0, "shard_begin[0] must be 0");
+  FusedWorkspace w = carve_fused(d_workspace, op, n_total, num_rows);
+  if (d_workspace == nullptr || workspace_bytes < w.bytes) {
+    set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+    return ASP_ERR_WORKSPACE;
+  }
+  GatherArgs a{};
+  a.world = static_cast<int>(world);
+  uint64_t units = 0;
+  for (uint32_t k = 0; k < world; ++k) {
+    const uint32_t q = (rank + 1 + k) % world;  // own block last
+    ASP_REQUIRE(shard_begin[q + 1] >= shard_begin[q], "shard_begin must be non-decreasing");
+    a.order[k] = static_cast<int>(q);
+    a.unit_begin[k] = units;
+    units += (shard_begin[q + 1] - shard_begin[q] + 1) / 2;
+  }
+  a.unit_begin[world] = units;
+  for (uint32_t q = 0; q < world; ++q) {
+    ASP_REQUIRE(shard_begin[q + 1] == shard_begin[q] || (d_shard_spins[q] && d_shard_psi[q]), "NULL shard pointer");
+    ASP_REQUIRE((reinterpret_cast<uintptr_t>(d_shard_spins[q]) & 15u) == 0 && (reinterpret_cast<uintptr_t>(d_shard_psi[q]) & 15u) == 0,
+                "shard buffers must be 16-byte aligned");
+    a.shard_spins[q] = d_shard_spins[q];
+    a.shard_psi[q] = d_shard_psi[q];
+    a.begin[q] = shard_begin[q];
+  }
+  a.begin[world] = n_total;
+  a.ready = reinterpret_cast<const unsigned long long *>(d_ready);
+  a.epoch = epoch;
+  a.spins = d_spins;
+  a.psi = d_psi;
+  a.n = static_cast<uint32_t>(n_total);
+  a.state_mask = op->state_mask;
+  a.num_buckets = w.num_buckets;
+  a.tshift = w.tshift;
+  a.fshift = w.fshift;
+  a.starts = w.starts;
+  a.filter = w.filter;
+  ASP_CUDA_CHECK(cudaMemsetAsync(static_cast<char *>(d_workspace) + w.zero_offset, 0, w.zero_bytes, s));
+  const uint64_t per_cta = static_cast<uint64_t>(kGxThreads) * kGxUnroll;
+  gather_index_kernel<<<static_cast<unsigned>((units + per_cta - 1) / per_cta), kGxThreads, 0, s>>>(a);
+  ASP_LAUNCH_CHECK();
+  return ASP_OK;
+}
+
 // Rows [row_begin + chunk_begin, +chunk_rows) of the block that starts at row_begin: chunk
 // number `chunk` (< kFxMaxChunks) of a call whose earlier chunks cover [0, chunk_begin).
 // d_indptr is the BLOCK's indptr; offsets continue from the previous chunk's total.
@@ -851,10 +1056,10 @@ size_t asp_extract_csr_workspace_bytes(asp_operator const *op, uint64_t n_total,
   return fused_workspace_bytes(op, n_total, num_rows);
 }
 
-int asp_extract_csr(asp_operator const *op, uint64_t n_total, uint64_t const *d_spins, double const *d_psi,
-                    uint64_t row_begin, uint64_t num_rows, void *d_workspace, size_t workspace_bytes,
-                    uint64_t capacity, int64_t *d_indptr, int32_t *d_indices, double *d_data, uint64_t *h_nnz,
-                    void *stream) {
+static int extract_csr_impl(asp_operator const *op, uint64_t n_total, uint64_t const *d_spins, double const *d_psi,
+                            uint64_t row_begin, uint64_t num_rows, void *d_workspace, size_t workspace_bytes,
+                            uint64_t capacity, int64_t *d_indptr, int32_t *d_indices, double *d_data, uint64_t *h_nnz,
+                            void *stream, bool indexed) {
   auto s = static_cast<cudaStream_t>(stream);
   int rc = fused_check_operator(op);
   if (rc != ASP_OK) return rc;
@@ -871,8 +1076,12 @@ int asp_extract_csr(asp_operator const *op, uint64_t n_total, uint64_t const *d_
     return ASP_OK;
   }
   ASP_REQUIRE(d_spins && d_psi, "NULL input buffer");
-  rc = fused_prepare(op, n_total, d_spins, num_rows, d_workspace, workspace_bytes, s);
-  if (rc != ASP_OK) return rc;
+  if (indexed) {  // the workspace was zeroed and indexed for this very (n_total, num_rows) by asp_gather_index
+    ASP_REQUIRE(d_workspace != nullptr && workspace_bytes >= fused_workspace_bytes(op, n_total, num_rows), "workspace too small");
+  } else {
+    rc = fused_prepare(op, n_total, d_spins, num_rows, d_workspace, workspace_bytes, s);
+    if (rc != ASP_OK) return rc;
+  }
   rc = fused_launch(op, n_total, d_spins, d_psi, row_begin, num_rows, 0, 0, num_rows, d_workspace, capacity, d_indptr, d_indices,
                     d_data, nullptr, s);
   if (rc != ASP_OK) return rc;
@@ -888,6 +1097,36 @@ int asp_extract_csr(asp_operator const *op, uint64_t n_total, uint64_t const *d_
     }
   }
   return ASP_OK;
+}
+
+int asp_extract_csr(asp_operator const *op, uint64_t n_total, uint64_t const *d_spins, double const *d_psi,
+                    uint64_t row_begin, uint64_t num_rows, void *d_workspace, size_t workspace_bytes,
+                    uint64_t capacity, int64_t *d_indptr, int32_t *d_indices, double *d_data, uint64_t *h_nnz,
+                    void *stream) {
+  return extract_csr_impl(op, n_total, d_spins, d_psi, row_begin, num_rows, d_workspace, workspace_bytes, capacity, d_indptr,
+                          d_indices, d_data, h_nnz, stream, /*indexed=*/false);
+}
+
+int asp_gather_index(asp_operator const *op, uint32_t world, uint32_t rank, uint64_t const *shard_begin,
+                     uint64_t const *const *d_shard_spins, double const *const *d_shard_psi, uint64_t const *d_ready,
+                     uint64_t epoch, uint64_t *d_spins, double *d_psi, uint64_t num_rows, void *d_workspace,
+                     size_t workspace_bytes, void *stream) {
+  int rc = fused_check_operator(op);
+  if (rc != ASP_OK) return rc;
+  ASP_REQUIRE(shard_begin && d_shard_spins && d_shard_psi, "NULL shard table");
+  ASP_REQUIRE(world >= 1 && world <= 16, "world size must be in 1..16");
+  ASP_REQUIRE(shard_begin[world] > 0 && shard_begin[world] < (1ull << 31), "the gathered basis needs 0 < n_total < 2^31");
+  ASP_REQUIRE(d_spins && d_psi, "NULL output buffer");
+  return fused_prepare_gather(op, world, rank, shard_begin, d_shard_spins, d_shard_psi, d_ready, epoch, d_spins, d_psi, num_rows,
+                              d_workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int asp_extract_csr_indexed(asp_operator const *op, uint64_t n_total, uint64_t const *d_spins, double const *d_psi,
+                            uint64_t row_begin, uint64_t num_rows, void *d_workspace, size_t workspace_bytes,
+                            uint64_t capacity, int64_t *d_indptr, int32_t *d_indices, double *d_data, uint64_t *h_nnz,
+                            void *stream) {
+  return extract_csr_impl(op, n_total, d_spins, d_psi, row_begin, num_rows, d_workspace, workspace_bytes, capacity, d_indptr,
+                          d_indices, d_data, h_nnz, stream, /*indexed=*/true);
 }
 
 }  // extern "C"

@@ -9,6 +9,10 @@ shards naturally, so only two exchange steps exist:
 
 Row blocks and replica blocks are contiguous and deterministic, so the sharded result is
 bit-identical to the single-GPU one (KAT-7).
+
+X1 has two implementations: ``all_gather_blocks`` (NCCL; gloo in CPU tests) and ``PeerBasis``
+(the row blocks stay in NVLink peer memory and ONE kernel pulls + indexes them:
+asp_gather_index, csrc/extract_fused.cu -- the fast path on a B200 node).
 """
 from __future__ import annotations
 
@@ -59,6 +63,128 @@ def all_gather_blocks(local: torch.Tensor, total: int) -> torch.Tensor:
     dist.all_gather_into_tensor(gathered, padded)
     parts = [gathered[r * longest: r * longest + sizes[r]] for r in range(world)]
     return torch.cat(parts)
+
+
+class _RawDeviceMemory:
+    """Zero-copy torch view of memory the C library allocated (``torch.as_tensor`` honours
+    ``__cuda_array_interface__``)."""
+
+    def __init__(self, address: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (address, False), "version": 2}
+
+
+class PeerBasis:
+    """X1 over NVLink peer memory: this rank's row block of the sorted basis (keys + amplitudes)
+    lives in a buffer every other process of the node maps through CUDA IPC.
+
+    Per exchange epoch (all calls enqueue on the current stream; ranks are ordered by epoch flags
+    in peer memory, not by host barriers or NCCL calls):
+
+        pb.begin_epoch()            # waits until every peer has finished READING my previous block
+        pb.spins[:m] = ...; pb.psi[:m] = ...   # produce the block in place (or leave it)
+        pb.publish()                # release: "my block is complete for this epoch" -> all peers
+        full_spins, full_psi = pb.gather_index(op, shard_begin, num_rows, workspace)
+                                    # ONE kernel: pull all blocks, private full copy, table + filter
+        pb.release()                # "I have finished reading this epoch" -> all peers
+        ... asp_extract_csr_indexed on the indexed workspace ...
+    """
+
+    FLAG_BYTES = 256  # ready[16] u64 at +0, done[16] u64 at +128
+    DONE_SLOT = 16
+
+    def __init__(self, capacity_rows: int, device=None):
+        from ._lib import check, ffi, lib, require_cuda
+
+        self.device = device if device is not None else require_cuda()
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        if self.world > 16:
+            raise ValueError("PeerBasis supports at most 16 ranks (one NVSwitch domain)")
+        self.capacity = (int(capacity_rows) + 31) // 32 * 32
+        nbytes = self.FLAG_BYTES + 16 * self.capacity
+        own = ffi.new("void **")
+        handle = ffi.new("unsigned char[64]")
+        check(lib().asp_peer_alloc(nbytes, own, handle))
+        self._own = int(ffi.cast("uintptr_t", own[0]))
+        self._opened = []
+        bases = [0] * self.world
+        bases[self.rank] = self._own
+        if self.world > 1:
+            mine = (bytes(ffi.buffer(handle, 64)), self.capacity)
+            every = [None] * self.world
+            dist.all_gather_object(every, mine)
+            if any(cap != self.capacity for _, cap in every):
+                raise ValueError("PeerBasis: every rank must pass the same capacity_rows")
+            for q, (h, _) in enumerate(every):
+                if q == self.rank:
+                    continue
+                out = ffi.new("void **")
+                check(lib().asp_peer_open(ffi.from_buffer("unsigned char[]", h), out))
+                bases[q] = int(ffi.cast("uintptr_t", out[0]))
+                self._opened.append(bases[q])
+        self._bases = bases
+        raw = torch.as_tensor(_RawDeviceMemory(self._own, nbytes), device=self.device)
+        self._raw = raw
+        body = raw[self.FLAG_BYTES:]
+        self.spins = body[: 8 * self.capacity].view(torch.int64)
+        self.psi = body[8 * self.capacity:].view(torch.float64)
+        self._flags = ffi.new("uint64_t *[]", [ffi.cast("uint64_t *", b) for b in bases])
+        self._shard_spins = ffi.new("uint64_t const *[]", [ffi.cast("uint64_t const *", b + self.FLAG_BYTES) for b in bases])
+        self._shard_psi = ffi.new("double const *[]", [ffi.cast("double const *", b + self.FLAG_BYTES + 8 * self.capacity) for b in bases])
+        self.epoch = 0
+        self._full = None
+
+    # -- epoch protocol ------------------------------------------------------------------------
+    def begin_epoch(self):
+        from ._lib import check, ffi, lib, stream
+
+        self.epoch += 1
+        if self.epoch > 1:
+            check(lib().asp_peer_wait(self.world, ffi.cast("uint64_t const *", self._own + 8 * self.DONE_SLOT), self.epoch - 1, stream()))
+
+    def publish(self):
+        from ._lib import check, lib, stream
+
+        check(lib().asp_peer_signal(self.world, self._flags, self.rank, self.epoch, stream()))
+
+    def release(self):
+        from ._lib import check, lib, stream
+
+        check(lib().asp_peer_signal(self.world, self._flags, self.DONE_SLOT + self.rank, self.epoch, stream()))
+
+    def gather_index(self, operator, shard_begin, num_rows: int, workspace: torch.Tensor):
+        """-> (full_spins int64 [n_total], full_psi f64 [n_total]); ``workspace`` is left indexed
+        for asp_extract_csr_indexed(operator, n_total, ..., num_rows)."""
+        from ._lib import check, ffi, lib, ptr, stream
+
+        begins = [int(b) for b in shard_begin]
+        assert len(begins) == self.world + 1 and begins[0] == 0
+        assert all(begins[q + 1] - begins[q] <= self.capacity for q in range(self.world))
+        n_total = begins[-1]
+        if self._full is None or self._full[0].shape[0] != n_total:
+            self._full = (torch.empty(n_total, dtype=torch.int64, device=self.device),
+                          torch.empty(n_total, dtype=torch.float64, device=self.device))
+        full_spins, full_psi = self._full
+        check(lib().asp_gather_index(operator.handle, self.world, self.rank, ffi.new("uint64_t[]", begins), self._shard_spins,
+                                     self._shard_psi, ffi.cast("uint64_t const *", self._own), self.epoch,
+                                     ptr(full_spins, "uint64_t *"), ptr(full_psi, "double *"), num_rows,
+                                     ptr(workspace, "void *"), workspace.numel(), stream()))
+        return full_spins, full_psi
+
+    def close(self):
+        """Unmap the peers' blocks, then (after a host barrier: nobody may still map it) free ours."""
+        from ._lib import ffi, lib
+
+        if self._own == 0:
+            return
+        torch.cuda.synchronize()
+        self.spins = self.psi = self._raw = self._full = None
+        for address in self._opened:
+            lib().asp_peer_close(ffi.cast("void *", address))
+        self._opened = []
+        barrier()
+        lib().asp_peer_free(ffi.cast("void *", self._own))
+        self._own = 0
 
 
 def exclusive_offset(local_count: int, device) -> Tuple[int, int]:

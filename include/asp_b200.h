@@ -253,6 +253,47 @@ int asp_cutoff_components(uint64_t n, int64_t const *d_indptr, int32_t const *d_
                           double const *d_data, uint64_t nnz, double reltol,
                           unsigned char const *d_frozen, int32_t *d_labels, void *stream);
 
+/* ------------------------------------------------------------------------------------
+ * 7. Multi-GPU exchange X1 over NVLink peer memory (one process per GPU).
+ *    The reference is single-process: every caller holds the whole basis (common.py:146).
+ *    Sharded, every rank needs all row blocks of the sorted basis.  The blocks live in
+ *    peer buffers (device memory other processes map through a 64-byte CUDA IPC handle
+ *    that travels over any host channel); asp_gather_index pulls them over NVLink, writes
+ *    the rank's private full copy AND indexes it in ONE kernel (replaces
+ *    ncclAllGather x2 + the index pass of asp_extract_csr); asp_extract_csr_indexed then
+ *    runs the single-pass extraction on the indexed workspace.
+ *    Epoch flags (uint64 arrays in peer memory, zeroed by asp_peer_alloc) order the ranks on
+ *    the device: asp_peer_signal stores `value` into d_flags[p][slot] of every rank p
+ *    (system-scope release, stream-ordered after the caller's earlier work);
+ *    asp_peer_wait / asp_gather_index spin until flags[q] >= value (system-scope acquire;
+ *    10 s without progress traps instead of hanging the device).
+ * ---------------------------------------------------------------------------------- */
+int asp_peer_alloc(size_t bytes, void **d_ptr, unsigned char *handle /* [64] out */);
+int asp_peer_open(unsigned char const *handle /* [64] */, void **d_ptr);
+int asp_peer_close(void *d_ptr);
+int asp_peer_free(void *d_ptr);
+int asp_peer_signal(uint32_t world, uint64_t *const *d_flags /* host [world] of device ptrs */,
+                    uint32_t slot, uint64_t value, void *stream);
+int asp_peer_wait(uint32_t world, uint64_t const *d_flags /* device [world] */, uint64_t value,
+                  void *stream);
+/* shard_begin: host [world+1], global index of every block's first key (shard_begin[world] =
+ * n_total); d_shard_spins / d_shard_psi: host [world] of device pointers (16-byte aligned; own
+ * or peer-mapped).  d_ready: this rank's flag array [world] (NULL = blocks are already
+ * complete); block q is read once d_ready[q] >= epoch.  d_spins / d_psi [n_total]: private
+ * full copy (out).  d_workspace: asp_extract_csr_workspace_bytes(op, n_total, num_rows). */
+int asp_gather_index(asp_operator const *op, uint32_t world, uint32_t rank,
+                     uint64_t const *shard_begin, uint64_t const *const *d_shard_spins,
+                     double const *const *d_shard_psi, uint64_t const *d_ready, uint64_t epoch,
+                     uint64_t *d_spins, double *d_psi, uint64_t num_rows, void *d_workspace,
+                     size_t workspace_bytes, void *stream);
+/* asp_extract_csr without its zero + index pass: the workspace was prepared by asp_gather_index
+ * for the same (op, n_total, num_rows) on the same stream. */
+int asp_extract_csr_indexed(asp_operator const *op, uint64_t n_total, uint64_t const *d_spins,
+                            double const *d_psi, uint64_t row_begin, uint64_t num_rows,
+                            void *d_workspace, size_t workspace_bytes, uint64_t capacity,
+                            int64_t *d_indptr, int32_t *d_indices, double *d_data, uint64_t *h_nnz,
+                            void *stream);
+
 /* Number of kernel launches the library has issued in this process (bench accounting). */
 uint64_t asp_kernel_launch_count(void);
 

@@ -213,6 +213,54 @@ def test_row_block_shards_concatenate_to_the_unsharded_result():
         assert torch.equal(torch.cat(glued), indptr)
 
 
+def test_gather_index_kernel_over_emulated_shards_equals_the_unsharded_build():
+    """X1 fused with the index build (asp_gather_index): the basis handed over as row blocks of odd,
+    even and zero length (here all on one device) must give the same private copy, the same index and
+    hence the same CSR, bit for bit, as asp_extract_csr on the whole array."""
+    op = _u1_operator("heisenberg_kagome_36")
+    spins = synthetic.cluster_closed_states(op, 50_001, 5, DEV)
+    n = int(spins.shape[0])
+    psi = synthetic.synthetic_amplitudes(n, 5, device=DEV)
+    ref = common.extract_csr_device(op, spins, psi)
+    for bounds in ([0, n], [0, 1, n], [0, 12_345, 12_345, 30_000, n], [0, 0, 7, 4_096, 20_001, 20_002, n, n]):
+        world = len(bounds) - 1
+        parts_s = [spins[bounds[q]:bounds[q + 1]].clone() if bounds[q + 1] > bounds[q] else torch.zeros(2, dtype=torch.int64, device=DEV) for q in range(world)]
+        parts_p = [psi[bounds[q]:bounds[q + 1]].clone() if bounds[q + 1] > bounds[q] else torch.zeros(2, dtype=torch.float64, device=DEV) for q in range(world)]
+        for rank in {0, world - 1, world // 2}:
+            row_begin, num_rows = bounds[rank], bounds[rank + 1] - bounds[rank]
+            need = int(lib().asp_extract_csr_workspace_bytes(op.handle, n, num_rows))
+            workspace = torch.empty(need, dtype=torch.uint8, device=DEV)
+            full_s = torch.zeros(n, dtype=torch.int64, device=DEV)
+            full_p = torch.zeros(n, dtype=torch.float64, device=DEV)
+            common.check(lib().asp_gather_index(
+                op.handle, world, rank, ffi.new("uint64_t[]", bounds),
+                ffi.new("uint64_t const *[]", [common.ptr(t, "uint64_t const *") for t in parts_s]),
+                ffi.new("double const *[]", [common.ptr(t, "double const *") for t in parts_p]),
+                ffi.NULL, 0, common.ptr(full_s, "uint64_t *"), common.ptr(full_p, "double *"), num_rows,
+                common.ptr(workspace, "void *"), need, common.stream()))
+            assert torch.equal(full_s, spins) and torch.equal(full_p, psi)
+            if num_rows == 0:
+                continue
+            indptr, indices, data = common.extract_csr_indexed_device(op, full_s, full_p, row_begin, num_rows, workspace,
+                                                                      capacity=int(ref[1].numel()))
+            lo, hi = int(ref[0][row_begin]), int(ref[0][row_begin + num_rows])
+            assert torch.equal(indptr, ref[0][row_begin:row_begin + num_rows + 1] - lo)
+            assert torch.equal(indices, ref[1][lo:hi]) and torch.equal(data, ref[2][lo:hi])
+
+
+def test_peer_memory_exchange_on_two_gpus():
+    """X1 over NVLink peer memory with real processes: tests/_peer_sharding.py under torchrun, 2 ranks."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run: gpurun --gpus 2 -- python -m pytest tests -m gpu -k peer_memory)")
+    import subprocess
+    import sys
+
+    script = os.path.join(os.path.dirname(__file__), "_peer_sharding.py")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29541", script], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "PEER_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
 def test_batched_apply_device_matches_oracle_including_symmetry_groups():
     """Neighbour generation incl. orbit representatives / norms for the full kagome_36
     (|G| = 144 x 2) and pyrochlore (|G| = 384 x 2) groups; canonical per-row comparison."""
