@@ -122,6 +122,12 @@ __host__ __device__ __forceinline__ uint32_t filter_hash(uint64_t key) {
   return y;
 }
 
+// The two bits as one 64-bit word (uint2 {x, y} little endian): the index kernels set them with ONE
+// 64-bit atomic -- the index build is bound by L2 atomic throughput.
+__host__ __device__ __forceinline__ unsigned long long filter_bits(uint32_t h) {
+  return (1ull << (h & 31u)) | (1ull << (32u + ((h >> 8) & 31u)));
+}
+
 // Loads that bypass L1 allocation: filter words, table entries, keys and gathered amplitudes are
 // touched once per SM, while the warp's hit list (written, then read back) should stay in L1.
 #ifndef ASP_FX_STREAM_FILTER
@@ -204,9 +210,7 @@ __global__ void __launch_bounds__(256) build_index_kernel(const uint64_t *__rest
     for (uint64_t k = b + 1; k <= last; ++k) starts[k] = n;
   if ((key & ~state_mask) == 0) {
     const uint32_t h = filter_hash(key);
-    uint2 *w = filter + (key >> fshift);
-    atomicOr(&w->x, 1u << (h & 31u));
-    atomicOr(&w->y, 1u << ((h >> 8) & 31u));
+    atomicOr(reinterpret_cast<unsigned long long *>(filter + (key >> fshift)), filter_bits(h));  // one RED.OR.64 per key
   }
 }
 
@@ -272,19 +276,14 @@ __device__ __forceinline__ unsigned long long ld_peer_u64(const void *p) {
   return v;
 }
 
-__device__ __forceinline__ void index_one(const GatherArgs &a, uint64_t i, uint64_t key, bool has_prev, uint64_t pk) {
+// First-position table entries owed by key i (predecessor pk): buckets (bucket(pk), bucket(key)].
+__device__ __forceinline__ void index_table(const GatherArgs &a, uint64_t i, uint64_t key, bool has_prev, uint64_t pk) {
   const uint64_t last = a.num_buckets;
   const uint64_t b = (key & ~a.state_mask) ? last : key >> a.tshift;
   const uint64_t prev = has_prev ? ((pk & ~a.state_mask) ? last : pk >> a.tshift) + 1 : 0;
   for (uint64_t k = prev; k <= b && k <= last; ++k) a.starts[k] = static_cast<uint32_t>(i);
   if (i == a.n - 1)
     for (uint64_t k = b + 1; k <= last; ++k) a.starts[k] = a.n;
-  if ((key & ~a.state_mask) == 0) {
-    const uint32_t h = filter_hash(key);
-    uint2 *w = a.filter + (key >> a.fshift);
-    atomicOr(&w->x, 1u << (h & 31u));
-    atomicOr(&w->y, 1u << ((h >> 8) & 31u));
-  }
 }
 
 __global__ void __launch_bounds__(kGxThreads) gather_index_kernel(const GatherArgs a) {
@@ -354,12 +353,24 @@ __global__ void __launch_bounds__(kGxThreads) gather_index_kernel(const GatherAr
     }
     a.spins[g[j]] = keys[j].x;
     reinterpret_cast<unsigned long long *>(a.psi)[g[j]] = amps[j].x;
-    index_one(a, g[j], keys[j].x, has_prev, pk);
+    index_table(a, g[j], keys[j].x, has_prev, pk);
+    const bool in0 = (keys[j].x & ~a.state_mask) == 0;
+    const uint64_t w0 = keys[j].x >> a.fshift;
+    unsigned long long bits0 = filter_bits(filter_hash(keys[j].x));
     if (cnt[j] == 2) {
       a.spins[g[j] + 1] = keys[j].y;
       reinterpret_cast<unsigned long long *>(a.psi)[g[j] + 1] = amps[j].y;
-      index_one(a, g[j] + 1, keys[j].y, true, keys[j].x);
+      index_table(a, g[j] + 1, keys[j].y, true, keys[j].x);
+      if ((keys[j].y & ~a.state_mask) == 0) {
+        const uint64_t w1 = keys[j].y >> a.fshift;
+        const unsigned long long bits1 = filter_bits(filter_hash(keys[j].y));
+        if (in0 && w1 == w0)
+          bits0 |= bits1;  // sorted keys: neighbours often share a filter word -> one atomic for both
+        else
+          atomicOr(reinterpret_cast<unsigned long long *>(a.filter + w1), bits1);
+      }
     }
+    if (in0) atomicOr(reinterpret_cast<unsigned long long *>(a.filter + w0), bits0);
   }
 }
 

@@ -43,6 +43,9 @@ def parse_args():
     p.add_argument("--replicas", type=int, default=64, help="annealing replicas per GPU")
     p.add_argument("--sweeps", type=int, default=16, help="annealing sweeps per step")
     p.add_argument("--cpu-sample", type=int, default=200_000, help="states of the bounded CPU-baseline sample")
+    p.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                   help="X1 at N > 1: 'peer' = row blocks in NVLink peer memory, one kernel pulls + indexes them; "
+                        "'nccl' = two all-gathers + index pass (the baseline)")
     p.add_argument("--skip-anneal", action="store_true")
     p.add_argument("--skip-cpu", action="store_true")
     p.add_argument("--skip-e2e", action="store_true")
@@ -254,9 +257,28 @@ def run_ours(args):
     capacity = nnz_known + nnz_known // 16
     del first
 
+    bounds = [D.block(n_total, r, world)[0] for r in range(world)] + [n_total]
+    peer = None
+    if world > 1 and args.exchange == "peer":
+        peer = D.PeerBasis(max(bounds[r + 1] - bounds[r] for r in range(world)), dev)
+        peer.spins[:num_rows] = my_spins
+        peer.psi[:num_rows] = my_psi
+
     def one_pass(timers=None):
         ex = [torch.cuda.Event(enable_timing=True) for _ in range(2)] if (timers is not None and world > 1) else None
-        if world > 1:  # X1: the exchange step of the path
+        indexed = False
+        if peer is not None:  # X1 fused with the index build, over NVLink peer memory
+            peer.begin_epoch()  # every peer has finished reading my previous block ...
+            peer.publish()      # ... which a real caller would now have rewritten in place
+            if ex:
+                ex[0].record()
+            full_spins, full_psi = peer.gather_index(op, bounds, num_rows, workspace)
+            if ex:
+                ex[1].record()
+                exchange.append(ex)
+            peer.release()
+            indexed = True
+        elif world > 1:  # X1 through NCCL: two all-gathers, then asp_extract_csr indexes the result
             if ex:
                 ex[0].record()
             full_spins = D.all_gather_blocks(my_spins, n_total)
@@ -273,10 +295,11 @@ def run_ours(args):
         if ev:
             ev[0].record()
         nnz = ffi.new("uint64_t *")
-        common.check(lib().asp_extract_csr(op.handle, n_total, common.ptr(full_spins, "uint64_t *"), common.ptr(full_psi, "double *"),
-                                           row_begin, num_rows, common.ptr(workspace, "void *"), workspace.numel(), capacity,
-                                           common.ptr(indptr, "int64_t *"), common.ptr(indices, "int32_t *"),
-                                           common.ptr(data, "double *"), nnz, common.stream()))
+        extract = lib().asp_extract_csr_indexed if indexed else lib().asp_extract_csr
+        common.check(extract(op.handle, n_total, common.ptr(full_spins, "uint64_t *"), common.ptr(full_psi, "double *"),
+                             row_begin, num_rows, common.ptr(workspace, "void *"), workspace.numel(), capacity,
+                             common.ptr(indptr, "int64_t *"), common.ptr(indices, "int32_t *"),
+                             common.ptr(data, "double *"), nnz, common.stream()))
         if ev:
             ev[1].record()
             timers.append(ev)
@@ -443,11 +466,13 @@ def run_ours(args):
             "config": {"workload": "heisenberg_kagome_36-shaped U(1) basis (36 spins, 72 bonds), %d sampled states per GPU, "
                                    "cluster-closed subset, Ising extraction to CSR" % args.states,
                        "states_total": n_total, "rows_per_gpu": num_rows, "couplings_total": int(nnz_total),
-                       "candidates_per_row": 37.0, "parallelism": "row blocks x%d, basis all-gathered" % world,
+                       "candidates_per_row": 37.0, "parallelism": "row blocks x%d, basis exchanged every step (%s)" % (world, "none" if world == 1 else args.exchange),
                        "l2": "inputs (%.0f MB) larger than L2" % ((n_total * 16 + need) / 1e6)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "anneal": anneal,
         }
         print(json.dumps(line))
+    if peer is not None:
+        peer.close()
     if world > 1:
         import torch.distributed as dist
 
