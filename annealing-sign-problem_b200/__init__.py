@@ -6,6 +6,13 @@ __version__ = "0.1.0"
 
 from .common import (  # noqa: F401
     IsingModel,
+    SamplingResult,
+    add_noise_to_amplitudes,
+    amplitude_overlap,
+    create_small_cluster_around_point,
+    determine_exact_solution,
+    ground_state_to_log_coeff_fn,
+    monte_carlo_sampling,
     binary_search,
     compute_accuracy_and_overlap,
     get_strongest_off_diag,

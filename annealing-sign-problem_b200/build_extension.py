@@ -20,7 +20,7 @@ ROOT = os.path.dirname(HERE)
 HEADER = os.path.join(ROOT, "include", "asp_b200.h")
 CSRC = os.path.join(HERE, "csrc")
 LIBRARY = os.path.join(HERE, "libasp_b200.so")
-SOURCES = ["operator.cu", "extract.cu", "extract_fused.cu", "legacy.cu", "reduce.cu", "anneal.cu", "greedy.cu", "apply.cu", "host.cu", "peer.cu"]
+SOURCES = ["operator.cu", "extract.cu", "extract_fused.cu", "legacy.cu", "reduce.cu", "anneal.cu", "greedy.cu", "apply.cu", "host.cu", "peer.cu", "sampling.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

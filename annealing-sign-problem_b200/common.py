@@ -467,3 +467,113 @@ def solve_ising_model(
         frozen_signs = frozen_signs[frozen_indices]
         x = sa.signs_to_bits(frozen_signs)
     return x
+
+
+# ---------------------------------------------------------------------------------------
+# Sampling front-end and frozen-spin glue -- common.py:262-285, 481-513,
+# 806-838; experiments/sampled_connected_components.py:653-669, 719-723
+# ---------------------------------------------------------------------------------------
+@dataclass
+class SamplingResult:  # common.py:262-265
+    spins: np.ndarray
+    weights: Optional[np.ndarray]
+
+
+def sample_indices_device(ground_state: torch.Tensor, uniform: torch.Tensor, sampled_power: float = 2) -> torch.Tensor:
+    """Index draws of ``np.random.choice(n, m, replace=True, p=|psi|^power/sum)`` for the given
+    uniform numbers: cumulative sum, normalisation and the m searches run on the device."""
+    dev = require_cuda()
+    out = torch.empty(uniform.shape[0], dtype=torch.int64, device=dev)
+    check(lib().asp_sample_indices(ground_state.shape[0], ptr(ground_state, "double *"), float(sampled_power), uniform.shape[0],
+                                   ptr(uniform, "double *"), ptr(out, "int64_t *"), ffi.NULL, stream()))
+    return out
+
+
+def monte_carlo_sampling(states, ground_state, number_samples: int, sampled_power: float = 2) -> SamplingResult:
+    """common.py:268-278.  The uniform numbers come from numpy's GLOBAL legacy stream exactly as
+    ``np.random.choice`` would draw them (``random_sample(number_samples)``), so after
+    ``np.random.seed(k)`` the sampled states are the reference's."""
+    dev = require_cuda()
+    states = np.asarray(states)
+    psi = torch.from_numpy(np.ascontiguousarray(ground_state, dtype=np.float64)).to(dev)
+    if psi.ndim != 1 or psi.shape[0] != len(states):
+        raise ValueError("'states' and 'ground_state' must be one-dimensional and of equal length")
+    uniform = torch.from_numpy(np.random.random_sample(int(number_samples))).to(dev)
+    indices = sample_indices_device(psi, uniform, sampled_power).cpu().numpy()
+    return SamplingResult(spins=states[indices], weights=None)
+
+
+def determine_exact_solution(spins, quantum_hamiltonian, ground_state):  # common.py:282-285
+    indices = quantum_hamiltonian.basis.batched_index(spins)
+    psi = np.asarray(ground_state)[indices]
+    return sa.signs_to_bits(np.sign(psi))
+
+
+def create_small_cluster_around_point(s0: int, hamiltonian, required_size: int = 20, keep_probability: float = 0.5):
+    """common.py:481-513: random breadth-first growth around ``s0`` (sequential by construction: one
+    np.random.rand() per not-yet-visited child, in the operator's neighbour order)."""
+    assert hamiltonian.basis.number_spins <= 64
+    s0 = int(s0)
+    spins = {s0}
+
+    def children_of(s):
+        xs, _ = hamiltonian.apply(s)
+        if xs.ndim > 1:
+            xs = xs[:, 0]
+        children = []
+        for x in xs:
+            if x in spins:
+                continue
+            if np.random.rand() <= keep_probability:
+                children.append(int(x))
+        return children
+
+    children = children_of(s0)
+    while len(spins) < required_size and len(children) > 0:
+        new_children = set()
+        for child in children:
+            spins.add(child)
+            if len(spins) >= required_size:
+                break
+            new_children |= set(children_of(child))
+        children = new_children
+    return sorted(list(spins))
+
+
+def ground_state_to_log_coeff_fn(ground_state: np.ndarray, basis: ls.SpinBasis):
+    """common.py:806-823: spins -> log|psi| + i*pi*[psi < 0], looked up in the full basis (device
+    search, asp_batched_index)."""
+    ground_state = np.asarray(ground_state, dtype=np.float64, order="C")
+    assert ground_state.ndim == 1
+    with np.errstate(divide="ignore"):
+        log_amplitudes = np.log(np.abs(ground_state))
+    phases = np.where(ground_state >= 0, 0, np.pi)
+
+    def log_coeff_fn(spins: np.ndarray) -> np.ndarray:
+        spins = np.asarray(spins, dtype=np.uint64, order="C")
+        if spins.ndim > 1:
+            spins = spins[:, 0]
+        indices = ls.batched_index(basis, spins)
+        a = log_amplitudes[indices]
+        b = phases[indices]
+        return a + 1j * b
+
+    return log_coeff_fn
+
+
+def add_noise_to_amplitudes(ground_state, eps: float):  # common.py:826-838
+    ground_state = np.asarray(ground_state, dtype=np.float64, order="C")
+    assert ground_state.ndim == 1
+    log_amplitudes = np.log(np.abs(ground_state))
+    signs = np.sign(ground_state)
+    noise = eps * 2 * (np.random.rand(log_amplitudes.size) - 0.5)
+    noisy_ground_state = signs * np.exp(log_amplitudes + noise)
+    noisy_ground_state /= np.linalg.norm(noisy_ground_state)
+    return noisy_ground_state
+
+
+def amplitude_overlap(cluster, ground_state, noisy_ground_state, basis):  # sampled_connected_components.py:719-723
+    indices = basis.batched_index(cluster)
+    a = np.abs(np.asarray(ground_state)[indices])
+    b = np.abs(np.asarray(noisy_ground_state)[indices])
+    return np.dot(a, b) / np.linalg.norm(a) / np.linalg.norm(b)

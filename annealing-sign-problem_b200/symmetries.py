@@ -128,12 +128,33 @@ class SpinBasis:
     def number_states(self) -> int:
         return int(self.states.shape[0])
 
+    def states_device(self) -> torch.Tensor:
+        """The sorted basis on the device (kept: batched_index is called once per cluster)."""
+        if getattr(self, "_states_dev", None) is None or self._states_dev_of is not self._states:
+            dev = require_cuda()
+            self._states_dev = torch.from_numpy(self.states.view(np.int64)).to(dev)
+            self._states_dev_of = self._states
+        return self._states_dev
+
+    def batched_index_device(self, spins: torch.Tensor) -> torch.Tensor:
+        """Positions of ``spins`` (int64 bit patterns, CUDA) in the basis; raises when one is absent
+        (lattice_symmetries raises too; the reference's callers rely on it: common.py:283, :817)."""
+        from ._lib import check, ffi, lib, ptr, stream
+
+        states = self.states_device()
+        spins = spins.contiguous()
+        out = torch.empty(spins.shape[0], dtype=torch.int64, device=states.device)
+        missing = ffi.new("uint64_t *")
+        check(lib().asp_batched_index(states.shape[0], ptr(states, "uint64_t *"), spins.shape[0], ptr(spins, "uint64_t *"),
+                                      ptr(out, "int64_t *"), missing, stream()))
+        if int(missing[0]) != 0:
+            raise ValueError("%d state(s) not in the basis" % int(missing[0]))
+        return out
+
     def batched_index(self, spins) -> np.ndarray:
-        spins = np.asarray(spins, dtype=np.uint64)
-        idx = np.searchsorted(self.states, spins)
-        if np.any(idx >= self.number_states) or np.any(self.states[np.minimum(idx, self.number_states - 1)] != spins):
-            raise ValueError("state not in the basis")
-        return idx
+        spins = np.ascontiguousarray(np.asarray(spins, dtype=np.uint64).reshape(-1))
+        dev = require_cuda()
+        return self.batched_index_device(torch.from_numpy(spins.view(np.int64)).to(dev)).cpu().numpy()
 
     def index(self, spin: int) -> int:
         return int(self.batched_index(np.array([spin], dtype=np.uint64))[0])
@@ -234,3 +255,8 @@ class Operator:
     def apply(self, spin: int):
         s, c, _ = self.batched_apply(np.array([spin], dtype=np.uint64))
         return s, c
+
+
+def batched_index(basis: SpinBasis, spins) -> np.ndarray:
+    """``ls.batched_index(basis, spins)`` as the reference calls it (common.py:817)."""
+    return basis.batched_index(spins)

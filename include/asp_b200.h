@@ -294,6 +294,23 @@ int asp_extract_csr_indexed(asp_operator const *op, uint64_t n_total, uint64_t c
                             int64_t *d_indptr, int32_t *d_indices, double *d_data, uint64_t *h_nnz,
                             void *stream);
 
+/* ------------------------------------------------------------------------------------
+ * 8. Sampling front-end: the data-parallel pieces that feed n and psi
+ *    into the extraction.
+ *    asp_batched_index: basis.batched_index / ls.batched_index as called at common.py:283,
+ *    :817 and sampled_connected_components.py:720,:730 -- d_index[j] = position of
+ *    d_needles[j] in the ascending (unsigned) unique array d_sorted[n], -1 when absent;
+ *    h_missing (may be NULL; non-NULL synchronises) = number of absent needles.
+ *    asp_sample_indices: monte_carlo_sampling (common.py:269-278), i.e. legacy
+ *    np.random.choice(n, m, replace=True, p = |psi|^power / sum): cdf = cumsum(|psi|^power),
+ *    cdf /= cdf[-1], d_index[j] = searchsorted(cdf, d_uniform[j], side="right") for the
+ *    caller's uniform draws in [0, 1).  d_cdf: optional [n] buffer that receives the cdf.
+ * ---------------------------------------------------------------------------------- */
+int asp_batched_index(uint64_t n, uint64_t const *d_sorted, uint64_t m, uint64_t const *d_needles,
+                      int64_t *d_index, uint64_t *h_missing, void *stream);
+int asp_sample_indices(uint64_t n, double const *d_psi, double power, uint64_t m,
+                       double const *d_uniform, int64_t *d_index, double *d_cdf, void *stream);
+
 /* Number of kernel launches the library has issued in this process (bench accounting). */
 uint64_t asp_kernel_launch_count(void);
 

@@ -167,3 +167,36 @@ def default_betas(indptr, indices, data, field, number_sweeps: int, beta0=None, 
         t = np.arange(ladder, dtype=np.float64) / (ladder - 1)
         betas = np.concatenate([b0 * (b1 / b0) ** t, np.full(quench, np.inf)])
     return np.ascontiguousarray(betas, dtype=np.float64)
+
+
+# ---------------------------------------------------------------------------------------
+# Sampling front-end, pinned by tests/golden/n3_*.npz (the reference's own
+# functions run in the build container, tests/golden/make_golden.py:sampling_case)
+# ---------------------------------------------------------------------------------------
+def sample_indices(ground_state, uniform, sampled_power: float = 2) -> np.ndarray:
+    """monte_carlo_sampling, annealing_sign_problem/common.py:274-277, with the uniform numbers made
+    explicit: legacy ``np.random.choice(n, m, replace=True, p)`` is ``cdf = p.cumsum(); cdf /=
+    cdf[-1]; cdf.searchsorted(random_sample(m), side="right")``."""
+    p = np.abs(np.asarray(ground_state, dtype=np.float64)) ** sampled_power
+    p /= np.sum(p)
+    cdf = p.cumsum()
+    cdf /= cdf[-1]
+    return cdf.searchsorted(np.asarray(uniform, dtype=np.float64), side="right")
+
+
+def batched_index(states, spins) -> np.ndarray:
+    """``basis.batched_index`` on a sorted basis (call sites common.py:283, :817): position of every
+    state, ValueError when one is absent."""
+    states = np.asarray(states, dtype=np.uint64)
+    spins = np.asarray(spins, dtype=np.uint64)
+    idx = np.searchsorted(states, spins)
+    if np.any(idx >= states.shape[0]) or np.any(states[np.minimum(idx, states.shape[0] - 1)] != spins):
+        raise ValueError("state not in the basis")
+    return idx
+
+
+def log_coeff(ground_state, states, spins) -> np.ndarray:
+    """ground_state_to_log_coeff_fn, common.py:806-823."""
+    ground_state = np.asarray(ground_state, dtype=np.float64)
+    idx = batched_index(states, spins)
+    return np.log(np.abs(ground_state))[idx] + 1j * np.where(ground_state >= 0, 0, np.pi)[idx]

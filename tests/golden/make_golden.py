@@ -171,6 +171,53 @@ def extension_case(ref_common, name, n_target, seed, reltol, out):
         os.path.basename(out), os.path.getsize(out)))
 
 
+def sampling_case(ref_common, name, seed, out):
+    """Row N3 of the scope table, produced by the reference's own functions: monte_carlo_sampling
+    (common.py:268-278), ground_state_to_log_coeff_fn (:806-823), determine_exact_solution (:282-285),
+    add_noise_to_amplitudes (:826-838), create_small_cluster_around_point (:481-513).  The stubs stand
+    in for lattice_symmetries only: ``ls.batched_index`` = numpy searchsorted on the sorted basis;
+    ``hamiltonian.apply(s)`` = the oracle operator's neighbours of s in ASCENDING key order (the
+    library's own order is unpinned; ascending is what this repo's operator emits)."""
+    rng = np.random.default_rng(seed)
+    op = OperatorNP.load(system_path(name))
+    states = op.basis.states
+    n = states.shape[0]
+    z = rng.standard_normal(n)
+    psi = np.where(rng.random(n) < 0.5, -1.0, 1.0) * np.exp(2.0 * z)
+    psi /= np.linalg.norm(psi)
+
+    class Basis:
+        number_spins = op.basis.number_spins
+
+        def batched_index(self, spins):
+            return np.searchsorted(states, np.asarray(spins, dtype=np.uint64))
+
+    class Hamiltonian:
+        basis = Basis()
+
+        def apply(self, s):
+            xs, cs, _ = op.apply_u64(np.array([s], dtype=np.uint64))
+            order = np.argsort(xs, kind="stable")
+            return xs[order], cs[order]
+
+    sys.modules["lattice_symmetries"].batched_index = lambda basis, spins: basis.batched_index(spins)
+    np.random.seed(seed)
+    mc2 = ref_common.monte_carlo_sampling(states, psi, 3000, 2).spins
+    mc1 = ref_common.monte_carlo_sampling(states, psi, 1000, 1).spins
+    fn = ref_common.ground_state_to_log_coeff_fn(psi, Basis())
+    log_coeff = fn(mc2[:500])
+    exact_bits = ref_common.determine_exact_solution(mc2, Hamiltonian(), psi)
+    np.random.seed(seed + 1)
+    noisy = ref_common.add_noise_to_amplitudes(psi, 0.3)
+    np.random.seed(seed + 2)
+    clusters = [np.asarray(ref_common.create_small_cluster_around_point(int(s0), Hamiltonian(), required_size=size, keep_probability=0.5),
+                           dtype=np.uint64) for s0, size in zip(mc2[:3], [20, 77, 300])]
+    np.savez_compressed(out, system=name, seed=seed, psi=psi, mc2=mc2, mc1=mc1, log_coeff=log_coeff, exact_bits=exact_bits,
+                        noisy_stride=noisy[::37], cluster0=clusters[0], cluster1=clusters[1], cluster2=clusters[2])
+    print("%-28s n=%d samples=%d/%d clusters=%s -> %s (%d bytes)" % (
+        name, n, mc2.shape[0], mc1.shape[0], [c.shape[0] for c in clusters], os.path.basename(out), os.path.getsize(out)))
+
+
 def known_answers(out):
     """Full-basis known-answer table, recomputed by the oracle's ED."""
     table = {}
@@ -201,3 +248,4 @@ def main():
 
 if __name__ == "__main__":
     main()
+    sampling_case(ref_common, "heisenberg_kagome_16", 6, os.path.join(HERE, "n3_heisenberg_kagome_16.npz"))

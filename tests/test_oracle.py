@@ -307,3 +307,23 @@ def test_greedy_port_matches_plain_python_and_is_a_local_minimum(oracle_capi):
     spin, _ = oracle_capi.greedy(j.indptr, j.indices, j.data, None)
     s = spin.astype(np.float64)
     assert abs(s @ (j @ s) + 2.0 * np.abs(w).sum()) < 1e-12 and spin[0] == 1
+
+
+def test_sampling_front_end_restatement_is_the_reference(golden_dir):
+    """N3: oracle restatements of monte_carlo_sampling / ground_state_to_log_coeff_fn /
+    determine_exact_solution against outputs of the reference's own functions."""
+    from oracle.operator_np import OperatorNP, system_path
+
+    g = np.load(os.path.join(golden_dir, "n3_heisenberg_kagome_16.npz"))
+    states = OperatorNP.load(system_path(str(g["system"]))).basis.states
+    psi = g["psi"]
+    np.random.seed(int(g["seed"]))
+    u2 = np.random.random_sample(g["mc2"].shape[0])
+    u1 = np.random.random_sample(g["mc1"].shape[0])
+    assert np.array_equal(states[live_path.sample_indices(psi, u2, 2)], g["mc2"])
+    assert np.array_equal(states[live_path.sample_indices(psi, u1, 1)], g["mc1"])
+    assert np.array_equal(live_path.log_coeff(psi, states, g["mc2"][:500]), g["log_coeff"])
+    idx = live_path.batched_index(states, g["mc2"])
+    assert np.array_equal(live_path.signs_to_bits(np.sign(psi[idx])), g["exact_bits"])
+    with pytest.raises(ValueError):
+        live_path.batched_index(states, np.array([states[3], states[-1] + np.uint64(1)], dtype=np.uint64))
