@@ -92,3 +92,56 @@ def test_batched_index_and_sampling_at_scale():
     draws = common.sample_indices_device(spike, u[:10000], 2).cpu().numpy()
     assert set(np.unique(draws)) == {17, 400}
     assert abs(np.mean(draws == 400) - 16 / 25) < 0.02
+
+
+def test_cluster_experiment_pipeline_end_to_end(tmp_path):
+    """sampled_connected_components.py:646-750 on kagome_16 with its exact ground state: sampling ->
+    clusters -> extraction -> extension + sparsification -> greedy / SA -> accuracy, overlap, CSV; and
+    the model dump (common.py:750-768) with its int32 index arrays."""
+    from annealing_sign_problem_b200 import experiments, formats
+    from oracle.operator_np import OperatorNP, ground_state, system_path
+
+    e0, psi, _ = ground_state(OperatorNP.load(system_path("heisenberg_kagome_16")))
+    op = asp.load_hamiltonian(asp.ls.system_path("heisenberg_kagome_16"))
+    path = str(tmp_path / "heisenberg_kagome_16.npz")
+    formats.save_ground_state(path, psi, e0, op.basis.states)
+    ground, energy, reps = formats.load_ground_state(path)
+    op.basis.build(reps)  # common.py:801
+    assert energy == e0
+
+    class Args:
+        seed, order, noise, global_cutoff, sampled_power = 11, 1, 0.0, 2e-2, 2
+        number_samples, min_cluster_size, max_cluster_size, keep_probability = 3, 30, 60, 0.5
+        annealing, number_sweeps, repetitions = True, 300, 16
+
+    np.random.seed(Args.seed)
+    fn = asp.ground_state_to_log_coeff_fn(ground, op.basis)
+    clusters = experiments.generate_clusters(op, ground, Args)
+    assert len(clusters) == 3 and all(30 <= c.shape[0] <= 60 or c.shape[0] < 30 for c in clusters)
+    out = str(tmp_path / "result.csv")
+    experiments.write_csv_header(out, Args)
+    for cluster in clusters:
+        columns = experiments.process_cluster(cluster, op, ground, ground, fn, Args, number_sweeps=Args.number_sweeps,
+                                              repetitions=Args.repetitions)
+        experiments.append_csv_row(out, columns)
+        assert len(columns) == 2 and columns[0].size == cluster.shape[0] and columns[1].size >= columns[0].size
+        for r in columns:
+            print(r.to_csv_str())
+            assert 0.5 <= r.greedy_accuracy <= 1 and 0.5 <= r.sa_accuracy <= 1
+            assert 0 <= r.greedy_overlap <= 1 + 1e-12 and 0 <= r.sa_overlap <= 1 + 1e-12
+            assert abs(r.amplitude_overlap - 1) < 1e-12  # no noise
+        # the extension sees every neighbour of the cluster: SA recovers (almost) all its signs
+        assert columns[1].sa_accuracy >= columns[0].sa_accuracy - 0.1
+        assert min(r.sa_overlap for r in columns) > 0.99 and min(r.greedy_overlap for r in columns) > 0.99
+    assert len(open(out).read().splitlines()) == 12 + 3
+    # model dump of the full-basis model: int32 CSR, energy of the exact signs = E0
+    model = asp.make_ising_model(op.basis.states, op, log_psi_fn=fn)
+    dump = str(tmp_path / "model.npz")
+    formats.dump_ising_model_to_hdf5(model, ground, dump)
+    d = np.load(dump)
+    assert d["indices"].dtype == np.int32 and d["indptr"].dtype == np.int32 and d["signs"].dtype == np.uint64
+    # 177 606 candidates (SURVEY.md appendix B) minus the diagonal entries that are exactly zero (12 parallel +
+    # 12 antiparallel bonds), which scipy's 0.5 (M + M^T) drops in the reference too (common.py:194)
+    assert d["indptr"][-1] == d["elements"].shape[0] == d["indices"].shape[0] and 170_000 < d["elements"].shape[0] <= 177_606
+    assert np.count_nonzero(d["elements"]) == d["elements"].shape[0]
+    assert abs(float(d["energy"]) - e0) < 1e-10 and not d["field"].any()
