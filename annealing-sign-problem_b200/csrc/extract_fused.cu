@@ -231,6 +231,7 @@ struct GatherArgs {
   const double *shard_psi[kGxMaxRanks];
   uint64_t begin[kGxMaxRanks + 1];       // global index of the first key of every block
   uint64_t unit_begin[kGxMaxRanks + 1];  // first key pair of the k-th VISITED block
+  uint64_t chunk_begin[kGxMaxRanks + 1]; // first 1024-key chunk of the k-th visited block (TMA variant)
   int order[kGxMaxRanks];                // k-th visited block
   int world;
   const unsigned long long *ready;  // local flags [world] (NULL: no waiting)
@@ -284,6 +285,31 @@ __device__ __forceinline__ void index_table(const GatherArgs &a, uint64_t i, uin
   for (uint64_t k = prev; k <= b && k <= last; ++k) a.starts[k] = static_cast<uint32_t>(i);
   if (i == a.n - 1)
     for (uint64_t k = b + 1; k <= last; ++k) a.starts[k] = a.n;
+}
+
+// Private copy + index of one or two consecutive keys (global positions g, g + 1).
+__device__ __forceinline__ void emit_pair(const GatherArgs &a, uint64_t g, uint32_t cnt, ulonglong2 keys, ulonglong2 amps, bool has_prev,
+                                          uint64_t pk) {
+  a.spins[g] = keys.x;
+  reinterpret_cast<unsigned long long *>(a.psi)[g] = amps.x;
+  index_table(a, g, keys.x, has_prev, pk);
+  const bool in0 = (keys.x & ~a.state_mask) == 0;
+  const uint64_t w0 = keys.x >> a.fshift;
+  unsigned long long bits0 = filter_bits(filter_hash(keys.x));
+  if (cnt == 2) {
+    a.spins[g + 1] = keys.y;
+    reinterpret_cast<unsigned long long *>(a.psi)[g + 1] = amps.y;
+    index_table(a, g + 1, keys.y, true, keys.x);
+    if ((keys.y & ~a.state_mask) == 0) {
+      const uint64_t w1 = keys.y >> a.fshift;
+      const unsigned long long bits1 = filter_bits(filter_hash(keys.y));
+      if (in0 && w1 == w0)
+        bits0 |= bits1;  // sorted keys: neighbours often share a filter word -> one atomic for both
+      else
+        atomicOr(reinterpret_cast<unsigned long long *>(a.filter + w1), bits1);
+    }
+  }
+  if (in0) atomicOr(reinterpret_cast<unsigned long long *>(a.filter + w0), bits0);
 }
 
 __global__ void __launch_bounds__(kGxThreads) gather_index_kernel(const GatherArgs a) {
@@ -351,28 +377,193 @@ __global__ void __launch_bounds__(kGxThreads) gather_index_kernel(const GatherAr
     } else if (lane == 0) {
       pk = ld_peer_u64(a.shard_spins[blk[j]] + loc[j] - 1);
     }
-    a.spins[g[j]] = keys[j].x;
-    reinterpret_cast<unsigned long long *>(a.psi)[g[j]] = amps[j].x;
-    index_table(a, g[j], keys[j].x, has_prev, pk);
-    const bool in0 = (keys[j].x & ~a.state_mask) == 0;
-    const uint64_t w0 = keys[j].x >> a.fshift;
-    unsigned long long bits0 = filter_bits(filter_hash(keys[j].x));
-    if (cnt[j] == 2) {
-      a.spins[g[j] + 1] = keys[j].y;
-      reinterpret_cast<unsigned long long *>(a.psi)[g[j] + 1] = amps[j].y;
-      index_table(a, g[j] + 1, keys[j].y, true, keys[j].x);
-      if ((keys[j].y & ~a.state_mask) == 0) {
-        const uint64_t w1 = keys[j].y >> a.fshift;
-        const unsigned long long bits1 = filter_bits(filter_hash(keys[j].y));
-        if (in0 && w1 == w0)
-          bits0 |= bits1;  // sorted keys: neighbours often share a filter word -> one atomic for both
-        else
-          atomicOr(reinterpret_cast<unsigned long long *>(a.filter + w1), bits1);
-      }
-    }
-    if (in0) atomicOr(reinterpret_cast<unsigned long long *>(a.filter + w0), bits0);
+    emit_pair(a, g[j], cnt[j], keys[j], amps[j], has_prev, pk);
   }
 }
+
+// ---- X1, TMA variant of the fused kernel: a persistent CTA keeps kTxStages bulk copies
+// (cp.async.bulk global -> shared, completion on an mbarrier) of 1024 keys + 1024 amplitudes in flight --
+// 128 KB per SM without a single register -- while its threads index the chunk that has landed and write
+// the private copy.  One elected thread waits for the block's ready flag and issues the copies.
+constexpr int kTxChunk = 1024;
+constexpr int kTxStages = 4;
+constexpr int kTxThreads = 256;
+constexpr int kTxCtasPerSM = 2;
+constexpr size_t kTxSmem = static_cast<size_t>(kTxStages) * kTxChunk * 16 + 64;
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+               "r"(bar)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kTxThreads, kTxCtasPerSM) gather_index_tma_kernel(const GatherArgs a) {
+  extern __shared__ __align__(128) unsigned char tx_smem[];
+  const uint32_t smem0 = smem_addr(tx_smem);
+  const uint32_t bars = smem0 + kTxStages * kTxChunk * 16;  // kTxStages mbarriers behind the stages
+  const uint64_t total = a.chunk_begin[a.world];
+  if (threadIdx.x == 0) {
+    for (int st = 0; st < kTxStages; ++st) mbar_init(bars + 8 * st, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t waited = 0;  // blocks whose ready flag this CTA's issuing thread has seen
+  auto locate = [&](uint64_t c, int &q, uint64_t &l0, uint32_t &cnt) {
+    int k = 0;
+    while (c >= a.chunk_begin[k + 1]) ++k;
+    q = a.order[k];
+    l0 = (c - a.chunk_begin[k]) * kTxChunk;
+    const uint64_t len = a.begin[q + 1] - a.begin[q];
+    cnt = static_cast<uint32_t>(min(static_cast<uint64_t>(kTxChunk), len - l0));
+  };
+  auto issue = [&](uint64_t it) {  // thread 0
+    const uint64_t c = blockIdx.x + it * gridDim.x;
+    if (c >= total) return;
+    int q;
+    uint64_t l0;
+    uint32_t cnt;
+    locate(c, q, l0, cnt);
+    if (a.ready != nullptr && !((waited >> q) & 1u)) {
+      wait_flag_or_trap(a.ready + q, a.epoch);
+      asm volatile("fence.proxy.async;" ::: "memory");  // the async proxy reads what the acquire made visible
+      waited |= 1u << q;
+    }
+    const uint32_t st = static_cast<uint32_t>(it % kTxStages);
+    const uint32_t even = cnt & ~1u;  // whole 16-byte units; an odd last key is read with a plain load
+    mbar_arrive_expect_tx(bars + 8 * st, even * 16u);
+    if (even) {
+      bulk_g2s(smem0 + st * (kTxChunk * 16), a.shard_spins[q] + l0, even * 8u, bars + 8 * st);
+      bulk_g2s(smem0 + st * (kTxChunk * 16) + kTxChunk * 8, a.shard_psi[q] + l0, even * 8u, bars + 8 * st);
+    }
+  };
+  if (threadIdx.x == 0)
+    for (int it = 0; it < kTxStages; ++it) issue(it);
+  for (uint64_t it = 0;; ++it) {
+    const uint64_t c = blockIdx.x + it * gridDim.x;
+    if (c >= total) break;
+    const uint32_t st = static_cast<uint32_t>(it % kTxStages);
+    int q;
+    uint64_t l0;
+    uint32_t cnt;
+    locate(c, q, l0, cnt);
+    mbar_wait(bars + 8 * st, static_cast<uint32_t>(it / kTxStages) & 1u);
+    const unsigned long long *s_keys = reinterpret_cast<const unsigned long long *>(tx_smem + st * (kTxChunk * 16));
+    const unsigned long long *s_amps = s_keys + kTxChunk;
+#pragma unroll
+    for (int h = 0; h < kTxChunk / 2 / kTxThreads; ++h) {
+      const uint32_t e = 2u * (h * kTxThreads + threadIdx.x);  // first entry of this thread's pair inside the chunk
+      if (e >= cnt) continue;
+      const bool two = e + 1 < cnt;
+      ulonglong2 keys, amps;
+      if (two) {
+        keys = *reinterpret_cast<const ulonglong2 *>(s_keys + e);
+        amps = *reinterpret_cast<const ulonglong2 *>(s_amps + e);
+      } else {  // odd tail of the block: not part of the bulk copy
+        keys = make_ulonglong2(ld_peer_u64(a.shard_spins[q] + l0 + e), 0ull);
+        amps = make_ulonglong2(ld_peer_u64(a.shard_psi[q] + l0 + e), 0ull);
+      }
+      const uint64_t g = a.begin[q] + l0 + e;
+      bool has_prev = true;
+      uint64_t pk;
+      if (e > 0) {
+        pk = s_keys[e - 1];
+      } else if (l0 > 0) {
+        pk = ld_peer_u64(a.shard_spins[q] + l0 - 1);
+      } else {
+        has_prev = g > 0;
+        pk = 0;
+        if (has_prev) {
+          int p = q - 1;
+          while (a.begin[p + 1] == a.begin[p]) --p;
+          if (a.ready != nullptr) wait_flag_or_trap(a.ready + p, a.epoch);
+          pk = ld_peer_u64(a.shard_spins[p] + (a.begin[p + 1] - a.begin[p] - 1));
+        }
+      }
+      emit_pair(a, g, two ? 2u : 1u, keys, amps, has_prev, pk);
+    }
+    __syncthreads();  // every thread is done with this stage: refill it
+    if (threadIdx.x == 0) issue(it + kTxStages);
+  }
+}
+
+// ---- X1, copy-engine variant: the blocks are pulled by cudaMemcpyAsync (the copy engines move 700 GB/s over
+// NVLink, more than SM loads reach) and indexed block by block on the SMs while later blocks still travel.
+// A thread indexes two consecutive keys of the block [b0, b1); the block's first key owes its table entries
+// to a key of ANOTHER block (which may not have arrived): the seam kernel adds them at the end.
+__global__ void __launch_bounds__(256) index_block_kernel(const uint64_t *__restrict__ spins, uint32_t n, uint32_t b0, uint32_t b1,
+                                                          uint64_t state_mask, int tshift, uint64_t num_buckets,
+                                                          uint32_t *__restrict__ starts, int fshift, uint2 *__restrict__ filter) {
+  const uint32_t i = b0 + 2u * (blockIdx.x * 256u + threadIdx.x);
+  if (i >= b1) return;
+  const uint64_t last = num_buckets;
+  const bool two = i + 1 < b1;
+  const uint64_t k0 = spins[i], k1 = two ? spins[i + 1] : 0ull;
+  const uint64_t bk0 = (k0 & ~state_mask) ? last : k0 >> tshift;
+  if (i > b0 || i == 0) {
+    uint64_t prev = 0;
+    if (i > 0) {
+      const uint64_t pk = spins[i - 1];
+      prev = ((pk & ~state_mask) ? last : pk >> tshift) + 1;
+    }
+    for (uint64_t k = prev; k <= bk0 && k <= last; ++k) starts[k] = i;
+  }
+  uint64_t b_last = bk0;
+  if (two) {
+    const uint64_t bk1 = (k1 & ~state_mask) ? last : k1 >> tshift;
+    for (uint64_t k = bk0 + 1; k <= bk1 && k <= last; ++k) starts[k] = i + 1;
+    b_last = bk1;
+  }
+  if ((two ? i + 1 : i) == n - 1)
+    for (uint64_t k = b_last + 1; k <= last; ++k) starts[k] = n;
+  const bool in0 = (k0 & ~state_mask) == 0, in1 = two && (k1 & ~state_mask) == 0;
+  unsigned long long bits0 = filter_bits(filter_hash(k0));
+  const uint64_t w0 = k0 >> fshift;
+  if (in1) {
+    const uint64_t w1 = k1 >> fshift;
+    const unsigned long long bits1 = filter_bits(filter_hash(k1));
+    if (in0 && w1 == w0)
+      bits0 |= bits1;
+    else
+      atomicOr(reinterpret_cast<unsigned long long *>(filter + w1), bits1);
+  }
+  if (in0) atomicOr(reinterpret_cast<unsigned long long *>(filter + w0), bits0);
+}
+
+struct SeamArgs {
+  uint32_t first[kGxMaxRanks];  // first key of every non-empty block but the one that starts at 0 (n: none)
+};
+__global__ void index_seam_kernel(const uint64_t *__restrict__ spins, uint32_t n, const SeamArgs seams, int world, uint64_t state_mask,
+                                  int tshift, uint64_t num_buckets, uint32_t *__restrict__ starts) {
+  const int q = threadIdx.x;
+  if (q >= world) return;
+  const uint32_t i = seams.first[q];
+  if (i == 0 || i >= n) return;
+  const uint64_t last = num_buckets;
+  const uint64_t key = spins[i], pk = spins[i - 1];
+  const uint64_t b = (key & ~state_mask) ? last : key >> tshift;
+  for (uint64_t k = ((pk & ~state_mask) ? last : pk >> tshift) + 1; k <= b && k <= last; ++k) starts[k] = i;
+}
+
+__global__ void wait_one_flag_kernel(const unsigned long long *flag, unsigned long long value) { wait_flag_or_trap(flag, value); }
 
 // Position of c (< 2^number_spins) in the sorted basis, or -1.
 __device__ __forceinline__ int32_t search_one(const FusedArgs &a, uint64_t c) {
@@ -840,6 +1031,7 @@ static int g_surv_entries_override = 0;
 static bool g_time_kernel = false;
 static cudaEvent_t g_ev_begin = nullptr, g_ev_end = nullptr;
 static int g_filter_bits_delta = 0, g_table_bits_delta = 0, g_stage_a_mode = 0;
+static int g_gather_mode = 2;  // asp_gather_index: 2 = one TMA kernel (default), 1 = one kernel with plain loads, 0 = copy engines + per-block index kernels
 
 static FusedWorkspace carve_fused(void *base, const asp_operator *op, uint64_t n_total, uint64_t num_rows) {
   FusedWorkspace w;
@@ -914,7 +1106,7 @@ int fused_prepare(const asp_operator *op, uint64_t n_total, const uint64_t *d_sp
 int fused_prepare_gather(const asp_operator *op, uint32_t world, uint32_t rank, const uint64_t *shard_begin,
                          const uint64_t *const *d_shard_spins, const double *const *d_shard_psi, const uint64_t *d_ready,
                          uint64_t epoch, uint64_t *d_spins, double *d_psi, uint64_t num_rows, void *d_workspace,
-                         size_t workspace_bytes, cudaStream_t s) {
+                         size_t workspace_bytes, cudaStream_t s, bool tma) {
   ASP_REQUIRE(world >= 1 && world <= static_cast<uint32_t>(kGxMaxRanks) && rank < world, "world size must be in 1..16");
   const uint64_t n_total = shard_begin[world];
   ASP_REQUIRE(shard_begin[0] == 0, "shard_begin[0] must be 0");
@@ -934,6 +1126,12 @@ int fused_prepare_gather(const asp_operator *op, uint32_t world, uint32_t rank, 
     units += (shard_begin[q + 1] - shard_begin[q] + 1) / 2;
   }
   a.unit_begin[world] = units;
+  uint64_t chunks = 0;
+  for (uint32_t k = 0; k < world; ++k) {
+    a.chunk_begin[k] = chunks;
+    chunks += (shard_begin[a.order[k] + 1] - shard_begin[a.order[k]] + 1023) / 1024;
+  }
+  a.chunk_begin[world] = chunks;
   for (uint32_t q = 0; q < world; ++q) {
     ASP_REQUIRE(shard_begin[q + 1] == shard_begin[q] || (d_shard_spins[q] && d_shard_psi[q]), "NULL shard pointer");
     ASP_REQUIRE((reinterpret_cast<uintptr_t>(d_shard_spins[q]) & 15u) == 0 && (reinterpret_cast<uintptr_t>(d_shard_psi[q]) & 15u) == 0,
@@ -955,8 +1153,75 @@ int fused_prepare_gather(const asp_operator *op, uint32_t world, uint32_t rank, 
   a.starts = w.starts;
   a.filter = w.filter;
   ASP_CUDA_CHECK(cudaMemsetAsync(static_cast<char *>(d_workspace) + w.zero_offset, 0, w.zero_bytes, s));
-  const uint64_t per_cta = static_cast<uint64_t>(kGxThreads) * kGxUnroll;
-  gather_index_kernel<<<static_cast<unsigned>((units + per_cta - 1) / per_cta), kGxThreads, 0, s>>>(a);
+  if (tma) {
+    ASP_CUDA_CHECK(cudaFuncSetAttribute(gather_index_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTxSmem)));
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(chunks, static_cast<uint64_t>(kNumSMs) * kTxCtasPerSM));
+    gather_index_tma_kernel<<<grid, kTxThreads, kTxSmem, s>>>(a);
+  } else {
+    const uint64_t per_cta = static_cast<uint64_t>(kGxThreads) * kGxUnroll;
+    gather_index_kernel<<<static_cast<unsigned>((units + per_cta - 1) / per_cta), kGxThreads, 0, s>>>(a);
+  }
+  ASP_LAUNCH_CHECK();
+  return ASP_OK;
+}
+
+// X1 with the copy engines: per block (own block first, then ring order) [wait for its ready flag ->
+// cudaMemcpyAsync keys + amplitudes into the private full copy] on a copy stream; on the caller's stream
+// the block is indexed as soon as its copies are done, while the next blocks travel.
+struct CopyLane {
+  cudaStream_t copy = nullptr;
+  cudaEvent_t start = nullptr, block[kGxMaxRanks] = {};
+  int device = -1;
+};
+static CopyLane g_lane;
+
+int fused_prepare_gather_ce(const asp_operator *op, uint32_t world, uint32_t rank, const uint64_t *shard_begin,
+                            const uint64_t *const *d_shard_spins, const double *const *d_shard_psi, const uint64_t *d_ready,
+                            uint64_t epoch, uint64_t *d_spins, double *d_psi, uint64_t num_rows, void *d_workspace,
+                            size_t workspace_bytes, cudaStream_t s) {
+  ASP_REQUIRE(world >= 1 && world <= static_cast<uint32_t>(kGxMaxRanks) && rank < world, "world size must be in 1..16");
+  const uint64_t n_total = shard_begin[world];
+  ASP_REQUIRE(shard_begin[0] == 0, "shard_begin[0] must be 0");
+  FusedWorkspace w = carve_fused(d_workspace, op, n_total, num_rows);
+  if (d_workspace == nullptr || workspace_bytes < w.bytes) {
+    set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+    return ASP_ERR_WORKSPACE;
+  }
+  int dev = 0;
+  ASP_CUDA_CHECK(cudaGetDevice(&dev));
+  if (g_lane.device != dev) {
+    ASP_REQUIRE(g_lane.device < 0, "one device per process");
+    ASP_CUDA_CHECK(cudaStreamCreateWithFlags(&g_lane.copy, cudaStreamNonBlocking));
+    ASP_CUDA_CHECK(cudaEventCreateWithFlags(&g_lane.start, cudaEventDisableTiming));
+    for (auto &e : g_lane.block) ASP_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    g_lane.device = dev;
+  }
+  ASP_CUDA_CHECK(cudaMemsetAsync(static_cast<char *>(d_workspace) + w.zero_offset, 0, w.zero_bytes, s));
+  ASP_CUDA_CHECK(cudaEventRecord(g_lane.start, s));  // the copies may overwrite the full copy only after the caller's earlier work
+  ASP_CUDA_CHECK(cudaStreamWaitEvent(g_lane.copy, g_lane.start, 0));
+  SeamArgs seams{};
+  for (uint32_t k = 0; k < world; ++k) {
+    const uint32_t q = (rank + k) % world;  // own block first (no flag to wait for), then ring order
+    ASP_REQUIRE(shard_begin[q + 1] >= shard_begin[q], "shard_begin must be non-decreasing");
+    const uint64_t b0 = shard_begin[q], len = shard_begin[q + 1] - b0;
+    seams.first[q] = len > 0 ? static_cast<uint32_t>(b0) : static_cast<uint32_t>(n_total);
+    if (len == 0) continue;
+    ASP_REQUIRE(d_shard_spins[q] && d_shard_psi[q], "NULL shard pointer");
+    if (d_ready != nullptr && q != rank) {
+      wait_one_flag_kernel<<<1, 1, 0, g_lane.copy>>>(reinterpret_cast<const unsigned long long *>(d_ready) + q, epoch);
+      ASP_LAUNCH_CHECK();
+    }
+    ASP_CUDA_CHECK(cudaMemcpyAsync(d_spins + b0, d_shard_spins[q], len * sizeof(uint64_t), cudaMemcpyDeviceToDevice, g_lane.copy));
+    ASP_CUDA_CHECK(cudaMemcpyAsync(d_psi + b0, d_shard_psi[q], len * sizeof(double), cudaMemcpyDeviceToDevice, g_lane.copy));
+    ASP_CUDA_CHECK(cudaEventRecord(g_lane.block[k], g_lane.copy));
+    ASP_CUDA_CHECK(cudaStreamWaitEvent(s, g_lane.block[k], 0));
+    index_block_kernel<<<static_cast<unsigned>((len + 511) / 512), 256, 0, s>>>(d_spins, static_cast<uint32_t>(n_total), static_cast<uint32_t>(b0),
+                                                                               static_cast<uint32_t>(b0 + len), op->state_mask, w.tshift,
+                                                                               w.num_buckets, w.starts, w.fshift, w.filter);
+    ASP_LAUNCH_CHECK();
+  }
+  index_seam_kernel<<<1, 32, 0, s>>>(d_spins, static_cast<uint32_t>(n_total), seams, static_cast<int>(world), op->state_mask, w.tshift,
+                                     w.num_buckets, w.starts);
   ASP_LAUNCH_CHECK();
   return ASP_OK;
 }
@@ -1128,9 +1393,14 @@ int asp_gather_index(asp_operator const *op, uint32_t world, uint32_t rank, uint
   ASP_REQUIRE(world >= 1 && world <= 16, "world size must be in 1..16");
   ASP_REQUIRE(shard_begin[world] > 0 && shard_begin[world] < (1ull << 31), "the gathered basis needs 0 < n_total < 2^31");
   ASP_REQUIRE(d_spins && d_psi, "NULL output buffer");
-  return fused_prepare_gather(op, world, rank, shard_begin, d_shard_spins, d_shard_psi, d_ready, epoch, d_spins, d_psi, num_rows,
-                              d_workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+  if (g_gather_mode != 0)
+    return fused_prepare_gather(op, world, rank, shard_begin, d_shard_spins, d_shard_psi, d_ready, epoch, d_spins, d_psi, num_rows,
+                                d_workspace, workspace_bytes, static_cast<cudaStream_t>(stream), g_gather_mode == 2);
+  return fused_prepare_gather_ce(op, world, rank, shard_begin, d_shard_spins, d_shard_psi, d_ready, epoch, d_spins, d_psi, num_rows,
+                                 d_workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
+
+void asp_set_gather_mode(int mode) { g_gather_mode = (mode == 0 || mode == 1) ? mode : 2; }
 
 int asp_extract_csr_indexed(asp_operator const *op, uint64_t n_total, uint64_t const *d_spins, double const *d_psi,
                             uint64_t row_begin, uint64_t num_rows, void *d_workspace, size_t workspace_bytes,

@@ -15,7 +15,7 @@ int fused_prepare(const asp_operator *op, uint64_t n_total, const uint64_t *d_sp
 int fused_prepare_gather(const asp_operator *op, uint32_t world, uint32_t rank, const uint64_t *shard_begin,
                          const uint64_t *const *d_shard_spins, const double *const *d_shard_psi, const uint64_t *d_ready,
                          uint64_t epoch, uint64_t *d_spins, double *d_psi, uint64_t num_rows, void *d_workspace,
-                         size_t workspace_bytes, cudaStream_t s);
+                         size_t workspace_bytes, cudaStream_t s, bool tma);
 int fused_launch(const asp_operator *op, uint64_t n_total, const uint64_t *d_spins, const double *d_psi, uint64_t row_begin,
                  uint64_t num_rows, int chunk, uint64_t chunk_begin, uint64_t chunk_rows, void *d_workspace, uint64_t capacity,
                  int64_t *d_indptr, int32_t *d_indices, double *d_data, unsigned long long *nnz_mirror, cudaStream_t s);

@@ -90,10 +90,17 @@ class PeerBasis:
     """
 
     FLAG_BYTES = 256  # ready[16] u64 at +0, done[16] u64 at +128
+    MODES = {"ce": 0, "sm": 1, "tma": 2}
     DONE_SLOT = 16
 
-    def __init__(self, capacity_rows: int, device=None):
+    def __init__(self, capacity_rows: int, device=None, mode: str = "tma"):
+        """mode (asp_set_gather_mode): "tma" = one persistent kernel, cp.async.bulk pulls chunks into shared
+        memory while the threads index the chunk that landed; "sm" = one kernel, plain 16-byte loads;
+        "ce" = copy engines pull, SMs index block by block behind them."""
         from ._lib import check, ffi, lib, require_cuda
+
+        assert mode in self.MODES
+        self.mode = mode
 
         self.device = device if device is not None else require_cuda()
         self.world = dist.get_world_size() if dist.is_initialized() else 1
@@ -165,6 +172,7 @@ class PeerBasis:
             self._full = (torch.empty(n_total, dtype=torch.int64, device=self.device),
                           torch.empty(n_total, dtype=torch.float64, device=self.device))
         full_spins, full_psi = self._full
+        lib().asp_set_gather_mode(self.MODES[self.mode])
         check(lib().asp_gather_index(operator.handle, self.world, self.rank, ffi.new("uint64_t[]", begins), self._shard_spins,
                                      self._shard_psi, ffi.cast("uint64_t const *", self._own), self.epoch,
                                      ptr(full_spins, "uint64_t *"), ptr(full_psi, "double *"), num_rows,

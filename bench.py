@@ -43,9 +43,9 @@ def parse_args():
     p.add_argument("--replicas", type=int, default=64, help="annealing replicas per GPU")
     p.add_argument("--sweeps", type=int, default=16, help="annealing sweeps per step")
     p.add_argument("--cpu-sample", type=int, default=200_000, help="states of the bounded CPU-baseline sample")
-    p.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
-                   help="X1 at N > 1: 'peer' = row blocks in NVLink peer memory, one kernel pulls + indexes them; "
-                        "'nccl' = two all-gathers + index pass (the baseline)")
+    p.add_argument("--exchange", default="peer", choices=["peer", "peer-sm", "peer-ce", "nccl"],
+                   help="X1 at N > 1: 'peer' = row blocks in NVLink peer memory, pulled by the copy engines and indexed block by "
+                        "block behind them; 'peer-sm' = one SM kernel pulls + indexes; 'nccl' = two all-gathers + index pass (the baseline)")
     p.add_argument("--skip-anneal", action="store_true")
     p.add_argument("--skip-cpu", action="store_true")
     p.add_argument("--skip-e2e", action="store_true")
@@ -259,8 +259,8 @@ def run_ours(args):
 
     bounds = [D.block(n_total, r, world)[0] for r in range(world)] + [n_total]
     peer = None
-    if world > 1 and args.exchange == "peer":
-        peer = D.PeerBasis(max(bounds[r + 1] - bounds[r] for r in range(world)), dev)
+    if world > 1 and args.exchange != "nccl":
+        peer = D.PeerBasis(max(bounds[r + 1] - bounds[r] for r in range(world)), dev, mode={"peer": "tma", "peer-sm": "sm", "peer-ce": "ce"}[args.exchange])
         peer.spins[:num_rows] = my_spins
         peer.psi[:num_rows] = my_psi
 

@@ -286,6 +286,14 @@ int asp_gather_index(asp_operator const *op, uint32_t world, uint32_t rank,
                      double const *const *d_shard_psi, uint64_t const *d_ready, uint64_t epoch,
                      uint64_t *d_spins, double *d_psi, uint64_t num_rows, void *d_workspace,
                      size_t workspace_bytes, void *stream);
+/* asp_gather_index has three implementations of the same contract (measured within 5 % of each
+ * other and of NCCL's all-gather alone, ~510 GB/s pulled per rank on 4 GPUs -- the fabric, not the
+ * kernel, sets the pace): 2 (default) = ONE persistent kernel, cp.async.bulk (TMA) keeps 128 KB per
+ * SM of peer memory in flight into shared memory while the threads index the chunk that landed and
+ * write the private copy; 1 = ONE kernel with plain 16-byte loads; 0 = the copy engines pull the
+ * blocks (cudaMemcpyAsync on an internal stream) and every block is indexed on the SMs as soon as
+ * it has landed. */
+void asp_set_gather_mode(int mode);
 /* asp_extract_csr without its zero + index pass: the workspace was prepared by asp_gather_index
  * for the same (op, n_total, num_rows) on the same stream. */
 int asp_extract_csr_indexed(asp_operator const *op, uint64_t n_total, uint64_t const *d_spins,

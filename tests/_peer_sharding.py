@@ -46,6 +46,7 @@ def main():
         full_p = D.all_gather_blocks(psi[begin:begin + rows].clone(), n)
         assert torch.equal(full_s, spins) and torch.equal(full_p, psi)
         # peer-memory path
+        pb.mode = ["ce", "sm", "tma", "tma"][epoch]  # every implementation of asp_gather_index
         pb.begin_epoch()
         pb.spins[:rows] = spins[begin:begin + rows]
         pb.psi[:rows] = psi[begin:begin + rows]

@@ -226,7 +226,8 @@ def test_gather_index_kernel_over_emulated_shards_equals_the_unsharded_build():
         world = len(bounds) - 1
         parts_s = [spins[bounds[q]:bounds[q + 1]].clone() if bounds[q + 1] > bounds[q] else torch.zeros(2, dtype=torch.int64, device=DEV) for q in range(world)]
         parts_p = [psi[bounds[q]:bounds[q + 1]].clone() if bounds[q + 1] > bounds[q] else torch.zeros(2, dtype=torch.float64, device=DEV) for q in range(world)]
-        for rank in {0, world - 1, world // 2}:
+        for rank, mode in [(0, 0), (0, 2), (world - 1, 1), (world - 1, 2), (world // 2, 0), (world // 2, 1), (world // 2, 2)]:
+            lib().asp_set_gather_mode(mode)  # 0 = copy engines + per-block index kernels, 1 = one SM kernel, 2 = one TMA kernel
             row_begin, num_rows = bounds[rank], bounds[rank + 1] - bounds[rank]
             need = int(lib().asp_extract_csr_workspace_bytes(op.handle, n, num_rows))
             workspace = torch.empty(need, dtype=torch.uint8, device=DEV)
@@ -246,6 +247,7 @@ def test_gather_index_kernel_over_emulated_shards_equals_the_unsharded_build():
             lo, hi = int(ref[0][row_begin]), int(ref[0][row_begin + num_rows])
             assert torch.equal(indptr, ref[0][row_begin:row_begin + num_rows + 1] - lo)
             assert torch.equal(indices, ref[1][lo:hi]) and torch.equal(data, ref[2][lo:hi])
+    lib().asp_set_gather_mode(2)
 
 
 def test_peer_memory_exchange_on_two_gpus():

@@ -39,21 +39,24 @@ def main():
     my_s, my_p = spins[begin:begin + mine].clone(), psi[begin:begin + mine].clone()
     need = int(lib().asp_extract_csr_workspace_bytes(op.handle, n, mine))
     ws = torch.empty(need, dtype=torch.uint8, device=dev)
-    out = {"peer": [], "nccl": [], "nccl_index": []}
+    out = {"peer": [], "peer_sm": [], "peer_tma": [], "nccl": [], "nccl_index": []}
     for it in range(25):
-        dist.barrier()
-        torch.cuda.synchronize()
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        pb.begin_epoch()
-        pb.publish()
-        e[0].record()
-        fs, fp = pb.gather_index(op, bounds, mine, ws)
-        e[1].record()
-        pb.release()
-        torch.cuda.synchronize()
-        out["peer"].append(e[0].elapsed_time(e[1]))
-        if it == 0:
-            assert torch.equal(fs, spins) and torch.equal(fp, psi)
+        for mode, key in (("ce", "peer"), ("sm", "peer_sm"), ("tma", "peer_tma")):
+            pb.mode = mode
+            dist.barrier()
+            torch.cuda.synchronize()
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            pb.begin_epoch()
+            pb.publish()
+            e[0].record()
+            fs, fp = pb.gather_index(op, bounds, mine, ws)
+            e[1].record()
+            pb.release()
+            torch.cuda.synchronize()
+            out[key].append(e[0].elapsed_time(e[1]))
+            if it == 0:
+                assert torch.equal(fs, spins) and torch.equal(fp, psi)
+        lib().asp_set_gather_mode(1)
         dist.barrier()
         torch.cuda.synchronize()
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -78,9 +81,10 @@ def main():
     dist.all_gather_object(every, res)
     if rank == 0:
         for r, x in enumerate(every):
-            print("rank %d: peer gather+index median %.3f ms (min %.3f) = %.0f GB/s pulled | nccl all-gather x2 %.3f ms (min %.3f) "
-                  "+ local copy+index %.3f ms" % (r, x["peer"][0], x["peer"][1], remote_gb / (x["peer"][0] * 1e-3), x["nccl"][0], x["nccl"][1],
-                                                x["nccl_index"][0]))
+            print("rank %d: copy-engine pull + block index median %.3f ms (min %.3f) = %.0f GB/s pulled | SM gather+index kernel %.3f ms "
+                  "(min %.3f) = %.0f GB/s | TMA gather+index kernel %.3f ms (min %.3f) = %.0f GB/s | nccl all-gather x2 %.3f ms (min %.3f) + local copy+index %.3f ms" % (
+                      r, x["peer"][0], x["peer"][1], remote_gb / (x["peer"][0] * 1e-3), x["peer_sm"][0], x["peer_sm"][1],
+                      remote_gb / (x["peer_sm"][0] * 1e-3), x["peer_tma"][0], x["peer_tma"][1], remote_gb / (x["peer_tma"][0] * 1e-3), x["nccl"][0], x["nccl"][1], x["nccl_index"][0]))
     dist.destroy_process_group()
 
 
