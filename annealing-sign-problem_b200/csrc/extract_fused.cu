@@ -191,31 +191,8 @@ __device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(static_cast<unsigned short>(v)));
 }
 
-// Index of the sorted basis: first-position table + Bloom filter, one thread per key.
-__global__ void __launch_bounds__(256) build_index_kernel(const uint64_t *__restrict__ spins, uint32_t n, uint64_t state_mask, int tshift,
-                                                          uint64_t num_buckets, uint32_t *__restrict__ starts, int fshift,
-                                                          uint2 *__restrict__ filter) {
-  const uint32_t i = blockIdx.x * 256u + threadIdx.x;
-  if (i >= n) return;
-  const uint64_t last = num_buckets;  // keys wider than the operator's word sort after every bucket
-  const uint64_t key = spins[i];
-  uint64_t b = (key & ~state_mask) ? last : key >> tshift;
-  uint64_t prev = 0;  // first bucket this thread fills
-  if (i > 0) {
-    const uint64_t pk = spins[i - 1];
-    prev = ((pk & ~state_mask) ? last : pk >> tshift) + 1;
-  }
-  for (uint64_t k = prev; k <= b && k <= last; ++k) starts[k] = i;
-  if (i == n - 1)
-    for (uint64_t k = b + 1; k <= last; ++k) starts[k] = n;
-  if ((key & ~state_mask) == 0) {
-    const uint32_t h = filter_hash(key);
-    atomicOr(reinterpret_cast<unsigned long long *>(filter + (key >> fshift)), filter_bits(h));  // one RED.OR.64 per key
-  }
-}
-
 // ---- X1 fused with the index build: pull every rank's row block over NVLink peer memory ----------
-// One kernel replaces ncclAllGather(keys) + ncclAllGather(amplitudes) + build_index_kernel: the blocks
+// One kernel replaces ncclAllGather(keys) + ncclAllGather(amplitudes) + the index pass: the blocks
 // of the sorted basis live in buffers the other processes of the node have mapped (CUDA IPC);
 // a thread pulls two consecutive keys and amplitudes of one block with 16-byte loads (several in
 // flight), writes the rank's private full copy and indexes the keys (first-position table + Bloom
@@ -1029,7 +1006,9 @@ struct FusedWorkspace {
 static int g_surv_entries_override = 0;
 // optional CUDA-event bracket around the extraction kernel alone (bench.py's roofline figure)
 static bool g_time_kernel = false;
-static cudaEvent_t g_ev_begin = nullptr, g_ev_end = nullptr;
+constexpr int kEvRing = 64;  // the last kEvRing launches keep their event pair
+static cudaEvent_t g_ev_begin[kEvRing] = {}, g_ev_end[kEvRing] = {};
+static uint64_t g_ev_launches = 0;
 static int g_filter_bits_delta = 0, g_table_bits_delta = 0, g_stage_a_mode = 0;
 static int g_gather_mode = 2;  // asp_gather_index: 2 = one TMA kernel (default), 1 = one kernel with plain loads, 0 = copy engines + per-block index kernels
 
@@ -1095,7 +1074,9 @@ int fused_prepare(const asp_operator *op, uint64_t n_total, const uint64_t *d_sp
     return ASP_ERR_WORKSPACE;
   }
   ASP_CUDA_CHECK(cudaMemsetAsync(static_cast<char *>(d_workspace) + w.zero_offset, 0, w.zero_bytes, s));
-  build_index_kernel<<<static_cast<unsigned>((n_total + 255) / 256), 256, 0, s>>>(d_spins, static_cast<uint32_t>(n_total), op->state_mask, w.tshift,
+  // two keys per thread: neighbours that share a filter word share one 64-bit atomic (the pass is bound by L2 atomics)
+  index_block_kernel<<<static_cast<unsigned>((n_total + 511) / 512), 256, 0, s>>>(d_spins, static_cast<uint32_t>(n_total), 0u,
+                                                                                 static_cast<uint32_t>(n_total), op->state_mask, w.tshift,
                                                                                  w.num_buckets, w.starts, w.fshift, w.filter);
   ASP_LAUNCH_CHECK();
   return ASP_OK;
@@ -1287,16 +1268,20 @@ int fused_launch(const asp_operator *op, uint64_t n_total, const uint64_t *d_spi
   ASP_REQUIRE(per_sm >= 1, "fused extraction kernel does not fit on an SM");
   const uint64_t resident = static_cast<uint64_t>(kNumSMs) * std::min(per_sm, kFxMaxCtasPerSM);
   const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(std::min<uint64_t>(a.num_tiles, resident), w.scratch_ctas));
+  const int ev_slot = static_cast<int>(g_ev_launches % kEvRing);
   if (g_time_kernel) {
-    if (!g_ev_begin) {
-      ASP_CUDA_CHECK(cudaEventCreate(&g_ev_begin));
-      ASP_CUDA_CHECK(cudaEventCreate(&g_ev_end));
+    if (!g_ev_begin[ev_slot]) {
+      ASP_CUDA_CHECK(cudaEventCreate(&g_ev_begin[ev_slot]));
+      ASP_CUDA_CHECK(cudaEventCreate(&g_ev_end[ev_slot]));
     }
-    ASP_CUDA_CHECK(cudaEventRecord(g_ev_begin, s));
+    ASP_CUDA_CHECK(cudaEventRecord(g_ev_begin[ev_slot], s));
   }
   extract_csr_kernel<<<grid, kFxThreads, smem, s>>>(a);
   ASP_LAUNCH_CHECK();
-  if (g_time_kernel) ASP_CUDA_CHECK(cudaEventRecord(g_ev_end, s));
+  if (g_time_kernel) {
+    ASP_CUDA_CHECK(cudaEventRecord(g_ev_end[ev_slot], s));
+    ++g_ev_launches;
+  }
   return ASP_OK;
 }
 
@@ -1320,12 +1305,16 @@ void asp_debug_set_extract_tuning(int filter_bits_delta, int table_bits_delta, i
 
 void asp_debug_time_extract_kernel(int enable) { g_time_kernel = enable != 0; }
 
-float asp_debug_last_extract_kernel_ms(void) {
+float asp_debug_extract_kernel_ms(int back) {
   float ms = -1.0f;
-  if (!g_ev_begin || cudaEventSynchronize(g_ev_end) != cudaSuccess) return -1.0f;
-  if (cudaEventElapsedTime(&ms, g_ev_begin, g_ev_end) != cudaSuccess) return -1.0f;
+  if (back < 0 || back >= kEvRing || static_cast<uint64_t>(back) >= g_ev_launches) return -1.0f;
+  const int slot = static_cast<int>((g_ev_launches - 1 - static_cast<uint64_t>(back)) % kEvRing);
+  if (!g_ev_begin[slot] || cudaEventSynchronize(g_ev_end[slot]) != cudaSuccess) return -1.0f;
+  if (cudaEventElapsedTime(&ms, g_ev_begin[slot], g_ev_end[slot]) != cudaSuccess) return -1.0f;
   return ms;
 }
+
+float asp_debug_last_extract_kernel_ms(void) { return asp_debug_extract_kernel_ms(0); }
 
 size_t asp_extract_csr_workspace_bytes(asp_operator const *op, uint64_t n_total, uint64_t num_rows) {
   if (!op) return 0;

@@ -294,7 +294,9 @@ def run_ours(args):
         data = torch.empty(capacity, dtype=torch.float64, device=dev)
         if ev:
             ev[0].record()
-        nnz = ffi.new("uint64_t *")
+        # timed passes do not read the count back (h_nnz = NULL: no host round trip; the count is indptr[-1],
+        # checked after the timed region) -- the capacity is known from the sizing pass
+        nnz = ffi.new("uint64_t *") if timers is None else ffi.NULL
         extract = lib().asp_extract_csr_indexed if indexed else lib().asp_extract_csr
         common.check(extract(op.handle, n_total, common.ptr(full_spins, "uint64_t *"), common.ptr(full_psi, "double *"),
                              row_begin, num_rows, common.ptr(workspace, "void *"), workspace.numel(), capacity,
@@ -303,7 +305,8 @@ def run_ours(args):
         if ev:
             ev[1].record()
             timers.append(ev)
-            kernel_only.append(float(lib().asp_debug_last_extract_kernel_ms()))
+        if timers is not None:
+            return indptr, indices, data
         m = int(nnz[0])
         return indptr, indices[:m], data[:m]
 
@@ -331,7 +334,8 @@ def run_ours(args):
     launches = int(lib().asp_kernel_launch_count()) - launches0
     clocks = sampler.stop() if rank == 0 else None
     lib().asp_debug_time_extract_kernel(0)
-    call_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in timers]))  # memset + index kernel + extraction kernel + count read-back
+    call_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in timers]))  # memset + index kernel + extraction kernel
+    kernel_only = [float(lib().asp_debug_extract_kernel_ms(k)) for k in range(min(args.steps, 64))]  # read AFTER the timed region
     kernel_ms = float(np.mean(kernel_only))                                 # extract_csr_kernel alone
     nnz_total = D.sum_over_ranks(float(nnz_mine), dev)
     candidates_mine = None
@@ -343,12 +347,16 @@ def run_ours(args):
         "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": kernel_ms, "call_ms": call_ms,
         "exchange_ms": float(np.mean([e[0].elapsed_time(e[1]) for e in exchange])) if exchange else 0.0,
         "frac_whole_call": algo_bytes / (call_ms * 1e-3) / 1e9 / peak,
-        "note": "kernel_ms: CUDA events around extract_csr_kernel alone on its launching stream (asp_debug_time_extract_kernel); "
-                "call_ms: events around the whole asp_extract_csr call (memset + build_index_kernel + extract_csr_kernel + 8-byte "
-                "count read-back); exchange_ms: the two NCCL all-gathers of X1 (N > 1; includes waiting for the slowest rank); algorithmic bytes = 24 B/row + 20 B/coupling (SURVEY.md 8d); the kernel is bound by instruction "
-                "issue, not by HBM (DESIGN.md 4.1, profiles/)",
+        "note": "kernel_ms: CUDA events around extract_csr_kernel alone on its launching stream (asp_debug_time_extract_kernel; read after "
+                "the timed region); call_ms: events around the whole asp_extract_csr call (memset + index_block_kernel + extract_csr_kernel; "
+                "timed passes do not read the count back, it is checked afterwards); exchange_ms (N > 1; includes waiting for the slowest rank): "
+                "--exchange peer = asp_gather_index, ONE kernel that pulls every row block over NVLink peer memory (cp.async.bulk) AND builds "
+                "the index behind the transfer (so call_ms has no index pass); --exchange nccl = the two NCCL all-gathers; algorithmic bytes = "
+                "24 B/row + 20 B/coupling (SURVEY.md 8d); the kernel is bound by instruction issue, not by HBM (DESIGN.md 4.1, profiles/)",
     }
     indptr, indices, data = out
+    assert int(indptr[-1]) == nnz_mine, "timed pass produced a different coupling count"
+    indices, data = indices[:nnz_mine], data[:nnz_mine]
 
     # ---- end to end through the C ABI with HOST (pinned) buffers ----------------------------
     e2e = None

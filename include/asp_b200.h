@@ -153,6 +153,8 @@ void asp_debug_set_extract_tuning(int filter_bits_delta, int table_bits_delta, i
 void asp_debug_set_apply_mode(int mode); /* 1 = asp_operator_apply_dev always takes its general kernels */
 void asp_debug_time_extract_kernel(int enable);
 float asp_debug_last_extract_kernel_ms(void);
+/* Same for the launch `back` launches before the last one (0 = last; the last 64 timed launches are kept). */
+float asp_debug_extract_kernel_ms(int back);
 
 /* Canonical CSR of generation-order rows (raw output of asp_build_matrix_dev): inside each
  * row a stable sort by column, duplicates summed in generation order -- what scipy's
