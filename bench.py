@@ -29,7 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SYSTEM = "heisenberg_kagome_36"
-TRAFFIC_BYTES = 2_516_333_344  # dram__bytes_read.sum + dram__bytes_write.sum of extract_csr_kernel per launch, ncu --set full (profiles/r1_ncu_v3_traffic.csv)
+TRAFFIC_BYTES = 2_559_235_000  # dram__bytes_read.sum + dram__bytes_write.sum of extract_csr_kernel per launch, ncu --set full (profiles/r1_final_ncu_traffic.csv)
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
 
 
