@@ -73,6 +73,11 @@ class _RawDeviceMemory:
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (address, False), "version": 2}
 
 
+class PeerMemoryUnavailable(RuntimeError):
+    """Peer memory could not be set up on at least one rank (raised on EVERY rank, so the caller's
+    choice of exchange stays collective)."""
+
+
 class PeerBasis:
     """X1 over NVLink peer memory: this rank's row block of the sorted basis (keys + amplitudes)
     lives in a buffer every other process of the node maps through CUDA IPC.
@@ -109,26 +114,51 @@ class PeerBasis:
             raise ValueError("PeerBasis supports at most 16 ranks (one NVSwitch domain)")
         self.capacity = (int(capacity_rows) + 31) // 32 * 32
         nbytes = self.FLAG_BYTES + 16 * self.capacity
+        # Every collective below is reached by EVERY rank whatever failed locally, so a rank that cannot
+        # allocate or map peer memory makes all ranks raise together (callers fall back to NCCL in step).
         own = ffi.new("void **")
         handle = ffi.new("unsigned char[64]")
-        check(lib().asp_peer_alloc(nbytes, own, handle))
-        self._own = int(ffi.cast("uintptr_t", own[0]))
-        self._opened = []
+        error = None
+        self._own, self._opened = 0, []
+        try:
+            check(lib().asp_peer_alloc(nbytes, own, handle))
+            self._own = int(ffi.cast("uintptr_t", own[0]))
+        except Exception as exc:  # noqa: BLE001
+            error = "rank %d: %s" % (self.rank, exc)
         bases = [0] * self.world
         bases[self.rank] = self._own
         if self.world > 1:
-            mine = (bytes(ffi.buffer(handle, 64)), self.capacity)
+            mine = (bytes(ffi.buffer(handle, 64)) if error is None else None, self.capacity, error)
             every = [None] * self.world
             dist.all_gather_object(every, mine)
-            if any(cap != self.capacity for _, cap in every):
-                raise ValueError("PeerBasis: every rank must pass the same capacity_rows")
-            for q, (h, _) in enumerate(every):
-                if q == self.rank:
-                    continue
-                out = ffi.new("void **")
-                check(lib().asp_peer_open(ffi.from_buffer("unsigned char[]", h), out))
-                bases[q] = int(ffi.cast("uintptr_t", out[0]))
-                self._opened.append(bases[q])
+            errors = [e for _, _, e in every if e]
+            if not errors and any(cap != self.capacity for _, cap, _ in every):
+                errors = ["every rank must pass the same capacity_rows"]
+            if not errors:
+                try:
+                    for q, (h, _, _) in enumerate(every):
+                        if q == self.rank:
+                            continue
+                        out = ffi.new("void **")
+                        check(lib().asp_peer_open(ffi.from_buffer("unsigned char[]", h), out))
+                        bases[q] = int(ffi.cast("uintptr_t", out[0]))
+                        self._opened.append(bases[q])
+                except Exception as exc:  # noqa: BLE001
+                    error = "rank %d: %s" % (self.rank, exc)
+                outcome = [None] * self.world
+                dist.all_gather_object(outcome, error)
+                errors = [e for e in outcome if e]
+            if errors:
+                for address in self._opened:
+                    lib().asp_peer_close(ffi.cast("void *", address))
+                self._opened = []
+                barrier()
+                if self._own:
+                    lib().asp_peer_free(ffi.cast("void *", self._own))
+                    self._own = 0
+                raise PeerMemoryUnavailable("; ".join(errors))
+        elif error is not None:
+            raise PeerMemoryUnavailable(error)
         self._bases = bases
         raw = torch.as_tensor(_RawDeviceMemory(self._own, nbytes), device=self.device)
         self._raw = raw

@@ -259,8 +259,16 @@ def run_ours(args):
 
     bounds = [D.block(n_total, r, world)[0] for r in range(world)] + [n_total]
     peer = None
+    exchange_used = "none" if world == 1 else args.exchange
     if world > 1 and args.exchange != "nccl":
-        peer = D.PeerBasis(max(bounds[r + 1] - bounds[r] for r in range(world)), dev, mode={"peer": "tma", "peer-sm": "sm", "peer-ce": "ce"}[args.exchange])
+        try:
+            peer = D.PeerBasis(max(bounds[r + 1] - bounds[r] for r in range(world)), dev,
+                               mode={"peer": "tma", "peer-sm": "sm", "peer-ce": "ce"}[args.exchange])
+        except D.PeerMemoryUnavailable as exc:  # raised on every rank together: all ranks take the NCCL exchange
+            if rank == 0:
+                print("bench: peer memory unavailable (%s); X1 falls back to NCCL all-gather" % exc, file=sys.stderr)
+            exchange_used = "nccl (peer memory unavailable)"
+    if peer is not None:
         peer.spins[:num_rows] = my_spins
         peer.psi[:num_rows] = my_psi
 
@@ -474,7 +482,7 @@ def run_ours(args):
             "config": {"workload": "heisenberg_kagome_36-shaped U(1) basis (36 spins, 72 bonds), %d sampled states per GPU, "
                                    "cluster-closed subset, Ising extraction to CSR" % args.states,
                        "states_total": n_total, "rows_per_gpu": num_rows, "couplings_total": int(nnz_total),
-                       "candidates_per_row": 37.0, "parallelism": "row blocks x%d, basis exchanged every step (%s)" % (world, "none" if world == 1 else args.exchange),
+                       "candidates_per_row": 37.0, "parallelism": "row blocks x%d, basis exchanged every step (%s)" % (world, exchange_used),
                        "l2": "inputs (%.0f MB) larger than L2" % ((n_total * 16 + need) / 1e6)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "anneal": anneal,
         }

@@ -30,6 +30,14 @@ def main():
     e, b, owner = D.reduce_best(-3.0, bits)  # tie -> lowest rank
     assert owner == 0 and torch.equal(b, torch.full((5,), 10, dtype=torch.int64))
     assert D.max_over_ranks(float(rank), "cpu") == 1.0 and D.sum_over_ranks(1.5, "cpu") == 3.0
+    # peer memory cannot exist without a CUDA device: EVERY rank must learn that together (the error
+    # travels through the same collectives a successful set-up uses), so callers can switch to the
+    # all-gather exchange in step
+    try:
+        D.PeerBasis(1000, device=torch.device("cpu"))
+        raise SystemExit("PeerBasis must not come up without CUDA")
+    except D.PeerMemoryUnavailable as exc:
+        assert "rank 0" in str(exc) and "rank 1" in str(exc), str(exc)
     D.barrier()
     if rank == 0:
         print("SHARDING_OK")
