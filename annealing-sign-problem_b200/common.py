@@ -178,6 +178,22 @@ def extract_csr_indexed_device(operator: ls.Operator, spins: torch.Tensor, psi: 
     return indptr, indices[:m], data[:m]
 
 
+def extract_indexed_to_host(operator: ls.Operator, spins: torch.Tensor, psi: torch.Tensor, row_begin: int, num_rows: int,
+                            workspace: torch.Tensor, h_indptr: torch.Tensor, h_indices: torch.Tensor, h_data: torch.Tensor) -> int:
+    """The sharded end-to-end call (asp_extract_indexed_to_host): extraction on a workspace indexed by
+    asp_gather_index, CSR rows written to the caller's (pinned) HOST tensors chunk by chunk while the next
+    chunk is extracted.  -> number of couplings."""
+    require_cuda()
+    assert h_indptr.dtype == torch.int64 and h_indices.dtype == torch.int32 and h_data.dtype == torch.float64
+    assert h_indptr.numel() >= num_rows + 1 and h_indices.numel() == h_data.numel()
+    nnz = ffi.new("uint64_t *")
+    check(lib().asp_extract_indexed_to_host(operator.handle, int(spins.shape[0]), ptr(spins, "uint64_t *"), ptr(psi, "double *"),
+                                            row_begin, num_rows, ptr(workspace, "void *"), workspace.numel(), h_indices.numel(),
+                                            ffi.cast("int64_t *", h_indptr.data_ptr()), ffi.cast("int32_t *", h_indices.data_ptr()),
+                                            ffi.cast("double *", h_data.data_ptr()), nnz, stream()))
+    return int(nnz[0])
+
+
 def build_csr_from_candidates_device(spins, psi, row_begin, other_spins, other_coeffs, other_counts, max_row_len=0):
     """Explicit-candidate path (what cbits/build_matrix.c does) + canonical CSR."""
     dev = require_cuda()

@@ -109,6 +109,50 @@ void release_busy(Arena &A) {
 
 }  // namespace
 
+// The chunked extraction + drain shared by the host entry points: chunk c+1 is extracted while chunk c's
+// rows travel back over PCIe.  The workspace is already zeroed and indexed; d_indptr/d_indices/d_data are
+// the arena's output buffers.
+static int extract_chunks_to_host(Arena &A, asp_operator const *op, uint64_t n, const uint64_t *d_spins, const double *d_psi,
+                                  uint64_t row_begin, uint64_t num_rows, uint64_t chunk_rows, int chunks, void *d_workspace,
+                                  uint64_t dev_capacity, uint64_t capacity, int64_t *d_indptr, int32_t *d_indices, double *d_data,
+                                  unsigned long long *d_totals, int64_t *h_indptr, int32_t *h_indices, double *h_data, uint64_t *h_nnz) {
+  int rc = ASP_OK;
+  {
+    for (int c = 0; c < chunks; ++c) {
+      const uint64_t begin = c * chunk_rows, rows = std::min(chunk_rows, num_rows - begin);
+      rc = asp::fused_launch(op, n, d_spins, d_psi, row_begin, num_rows, c, begin, rows, d_workspace, dev_capacity, d_indptr,
+                             d_indices, d_data, d_totals + c, A.compute);
+      if (rc != ASP_OK) goto out;
+      HOST_CUDA(cudaEventRecord(A.ev_chunk[c], A.compute));
+    }
+    // drain: as soon as a chunk is done its rows go back while the next chunk is extracted
+    unsigned long long done = 0;
+    bool overflow = false;
+    for (int c = 0; c < chunks; ++c) {
+      HOST_CUDA(cudaEventSynchronize(A.ev_chunk[c]));
+      const unsigned long long total = *static_cast<volatile unsigned long long *>(A.h_totals + c);
+      const uint64_t begin = c * chunk_rows, rows = std::min(chunk_rows, num_rows - begin);
+      const uint64_t extra = (c == chunks - 1) ? 1 : 0;  // the closing indptr entry
+      HOST_CUDA(cudaMemcpyAsync(h_indptr + begin, d_indptr + begin, (rows + extra) * sizeof(int64_t), cudaMemcpyDeviceToHost, A.copy_out));
+      if (total > capacity) overflow = true;
+      if (!overflow && total > done) {
+        HOST_CUDA(cudaMemcpyAsync(h_indices + done, d_indices + done, (total - done) * sizeof(int32_t), cudaMemcpyDeviceToHost, A.copy_out));
+        HOST_CUDA(cudaMemcpyAsync(h_data + done, d_data + done, (total - done) * sizeof(double), cudaMemcpyDeviceToHost, A.copy_out));
+      }
+      done = total;
+    }
+    HOST_CUDA(cudaStreamSynchronize(A.copy_out));
+    *h_nnz = done;
+    if (overflow) {
+      asp::set_error("output capacity too small: %llu couplings, room for %llu (h_indptr is complete; call again with the larger capacity)",
+                     done, static_cast<unsigned long long>(capacity));
+      rc = ASP_ERR_WORKSPACE;
+    }
+  }
+out:
+  return rc;
+}
+
 struct asp_host_job {
   uint64_t num_rows = 0, nnz = 0;
 };
@@ -171,39 +215,61 @@ int asp_extract_host(asp_operator const *op, uint64_t n, uint64_t const *h_spins
     rc = asp::fused_prepare(op, n, d_spins, num_rows, A.workspace.p, A.workspace.cap, A.compute);
     if (rc != ASP_OK) goto out;
     HOST_CUDA(cudaStreamWaitEvent(A.compute, A.ev_psi, 0));
-    for (int c = 0; c < chunks; ++c) {
-      const uint64_t begin = c * chunk_rows, rows = std::min(chunk_rows, num_rows - begin);
-      rc = asp::fused_launch(op, n, d_spins, d_psi, row_begin, num_rows, c, begin, rows, A.workspace.p, dev_capacity, d_indptr,
-                             d_indices, d_data, d_totals + c, A.compute);
-      if (rc != ASP_OK) goto out;
-      HOST_CUDA(cudaEventRecord(A.ev_chunk[c], A.compute));
-    }
-    // drain: as soon as a chunk is done its rows go back while the next chunk is extracted
-    unsigned long long done = 0;
-    bool overflow = false;
-    for (int c = 0; c < chunks; ++c) {
-      HOST_CUDA(cudaEventSynchronize(A.ev_chunk[c]));
-      const unsigned long long total = *static_cast<volatile unsigned long long *>(A.h_totals + c);
-      const uint64_t begin = c * chunk_rows, rows = std::min(chunk_rows, num_rows - begin);
-      const uint64_t extra = (c == chunks - 1) ? 1 : 0;  // the closing indptr entry
-      HOST_CUDA(cudaMemcpyAsync(h_indptr + begin, d_indptr + begin, (rows + extra) * sizeof(int64_t), cudaMemcpyDeviceToHost, A.copy_out));
-      if (total > capacity) overflow = true;
-      if (!overflow && total > done) {
-        HOST_CUDA(cudaMemcpyAsync(h_indices + done, d_indices + done, (total - done) * sizeof(int32_t), cudaMemcpyDeviceToHost, A.copy_out));
-        HOST_CUDA(cudaMemcpyAsync(h_data + done, d_data + done, (total - done) * sizeof(double), cudaMemcpyDeviceToHost, A.copy_out));
-      }
-      done = total;
-    }
-    HOST_CUDA(cudaStreamSynchronize(A.copy_out));
-    *h_nnz = done;
-    if (overflow) {
-      asp::set_error("output capacity too small: %llu couplings, room for %llu (h_indptr is complete; call again with the larger capacity)",
-                     done, static_cast<unsigned long long>(capacity));
-      rc = ASP_ERR_WORKSPACE;
-    }
+    rc = extract_chunks_to_host(A, op, n, d_spins, d_psi, row_begin, num_rows, chunk_rows, chunks, A.workspace.p, dev_capacity, capacity,
+                                d_indptr, d_indices, d_data, d_totals, h_indptr, h_indices, h_data, h_nnz);
   }
 out:
   if (rc == ASP_ERR_CUDA) cudaDeviceSynchronize();  // leave no work in flight behind a failed call
+  release_busy(A);
+  return rc;
+}
+
+int asp_extract_indexed_to_host(asp_operator const *op, uint64_t n, uint64_t const *d_spins, double const *d_psi, uint64_t row_begin,
+                                uint64_t num_rows, void *d_workspace, size_t workspace_bytes, uint64_t capacity, int64_t *h_indptr,
+                                int32_t *h_indices, double *h_data, uint64_t *h_nnz, void *stream) {
+  int rc = asp::fused_check_operator(op);
+  if (rc != ASP_OK) return rc;
+  ASP_REQUIRE(h_nnz && h_indptr, "NULL argument");
+  ASP_REQUIRE(capacity == 0 || (h_indices && h_data), "NULL output buffer");
+  ASP_REQUIRE(n < (1ull << 31), "int32 column indices need n_total < 2^31 (scipy picks int32 the same way)");
+  ASP_REQUIRE(row_begin + num_rows <= n, "row block exceeds the basis");
+  *h_nnz = 0;
+  if (num_rows == 0 || n == 0) {
+    h_indptr[0] = 0;
+    return ASP_OK;
+  }
+  ASP_REQUIRE(d_spins && d_psi && d_workspace, "NULL device buffer");
+  ASP_REQUIRE(workspace_bytes >= asp::fused_workspace_bytes(op, n, num_rows), "workspace too small");
+  Arena &A = g_arena;
+  rc = acquire(A);
+  if (rc != ASP_OK) return rc;
+  {
+    uint64_t chunk_rows = (num_rows + 7) / 8;
+    if (chunk_rows < (1u << 17)) chunk_rows = 1u << 17;
+    chunk_rows = (chunk_rows + kFusedTileRows - 1) / kFusedTileRows * kFusedTileRows;
+    const int chunks = static_cast<int>((num_rows + chunk_rows - 1) / chunk_rows);
+    const uint64_t worst = num_rows * op->max_candidates();
+    const uint64_t dev_capacity = std::min(capacity, worst);
+    rc = A.reserve(A.indptr, (num_rows + 1) * sizeof(int64_t));
+    if (rc == ASP_OK) rc = A.reserve(A.indices, (dev_capacity + 1) * sizeof(int32_t), false);
+    if (rc == ASP_OK) rc = A.reserve(A.data, (dev_capacity + 1) * sizeof(double), false);
+    if (rc != ASP_OK) goto out;
+    unsigned long long *d_totals = nullptr;
+    HOST_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&d_totals), A.h_totals, 0));
+    // the caller's stream gathered and indexed the basis: the arena's compute stream continues behind it
+    HOST_CUDA(cudaEventRecord(A.ev_spins, static_cast<cudaStream_t>(stream)));
+    HOST_CUDA(cudaStreamWaitEvent(A.compute, A.ev_spins, 0));
+    rc = extract_chunks_to_host(A, op, n, d_spins, d_psi, row_begin, num_rows, chunk_rows, chunks, d_workspace, dev_capacity, capacity,
+                                static_cast<int64_t *>(A.indptr.p), static_cast<int32_t *>(A.indices.p), static_cast<double *>(A.data.p),
+                                d_totals, h_indptr, h_indices, h_data, h_nnz);
+    // the caller's stream must not reuse the workspace or the basis before the chunks are done
+    if (rc == ASP_OK) {
+      HOST_CUDA(cudaEventRecord(A.ev_psi, A.compute));
+      HOST_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), A.ev_psi, 0));
+    }
+  }
+out:
+  if (rc == ASP_ERR_CUDA) cudaDeviceSynchronize();
   release_busy(A);
   return rc;
 }

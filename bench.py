@@ -375,7 +375,22 @@ def run_ours(args):
         h_indices = torch.empty(capacity, dtype=torch.int32).pin_memory()
         h_data = torch.empty(capacity, dtype=torch.float64).pin_memory()
 
-        def host_pass():
+        if peer is not None:
+            # sharded end to end: every rank uploads ONLY its own row block (pinned host -> its peer buffer), the
+            # full basis arrives over NVLink (asp_gather_index), the CSR rows go back to pinned host memory
+            h_my_spins = my_spins.cpu().pin_memory()
+            h_my_psi = my_psi.cpu().pin_memory()
+
+        def host_pass_sharded():
+            peer.begin_epoch()
+            peer.spins[:num_rows].copy_(h_my_spins, non_blocking=True)
+            peer.psi[:num_rows].copy_(h_my_psi, non_blocking=True)
+            peer.publish()
+            full_spins, full_psi = peer.gather_index(op, bounds, num_rows, workspace)
+            peer.release()
+            assert common.extract_indexed_to_host(op, full_spins, full_psi, row_begin, num_rows, workspace, h_indptr, h_indices, h_data) == nnz_mine
+
+        def host_pass_full():
             nnz = ffi.new("uint64_t *")
             common.check(lib().asp_extract_host(op.handle, n_total, ffi.cast("uint64_t *", h_spins.data_ptr()),
                                                 ffi.cast("double *", h_psi.data_ptr()), row_begin, num_rows, capacity,
@@ -383,6 +398,7 @@ def run_ours(args):
                                                 ffi.cast("double *", h_data.data_ptr()), nnz))
             assert int(nnz[0]) == nnz_mine
 
+        host_pass = host_pass_sharded if peer is not None else host_pass_full
         e2e_steps = max(2, min(args.steps, 5))
         host_pass()
         D.barrier()
@@ -394,9 +410,13 @@ def run_ours(args):
         e2e_s = D.max_over_ranks(time.perf_counter() - t0, dev)
         assert int(h_indptr[-1]) == nnz_mine
         e2e = {"value": nnz_total * e2e_steps / e2e_s, "unit": "couplings/s",
-               "h2d_bytes_per_step": int(n_total * 16), "d2h_bytes_per_step": int((num_rows + 1) * 8 + nnz_mine * 12),
+               "h2d_bytes_per_step": int((num_rows if peer is not None else n_total) * 16),
+               "d2h_bytes_per_step": int((num_rows + 1) * 8 + nnz_mine * 12),
                "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
-               "api": "asp_extract_host (include/asp_b200.h), pinned host buffers, row chunks copied back while the next chunk is extracted"}
+               "api": ("per rank: own row block pinned host -> peer buffer, asp_gather_index over NVLink, asp_extract_indexed_to_host "
+                       "(row chunks copied back while the next chunk is extracted); bytes are per rank" if peer is not None else
+                       "asp_extract_host (include/asp_b200.h), pinned host buffers, row chunks copied back while the next chunk is "
+                       "extracted" + ("; every rank uploads the full basis; bytes are per rank" if world > 1 else ""))}
         del h_spins, h_psi, h_indptr, h_indices, h_data
 
     # ---- annealing stage on the extracted model (replicas shard over ranks) ------------------

@@ -288,6 +288,15 @@ int asp_gather_index(asp_operator const *op, uint32_t world, uint32_t rank,
                      double const *const *d_shard_psi, uint64_t const *d_ready, uint64_t epoch,
                      uint64_t *d_spins, double *d_psi, uint64_t num_rows, void *d_workspace,
                      size_t workspace_bytes, void *stream);
+/* The sharded end-to-end path: asp_gather_index on `stream`, then this call -- the single-pass
+ * extraction of rows [row_begin, row_begin+num_rows) in row chunks on the indexed workspace, every
+ * chunk's rows copied to the caller's HOST buffers (pinned: asynchronously) while the next chunk is
+ * extracted.  Same output contract as asp_extract_host. */
+int asp_extract_indexed_to_host(asp_operator const *op, uint64_t n_total, uint64_t const *d_spins,
+                                double const *d_psi, uint64_t row_begin, uint64_t num_rows,
+                                void *d_workspace, size_t workspace_bytes, uint64_t capacity,
+                                int64_t *h_indptr, int32_t *h_indices, double *h_data, uint64_t *h_nnz,
+                                void *stream);
 /* asp_gather_index has three implementations of the same contract (measured within 5 % of each
  * other and of NCCL's all-gather alone, ~510 GB/s pulled per rank on 4 GPUs -- the fabric, not the
  * kernel, sets the pace): 2 (default) = ONE persistent kernel, cp.async.bulk (TMA) keeps 128 KB per

@@ -247,6 +247,19 @@ def test_gather_index_kernel_over_emulated_shards_equals_the_unsharded_build():
             lo, hi = int(ref[0][row_begin]), int(ref[0][row_begin + num_rows])
             assert torch.equal(indptr, ref[0][row_begin:row_begin + num_rows + 1] - lo)
             assert torch.equal(indices, ref[1][lo:hi]) and torch.equal(data, ref[2][lo:hi])
+            if mode == 2 and world == 4:  # the sharded host-buffer path: gather again, CSR straight into pinned host memory
+                common.check(lib().asp_gather_index(
+                    op.handle, world, rank, ffi.new("uint64_t[]", bounds),
+                    ffi.new("uint64_t const *[]", [common.ptr(t, "uint64_t const *") for t in parts_s]),
+                    ffi.new("double const *[]", [common.ptr(t, "double const *") for t in parts_p]),
+                    ffi.NULL, 0, common.ptr(full_s, "uint64_t *"), common.ptr(full_p, "double *"), num_rows,
+                    common.ptr(workspace, "void *"), need, common.stream()))
+                h_indptr = torch.empty(num_rows + 1, dtype=torch.int64).pin_memory()
+                h_indices = torch.empty(hi - lo + 5, dtype=torch.int32).pin_memory()
+                h_data = torch.empty(hi - lo + 5, dtype=torch.float64).pin_memory()
+                m = common.extract_indexed_to_host(op, full_s, full_p, row_begin, num_rows, workspace, h_indptr, h_indices, h_data)
+                assert m == hi - lo and torch.equal(h_indptr, indptr.cpu())
+                assert torch.equal(h_indices[:m], indices.cpu()) and torch.equal(h_data[:m], data.cpu())
     lib().asp_set_gather_mode(2)
 
 
