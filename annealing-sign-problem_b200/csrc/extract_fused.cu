@@ -209,6 +209,7 @@ struct GatherArgs {
   uint64_t begin[kGxMaxRanks + 1];       // global index of the first key of every block
   uint64_t unit_begin[kGxMaxRanks + 1];  // first key pair of the k-th VISITED block
   uint64_t chunk_begin[kGxMaxRanks + 1]; // first 1024-key chunk of the k-th visited block (TMA variant)
+  int stages;                            // bulk copies in flight per CTA (TMA variant)
   int order[kGxMaxRanks];                // k-th visited block
   int world;
   const unsigned long long *ready;  // local flags [world] (NULL: no waiting)
@@ -393,13 +394,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                : "memory");
 }
 
-__global__ void __launch_bounds__(kTxThreads, kTxCtasPerSM) gather_index_tma_kernel(const GatherArgs a) {
+__global__ void __launch_bounds__(kTxThreads, 6) gather_index_tma_kernel(const GatherArgs a) {
   extern __shared__ __align__(128) unsigned char tx_smem[];
   const uint32_t smem0 = smem_addr(tx_smem);
-  const uint32_t bars = smem0 + kTxStages * kTxChunk * 16;  // kTxStages mbarriers behind the stages
+  const int stages = a.stages;
+  const uint32_t bars = smem0 + static_cast<uint32_t>(stages) * kTxChunk * 16;  // mbarriers behind the stages
   const uint64_t total = a.chunk_begin[a.world];
   if (threadIdx.x == 0) {
-    for (int st = 0; st < kTxStages; ++st) mbar_init(bars + 8 * st, 1);
+    for (int st = 0; st < stages; ++st) mbar_init(bars + 8 * st, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -424,7 +426,7 @@ __global__ void __launch_bounds__(kTxThreads, kTxCtasPerSM) gather_index_tma_ker
       asm volatile("fence.proxy.async;" ::: "memory");  // the async proxy reads what the acquire made visible
       waited |= 1u << q;
     }
-    const uint32_t st = static_cast<uint32_t>(it % kTxStages);
+    const uint32_t st = static_cast<uint32_t>(it % stages);
     const uint32_t even = cnt & ~1u;  // whole 16-byte units; an odd last key is read with a plain load
     mbar_arrive_expect_tx(bars + 8 * st, even * 16u);
     if (even) {
@@ -433,16 +435,16 @@ __global__ void __launch_bounds__(kTxThreads, kTxCtasPerSM) gather_index_tma_ker
     }
   };
   if (threadIdx.x == 0)
-    for (int it = 0; it < kTxStages; ++it) issue(it);
+    for (int it = 0; it < stages; ++it) issue(it);
   for (uint64_t it = 0;; ++it) {
     const uint64_t c = blockIdx.x + it * gridDim.x;
     if (c >= total) break;
-    const uint32_t st = static_cast<uint32_t>(it % kTxStages);
+    const uint32_t st = static_cast<uint32_t>(it % stages);
     int q;
     uint64_t l0;
     uint32_t cnt;
     locate(c, q, l0, cnt);
-    mbar_wait(bars + 8 * st, static_cast<uint32_t>(it / kTxStages) & 1u);
+    mbar_wait(bars + 8 * st, static_cast<uint32_t>(it / stages) & 1u);
     const unsigned long long *s_keys = reinterpret_cast<const unsigned long long *>(tx_smem + st * (kTxChunk * 16));
     const unsigned long long *s_amps = s_keys + kTxChunk;
 #pragma unroll
@@ -478,7 +480,7 @@ __global__ void __launch_bounds__(kTxThreads, kTxCtasPerSM) gather_index_tma_ker
       emit_pair(a, g, two ? 2u : 1u, keys, amps, has_prev, pk);
     }
     __syncthreads();  // every thread is done with this stage: refill it
-    if (threadIdx.x == 0) issue(it + kTxStages);
+    if (threadIdx.x == 0) issue(it + stages);
   }
 }
 
@@ -1010,6 +1012,7 @@ constexpr int kEvRing = 64;  // the last kEvRing launches keep their event pair
 static cudaEvent_t g_ev_begin[kEvRing] = {}, g_ev_end[kEvRing] = {};
 static uint64_t g_ev_launches = 0;
 static int g_filter_bits_delta = 0, g_table_bits_delta = 0, g_stage_a_mode = 0;
+static int g_overlap = 0;      // asp_set_overlap_mode: leave room on every SM for the other kernel of a two-deep pipeline
 static int g_gather_mode = 2;  // asp_gather_index: 2 = one TMA kernel (default), 1 = one kernel with plain loads, 0 = copy engines + per-block index kernels
 
 static FusedWorkspace carve_fused(void *base, const asp_operator *op, uint64_t n_total, uint64_t num_rows) {
@@ -1135,9 +1138,12 @@ int fused_prepare_gather(const asp_operator *op, uint32_t world, uint32_t rank, 
   a.filter = w.filter;
   ASP_CUDA_CHECK(cudaMemsetAsync(static_cast<char *>(d_workspace) + w.zero_offset, 0, w.zero_bytes, s));
   if (tma) {
+    // alone: 2 CTAs per SM; beside an extraction (overlap mode): 1 CTA per SM next to the extraction's 5
+    a.stages = kTxStages;
+    const size_t smem = kTxSmem;
     ASP_CUDA_CHECK(cudaFuncSetAttribute(gather_index_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTxSmem)));
-    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(chunks, static_cast<uint64_t>(kNumSMs) * kTxCtasPerSM));
-    gather_index_tma_kernel<<<grid, kTxThreads, kTxSmem, s>>>(a);
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(chunks, static_cast<uint64_t>(kNumSMs) * (g_overlap ? 1 : kTxCtasPerSM)));
+    gather_index_tma_kernel<<<grid, kTxThreads, smem, s>>>(a);
   } else {
     const uint64_t per_cta = static_cast<uint64_t>(kGxThreads) * kGxUnroll;
     gather_index_kernel<<<static_cast<unsigned>((units + per_cta - 1) / per_cta), kGxThreads, 0, s>>>(a);
@@ -1266,7 +1272,8 @@ int fused_launch(const asp_operator *op, uint64_t n_total, const uint64_t *d_spi
   int per_sm = 0;
   ASP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, extract_csr_kernel, kFxThreads, smem));
   ASP_REQUIRE(per_sm >= 1, "fused extraction kernel does not fit on an SM");
-  const uint64_t resident = static_cast<uint64_t>(kNumSMs) * std::min(per_sm, kFxMaxCtasPerSM);
+  // overlap mode: one CTA slot less per SM, so that a gather_index_tma_kernel CTA (64 KB, 256 threads, 40 registers) fits beside the extraction
+  const uint64_t resident = static_cast<uint64_t>(kNumSMs) * std::max(1, std::min(per_sm, kFxMaxCtasPerSM) - (g_overlap ? 1 : 0));
   const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(std::min<uint64_t>(a.num_tiles, resident), w.scratch_ctas));
   const int ev_slot = static_cast<int>(g_ev_launches % kEvRing);
   if (g_time_kernel) {
@@ -1388,6 +1395,8 @@ int asp_gather_index(asp_operator const *op, uint32_t world, uint32_t rank, uint
   return fused_prepare_gather_ce(op, world, rank, shard_begin, d_shard_spins, d_shard_psi, d_ready, epoch, d_spins, d_psi, num_rows,
                                  d_workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
+
+void asp_set_overlap_mode(int enable) { g_overlap = enable != 0; }
 
 void asp_set_gather_mode(int mode) { g_gather_mode = (mode == 0 || mode == 1) ? mode : 2; }
 

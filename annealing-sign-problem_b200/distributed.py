@@ -189,19 +189,22 @@ class PeerBasis:
 
         check(lib().asp_peer_signal(self.world, self._flags, self.DONE_SLOT + self.rank, self.epoch, stream()))
 
-    def gather_index(self, operator, shard_begin, num_rows: int, workspace: torch.Tensor):
+    def gather_index(self, operator, shard_begin, num_rows: int, workspace: torch.Tensor, slot: int = 0):
         """-> (full_spins int64 [n_total], full_psi f64 [n_total]); ``workspace`` is left indexed
-        for asp_extract_csr_indexed(operator, n_total, ..., num_rows)."""
+        for asp_extract_csr_indexed(operator, n_total, ..., num_rows).  ``slot`` selects one of the
+        private copies (a two-deep pipeline gathers into one while the other is being extracted)."""
         from ._lib import check, ffi, lib, ptr, stream
 
         begins = [int(b) for b in shard_begin]
         assert len(begins) == self.world + 1 and begins[0] == 0
         assert all(begins[q + 1] - begins[q] <= self.capacity for q in range(self.world))
         n_total = begins[-1]
-        if self._full is None or self._full[0].shape[0] != n_total:
-            self._full = (torch.empty(n_total, dtype=torch.int64, device=self.device),
-                          torch.empty(n_total, dtype=torch.float64, device=self.device))
-        full_spins, full_psi = self._full
+        if self._full is None:
+            self._full = {}
+        if slot not in self._full or self._full[slot][0].shape[0] != n_total:
+            self._full[slot] = (torch.empty(n_total, dtype=torch.int64, device=self.device),
+                                torch.empty(n_total, dtype=torch.float64, device=self.device))
+        full_spins, full_psi = self._full[slot]
         lib().asp_set_gather_mode(self.MODES[self.mode])
         check(lib().asp_gather_index(operator.handle, self.world, self.rank, ffi.new("uint64_t[]", begins), self._shard_spins,
                                      self._shard_psi, ffi.cast("uint64_t const *", self._own), self.epoch,

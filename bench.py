@@ -46,6 +46,10 @@ def parse_args():
     p.add_argument("--exchange", default="peer", choices=["peer", "peer-sm", "peer-ce", "nccl"],
                    help="X1 at N > 1: 'peer' = row blocks in NVLink peer memory, pulled by the copy engines and indexed block by "
                         "block behind them; 'peer-sm' = one SM kernel pulls + indexes; 'nccl' = two all-gathers + index pass (the baseline)")
+    p.add_argument("--pipeline", type=int, default=1, choices=[1, 2],
+                   help="N > 1 with a peer exchange: 1 (default) = a step is exchange, then extraction; 2 = EXPERIMENT, measured and "
+                        "rejected (DESIGN.md 5): the exchange of step k+1 on a second stream beside the extraction of step k (double "
+                        "private copies and workspaces) -- both kernels are issue-bound and slow each other down by more than the overlap gains")
     p.add_argument("--skip-anneal", action="store_true")
     p.add_argument("--skip-cpu", action="store_true")
     p.add_argument("--skip-e2e", action="store_true")
@@ -318,10 +322,77 @@ def run_ours(args):
         m = int(nnz[0])
         return indptr, indices[:m], data[:m]
 
+    pipelined = peer is not None and args.pipeline == 2
+    if pipelined:
+        workspaces = [workspace, torch.empty_like(workspace)]
+        s_exchange, s_compute = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def run_pipelined(count, timers=None):
+        """Two-deep software pipeline over `count` independent steps: [begin_epoch, publish, asp_gather_index, release] of
+        step k+1 on the exchange stream while asp_extract_csr_indexed of step k runs on the compute stream.  Private
+        copy + workspace `k % 2`; a slot is gathered into again only after the extraction that read it is done."""
+        lib().asp_set_overlap_mode(1)
+        gathered = [torch.cuda.Event() for _ in range(2)]
+        extracted = [None, None]
+        fulls = [None, None]
+        here = torch.cuda.current_stream()
+        s_exchange.wait_stream(here)
+        s_compute.wait_stream(here)
+
+        def exchange_step(k):
+            with torch.cuda.stream(s_exchange):
+                if extracted[k % 2] is not None:
+                    s_exchange.wait_event(extracted[k % 2])
+                ex = [torch.cuda.Event(enable_timing=True) for _ in range(2)] if timers is not None else None
+                peer.begin_epoch()
+                peer.publish()
+                if ex:
+                    ex[0].record()
+                fulls[k % 2] = peer.gather_index(op, bounds, num_rows, workspaces[k % 2], slot=k % 2)
+                if ex:
+                    ex[1].record()
+                    exchange.append(ex)
+                peer.release()
+                gathered[k % 2].record()
+
+        out = None
+        exchange_step(0)
+        for k in range(count):
+            if k + 1 < count:
+                exchange_step(k + 1)  # queued FIRST: its flag kernels must not wait behind the extraction
+            with torch.cuda.stream(s_compute):
+                s_compute.wait_event(gathered[k % 2])
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)] if timers is not None else None
+                indptr = torch.empty(num_rows + 1, dtype=torch.int64, device=dev)
+                indices = torch.empty(capacity, dtype=torch.int32, device=dev)
+                data = torch.empty(capacity, dtype=torch.float64, device=dev)
+                if ev:
+                    ev[0].record()
+                full_spins, full_psi = fulls[k % 2]
+                common.check(lib().asp_extract_csr_indexed(op.handle, n_total, common.ptr(full_spins, "uint64_t *"), common.ptr(full_psi, "double *"),
+                                                           row_begin, num_rows, common.ptr(workspaces[k % 2], "void *"), workspaces[k % 2].numel(),
+                                                           capacity, common.ptr(indptr, "int64_t *"), common.ptr(indices, "int32_t *"),
+                                                           common.ptr(data, "double *"), ffi.NULL, common.stream()))
+                if ev:
+                    ev[1].record()
+                    timers.append(ev)
+                extracted[k % 2] = torch.cuda.Event()
+                extracted[k % 2].record()
+                out = (indptr, indices, data)
+        here.wait_stream(s_compute)
+        here.wait_stream(s_exchange)
+        lib().asp_set_overlap_mode(0)
+        return out
+
     for _ in range(args.warmup):
         out = one_pass()
     nnz_mine = int(out[1].numel())
     del out
+    if pipelined:
+        out = run_pipelined(max(2, args.warmup))
+        torch.cuda.synchronize()
+        assert int(out[0][-1]) == nnz_mine
+        del out
     uuid = getattr(torch.cuda.get_device_properties(dev), "uuid", None)
     sampler = ClockSampler("GPU-" + str(uuid) if uuid else "", local)
     if rank == 0:
@@ -333,8 +404,11 @@ def run_ours(args):
     torch.cuda.synchronize()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
-    for _ in range(args.steps):
-        out = one_pass(timers)
+    if pipelined:
+        out = run_pipelined(args.steps, timers)
+    else:
+        for _ in range(args.steps):
+            out = one_pass(timers)
     end.record()
     D.barrier()
     torch.cuda.synchronize()
@@ -502,7 +576,9 @@ def run_ours(args):
             "config": {"workload": "heisenberg_kagome_36-shaped U(1) basis (36 spins, 72 bonds), %d sampled states per GPU, "
                                    "cluster-closed subset, Ising extraction to CSR" % args.states,
                        "states_total": n_total, "rows_per_gpu": num_rows, "couplings_total": int(nnz_total),
-                       "candidates_per_row": 37.0, "parallelism": "row blocks x%d, basis exchanged every step (%s)" % (world, exchange_used),
+                       "candidates_per_row": 37.0, "parallelism": "row blocks x%d, basis exchanged every step (%s)%s" % (
+                           world, exchange_used, "; steps pipelined two deep: the exchange of step k+1 overlaps the extraction of step k "
+                           "(independent extractions, double buffers)" if pipelined else ""),
                        "l2": "inputs (%.0f MB) larger than L2" % ((n_total * 16 + need) / 1e6)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "anneal": anneal,
         }

@@ -305,6 +305,12 @@ int asp_extract_indexed_to_host(asp_operator const *op, uint64_t n_total, uint64
  * blocks (cudaMemcpyAsync on an internal stream) and every block is indexed on the SMs as soon as
  * it has landed. */
 void asp_set_gather_mode(int mode);
+/* Experiment, measured and not adopted: asp_gather_index of the NEXT basis on one
+ * stream beside asp_extract_csr_indexed of the current one on another (separate private copies and
+ * workspaces).  Both kernels are persistent, so neither would find room beside the other: with
+ * overlap mode on, the extraction leaves one CTA slot per SM free and the gather kernel takes
+ * exactly one. */
+void asp_set_overlap_mode(int enable);
 /* asp_extract_csr without its zero + index pass: the workspace was prepared by asp_gather_index
  * for the same (op, n_total, num_rows) on the same stream. */
 int asp_extract_csr_indexed(asp_operator const *op, uint64_t n_total, uint64_t const *d_spins,
