@@ -436,6 +436,14 @@ def run_ours(args):
                 "the index behind the transfer (so call_ms has no index pass); --exchange nccl = the two NCCL all-gathers; algorithmic bytes = "
                 "24 B/row + 20 B/coupling (SURVEY.md 8d); the kernel is bound by instruction issue, not by HBM (DESIGN.md 4.1, profiles/)",
     }
+    if world > 1:  # every rank's own clocks (a step is in effect a barrier: the slowest rank sets the pace)
+        import torch.distributed as dist
+
+        mine_stats = {"kernel_ms": round(kernel_ms, 4), "call_ms": round(call_ms, 4), "exchange_ms": round(roofline["exchange_ms"], 4),
+                      "step_ms": round(start.elapsed_time(end) / args.steps, 4)}
+        every_stats = [None] * world
+        dist.all_gather_object(every_stats, mine_stats)
+        roofline["per_rank"] = {k: [st[k] for st in every_stats] for k in mine_stats}
     indptr, indices, data = out
     assert int(indptr[-1]) == nnz_mine, "timed pass produced a different coupling count"
     indices, data = indices[:nnz_mine], data[:nnz_mine]

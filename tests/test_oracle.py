@@ -327,3 +327,41 @@ def test_sampling_front_end_restatement_is_the_reference(golden_dir):
     assert np.array_equal(live_path.signs_to_bits(np.sign(psi[idx])), g["exact_bits"])
     with pytest.raises(ValueError):
         live_path.batched_index(states, np.array([states[3], states[-1] + np.uint64(1)], dtype=np.uint64))
+
+
+def test_kat4_c_path_equals_live_path_on_random_problems(oracle_capi):
+    """KAT-4, hypothesis-driven: on random operators and random sampled subsets the merged + sorted output of
+    the build_matrix restatement (and of the reference's own C when oracle/_ref is built) has exactly the
+    indices of the live-path restatement; values to 1e-12."""
+    hypothesis = pytest.importorskip("hypothesis")
+    from hypothesis import HealthCheck, given, settings
+
+    from _strategies import problems, random_subset
+
+    impl = "ref" if oracle_capi.have_ref() else "port"
+
+    @settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(problems())
+    def check(problem):
+        cfg, seed, m = problem
+        spins, psi = random_subset(cfg, seed, m)
+        if spins.shape[0] == 0 or not np.any(psi):
+            return
+        op = OperatorNP.from_config(cfg)
+        with np.errstate(divide="ignore"):
+            live = live_path.make_ising_model(spins, op, log_psi=np.log(psi.astype(np.complex128))).exchange.tocsr()
+        live.sort_indices()
+        n = spins.shape[0]
+        unit = psi / np.linalg.norm(psi)
+        other_spins, other_coeffs, other_counts = op.apply_u64(spins)
+        idx = np.clip(np.searchsorted(spins, other_spins), 0, n - 1)
+        other_psi = np.where(spins[idx] == other_spins, unit[idx], 0.0)
+        rows, cols, vals, _ = oracle_capi.build_matrix(spins, np.ones(n, dtype=np.int64), unit, other_spins, other_coeffs, other_counts,
+                                                       other_psi, impl=impl)
+        raw = scipy.sparse.coo_matrix((vals, (rows.astype(np.int64), cols.astype(np.int64))), shape=(n, n)).tocsr()
+        sym = (0.5 * (raw + raw.T)).tocsr()  # common.py:194 (drops the couplings that cancel to zero)
+        sym.sort_indices()
+        assert np.array_equal(sym.indptr, live.indptr) and np.array_equal(sym.indices, live.indices)
+        np.testing.assert_allclose(sym.data, live.data, rtol=1e-12, atol=0)
+
+    check()
