@@ -1169,10 +1169,14 @@ int fused_prepare_gather_ce(const asp_operator *op, uint32_t world, uint32_t ran
   ASP_REQUIRE(world >= 1 && world <= static_cast<uint32_t>(kGxMaxRanks) && rank < world, "world size must be in 1..16");
   const uint64_t n_total = shard_begin[world];
   ASP_REQUIRE(shard_begin[0] == 0, "shard_begin[0] must be 0");
-  FusedWorkspace w = carve_fused(d_workspace, op, n_total, num_rows);
-  if (d_workspace == nullptr || workspace_bytes < w.bytes) {
-    set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
-    return ASP_ERR_WORKSPACE;
+  const bool index = op != nullptr;  // op == NULL: copies only (asp_gather_blocks), the caller indexes later
+  FusedWorkspace w{};
+  if (index) {
+    w = carve_fused(d_workspace, op, n_total, num_rows);
+    if (d_workspace == nullptr || workspace_bytes < w.bytes) {
+      set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+      return ASP_ERR_WORKSPACE;
+    }
   }
   int dev = 0;
   ASP_CUDA_CHECK(cudaGetDevice(&dev));
@@ -1183,7 +1187,7 @@ int fused_prepare_gather_ce(const asp_operator *op, uint32_t world, uint32_t ran
     for (auto &e : g_lane.block) ASP_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     g_lane.device = dev;
   }
-  ASP_CUDA_CHECK(cudaMemsetAsync(static_cast<char *>(d_workspace) + w.zero_offset, 0, w.zero_bytes, s));
+  if (index) ASP_CUDA_CHECK(cudaMemsetAsync(static_cast<char *>(d_workspace) + w.zero_offset, 0, w.zero_bytes, s));
   ASP_CUDA_CHECK(cudaEventRecord(g_lane.start, s));  // the copies may overwrite the full copy only after the caller's earlier work
   ASP_CUDA_CHECK(cudaStreamWaitEvent(g_lane.copy, g_lane.start, 0));
   SeamArgs seams{};
@@ -1202,14 +1206,17 @@ int fused_prepare_gather_ce(const asp_operator *op, uint32_t world, uint32_t ran
     ASP_CUDA_CHECK(cudaMemcpyAsync(d_psi + b0, d_shard_psi[q], len * sizeof(double), cudaMemcpyDeviceToDevice, g_lane.copy));
     ASP_CUDA_CHECK(cudaEventRecord(g_lane.block[k], g_lane.copy));
     ASP_CUDA_CHECK(cudaStreamWaitEvent(s, g_lane.block[k], 0));
+    if (!index) continue;
     index_block_kernel<<<static_cast<unsigned>((len + 511) / 512), 256, 0, s>>>(d_spins, static_cast<uint32_t>(n_total), static_cast<uint32_t>(b0),
                                                                                static_cast<uint32_t>(b0 + len), op->state_mask, w.tshift,
                                                                                w.num_buckets, w.starts, w.fshift, w.filter);
     ASP_LAUNCH_CHECK();
   }
-  index_seam_kernel<<<1, 32, 0, s>>>(d_spins, static_cast<uint32_t>(n_total), seams, static_cast<int>(world), op->state_mask, w.tshift,
-                                     w.num_buckets, w.starts);
-  ASP_LAUNCH_CHECK();
+  if (index) {
+    index_seam_kernel<<<1, 32, 0, s>>>(d_spins, static_cast<uint32_t>(n_total), seams, static_cast<int>(world), op->state_mask, w.tshift,
+                                       w.num_buckets, w.starts);
+    ASP_LAUNCH_CHECK();
+  }
   return ASP_OK;
 }
 
@@ -1394,6 +1401,16 @@ int asp_gather_index(asp_operator const *op, uint32_t world, uint32_t rank, uint
                                 d_workspace, workspace_bytes, static_cast<cudaStream_t>(stream), g_gather_mode == 2);
   return fused_prepare_gather_ce(op, world, rank, shard_begin, d_shard_spins, d_shard_psi, d_ready, epoch, d_spins, d_psi, num_rows,
                                  d_workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int asp_gather_blocks(uint32_t world, uint32_t rank, uint64_t const *shard_begin, uint64_t const *const *d_shard_spins,
+                      double const *const *d_shard_psi, uint64_t const *d_ready, uint64_t epoch, uint64_t *d_spins, double *d_psi,
+                      void *stream) {
+  ASP_REQUIRE(shard_begin && d_shard_spins && d_shard_psi, "NULL shard table");
+  ASP_REQUIRE(world >= 1 && world <= 16, "world size must be in 1..16");
+  ASP_REQUIRE(d_spins && d_psi, "NULL output buffer");
+  return fused_prepare_gather_ce(nullptr, world, rank, shard_begin, d_shard_spins, d_shard_psi, d_ready, epoch, d_spins, d_psi, 0, nullptr,
+                                 0, static_cast<cudaStream_t>(stream));
 }
 
 void asp_set_overlap_mode(int enable) { g_overlap = enable != 0; }

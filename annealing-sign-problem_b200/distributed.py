@@ -212,6 +212,26 @@ class PeerBasis:
                                      ptr(workspace, "void *"), workspace.numel(), stream()))
         return full_spins, full_psi
 
+    def gather_blocks(self, shard_begin, slot: int = 0):
+        """X1 by the copy engines alone (asp_gather_blocks): -> (full_spins, full_psi), not indexed.  Uses no SM, so
+        it overlaps completely with an extraction on another stream."""
+        from ._lib import check, ffi, lib, ptr, stream
+
+        begins = [int(b) for b in shard_begin]
+        assert len(begins) == self.world + 1 and begins[0] == 0
+        assert all(begins[q + 1] - begins[q] <= self.capacity for q in range(self.world))
+        n_total = begins[-1]
+        if self._full is None:
+            self._full = {}
+        if slot not in self._full or self._full[slot][0].shape[0] != n_total:
+            self._full[slot] = (torch.empty(n_total, dtype=torch.int64, device=self.device),
+                                torch.empty(n_total, dtype=torch.float64, device=self.device))
+        full_spins, full_psi = self._full[slot]
+        check(lib().asp_gather_blocks(self.world, self.rank, ffi.new("uint64_t[]", begins), self._shard_spins, self._shard_psi,
+                                      ffi.cast("uint64_t const *", self._own), self.epoch, ptr(full_spins, "uint64_t *"),
+                                      ptr(full_psi, "double *"), stream()))
+        return full_spins, full_psi
+
     def close(self):
         """Unmap the peers' blocks, then (after a host barrier: nobody may still map it) free ours."""
         from ._lib import ffi, lib

@@ -46,10 +46,11 @@ def parse_args():
     p.add_argument("--exchange", default="peer", choices=["peer", "peer-sm", "peer-ce", "nccl"],
                    help="X1 at N > 1: 'peer' = row blocks in NVLink peer memory, pulled by the copy engines and indexed block by "
                         "block behind them; 'peer-sm' = one SM kernel pulls + indexes; 'nccl' = two all-gathers + index pass (the baseline)")
-    p.add_argument("--pipeline", type=int, default=1, choices=[1, 2],
-                   help="N > 1 with a peer exchange: 1 (default) = a step is exchange, then extraction; 2 = EXPERIMENT, measured and "
-                        "rejected (DESIGN.md 5): the exchange of step k+1 on a second stream beside the extraction of step k (double "
-                        "private copies and workspaces) -- both kernels are issue-bound and slow each other down by more than the overlap gains")
+    p.add_argument("--pipeline", type=int, default=2, choices=[1, 2],
+                   help="N > 1 with a peer exchange: 2 (default) = steps are independent extractions (one per cluster in the "
+                        "reference's experiment): the copy engines gather the basis of step k+1 (asp_gather_blocks, no SM) while "
+                        "step k is indexed and extracted; 1 = strictly serial, X1 fused with the index build in one kernel "
+                        "(asp_gather_index)")
     p.add_argument("--skip-anneal", action="store_true")
     p.add_argument("--skip-cpu", action="store_true")
     p.add_argument("--skip-e2e", action="store_true")
@@ -324,14 +325,13 @@ def run_ours(args):
 
     pipelined = peer is not None and args.pipeline == 2
     if pipelined:
-        workspaces = [workspace, torch.empty_like(workspace)]
         s_exchange, s_compute = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
 
     def run_pipelined(count, timers=None):
-        """Two-deep software pipeline over `count` independent steps: [begin_epoch, publish, asp_gather_index, release] of
-        step k+1 on the exchange stream while asp_extract_csr_indexed of step k runs on the compute stream.  Private
-        copy + workspace `k % 2`; a slot is gathered into again only after the extraction that read it is done."""
-        lib().asp_set_overlap_mode(1)
+        """Two-deep software pipeline over `count` independent steps (in the reference's experiment: one extraction per
+        cluster).  Exchange stream: [begin_epoch, publish, asp_gather_blocks, release] of step k+1 -- the copy engines pull
+        the row blocks over NVLink, no SM involved -- while the compute stream runs asp_extract_csr (index + extraction) of
+        step k.  Two private copies of the basis; a copy is gathered into again only after the extraction that read it."""
         gathered = [torch.cuda.Event() for _ in range(2)]
         extracted = [None, None]
         fulls = [None, None]
@@ -348,7 +348,7 @@ def run_ours(args):
                 peer.publish()
                 if ex:
                     ex[0].record()
-                fulls[k % 2] = peer.gather_index(op, bounds, num_rows, workspaces[k % 2], slot=k % 2)
+                fulls[k % 2] = peer.gather_blocks(bounds, slot=k % 2)
                 if ex:
                     ex[1].record()
                     exchange.append(ex)
@@ -359,7 +359,7 @@ def run_ours(args):
         exchange_step(0)
         for k in range(count):
             if k + 1 < count:
-                exchange_step(k + 1)  # queued FIRST: its flag kernels must not wait behind the extraction
+                exchange_step(k + 1)  # queued first: its flag kernels must not wait behind the extraction
             with torch.cuda.stream(s_compute):
                 s_compute.wait_event(gathered[k % 2])
                 ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)] if timers is not None else None
@@ -369,10 +369,10 @@ def run_ours(args):
                 if ev:
                     ev[0].record()
                 full_spins, full_psi = fulls[k % 2]
-                common.check(lib().asp_extract_csr_indexed(op.handle, n_total, common.ptr(full_spins, "uint64_t *"), common.ptr(full_psi, "double *"),
-                                                           row_begin, num_rows, common.ptr(workspaces[k % 2], "void *"), workspaces[k % 2].numel(),
-                                                           capacity, common.ptr(indptr, "int64_t *"), common.ptr(indices, "int32_t *"),
-                                                           common.ptr(data, "double *"), ffi.NULL, common.stream()))
+                common.check(lib().asp_extract_csr(op.handle, n_total, common.ptr(full_spins, "uint64_t *"), common.ptr(full_psi, "double *"),
+                                                   row_begin, num_rows, common.ptr(workspace, "void *"), workspace.numel(), capacity,
+                                                   common.ptr(indptr, "int64_t *"), common.ptr(indices, "int32_t *"),
+                                                   common.ptr(data, "double *"), ffi.NULL, common.stream()))
                 if ev:
                     ev[1].record()
                     timers.append(ev)
@@ -381,7 +381,6 @@ def run_ours(args):
                 out = (indptr, indices, data)
         here.wait_stream(s_compute)
         here.wait_stream(s_exchange)
-        lib().asp_set_overlap_mode(0)
         return out
 
     for _ in range(args.warmup):
@@ -585,8 +584,8 @@ def run_ours(args):
                                    "cluster-closed subset, Ising extraction to CSR" % args.states,
                        "states_total": n_total, "rows_per_gpu": num_rows, "couplings_total": int(nnz_total),
                        "candidates_per_row": 37.0, "parallelism": "row blocks x%d, basis exchanged every step (%s)%s" % (
-                           world, exchange_used, "; steps pipelined two deep: the exchange of step k+1 overlaps the extraction of step k "
-                           "(independent extractions, double buffers)" if pipelined else ""),
+                           world, exchange_used, "; steps pipelined two deep: the copy engines gather the basis of step k+1 over NVLink while "
+                           "step k is indexed and extracted (independent extractions, two private copies)" if pipelined else ""),
                        "l2": "inputs (%.0f MB) larger than L2" % ((n_total * 16 + need) / 1e6)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "anneal": anneal,
         }

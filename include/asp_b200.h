@@ -288,6 +288,15 @@ int asp_gather_index(asp_operator const *op, uint32_t world, uint32_t rank,
                      double const *const *d_shard_psi, uint64_t const *d_ready, uint64_t epoch,
                      uint64_t *d_spins, double *d_psi, uint64_t num_rows, void *d_workspace,
                      size_t workspace_bytes, void *stream);
+/* X1 without the index: the copy engines pull every block into the private full copy (flags and
+ * arguments as for asp_gather_index).  No SM is used, so the call overlaps completely with an
+ * extraction running on another stream: a pipeline over independent extractions gathers basis
+ * k+1 this way while basis k is extracted, then runs the ordinary asp_extract_csr (which
+ * indexes) on it. */
+int asp_gather_blocks(uint32_t world, uint32_t rank, uint64_t const *shard_begin,
+                      uint64_t const *const *d_shard_spins, double const *const *d_shard_psi,
+                      uint64_t const *d_ready, uint64_t epoch, uint64_t *d_spins, double *d_psi,
+                      void *stream);
 /* The sharded end-to-end path: asp_gather_index on `stream`, then this call -- the single-pass
  * extraction of rows [row_begin, row_begin+num_rows) in row chunks on the indexed workspace, every
  * chunk's rows copied to the caller's HOST buffers (pinned: asynchronously) while the next chunk is

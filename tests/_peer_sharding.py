@@ -61,6 +61,20 @@ def main():
         out = common.extract_csr_indexed_device(op, got_s, got_p, begin, rows, workspace, capacity=int(ref[1].numel()))
         for a, b in zip(out, ref):
             assert torch.equal(a, b), "epoch %d rank %d: CSR differs" % (epoch, rank)
+        # copy-engine gather without index (asp_gather_blocks) + the ordinary extraction: what a pipeline over
+        # independent extractions runs on its exchange stream / compute stream
+        pb.begin_epoch()
+        pb.publish()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            cp_s, cp_p = pb.gather_blocks(bounds, slot=1)
+            pb.release()
+        torch.cuda.current_stream().wait_stream(side)
+        assert torch.equal(cp_s, spins) and torch.equal(cp_p, psi), "epoch %d rank %d: gather_blocks differs" % (epoch, rank)
+        out = common.extract_csr_device(op, cp_s, cp_p, begin, rows)
+        for a, b in zip(out, ref):
+            assert torch.equal(a, b), "epoch %d rank %d: CSR after gather_blocks differs" % (epoch, rank)
     pb.close()
     D.barrier()
     if rank == 0:
