@@ -484,6 +484,94 @@ __global__ void __launch_bounds__(kTxThreads, 6) gather_index_tma_kernel(const G
   }
 }
 
+// ---- X1, copy only, on the TMA: ONE thread per CTA moves chunks peer global -> shared -> private copy with bulk
+// copies in both directions (no register, no LSU instruction per byte).  32-thread CTAs with 64 KB of shared memory
+// fit beside a resident extraction kernel, so this is what gathers the NEXT basis while the current one is extracted.
+constexpr int kCxStages = 3;  // 48 KB: fits beside six resident extraction CTAs
+constexpr size_t kCxSmem = static_cast<size_t>(kCxStages) * kTxChunk * 16 + 64;
+
+__device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(32) gather_copy_tma_kernel(const GatherArgs a) {
+  extern __shared__ __align__(128) unsigned char cx_smem[];
+  const bool leader = threadIdx.x == 0;
+  const uint32_t smem0 = smem_addr(cx_smem);
+  const uint32_t bars = smem0 + kCxStages * kTxChunk * 16;
+  const uint64_t total = a.chunk_begin[a.world];
+  if (leader) {
+    for (int st = 0; st < kCxStages; ++st) mbar_init(bars + 8 * st, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t waited = 0;
+  auto locate = [&](uint64_t c, int &q, uint64_t &l0, uint32_t &cnt) {
+    int k = 0;
+    while (c >= a.chunk_begin[k + 1]) ++k;
+    q = a.order[k];
+    l0 = (c - a.chunk_begin[k]) * kTxChunk;
+    const uint64_t len = a.begin[q + 1] - a.begin[q];
+    cnt = static_cast<uint32_t>(min(static_cast<uint64_t>(kTxChunk), len - l0));
+  };
+  auto load = [&](uint64_t it) {  // leader only
+    const uint64_t c = blockIdx.x + it * gridDim.x;
+    if (c >= total) return;
+    int q;
+    uint64_t l0;
+    uint32_t cnt;
+    locate(c, q, l0, cnt);
+    if (a.ready != nullptr && !((waited >> q) & 1u)) {
+      wait_flag_or_trap(a.ready + q, a.epoch);
+      asm volatile("fence.proxy.async;" ::: "memory");
+      waited |= 1u << q;
+    }
+    const uint32_t st = static_cast<uint32_t>(it % kCxStages), even = cnt & ~1u;
+    mbar_arrive_expect_tx(bars + 8 * st, even * 16u);
+    if (even) {
+      bulk_g2s(smem0 + st * (kTxChunk * 16), a.shard_spins[q] + l0, even * 8u, bars + 8 * st);
+      bulk_g2s(smem0 + st * (kTxChunk * 16) + kTxChunk * 8, a.shard_psi[q] + l0, even * 8u, bars + 8 * st);
+    }
+  };
+  if (leader)
+    for (int it = 0; it < kCxStages; ++it) load(it);
+  for (uint64_t it = 0;; ++it) {
+    const uint64_t c = blockIdx.x + it * gridDim.x;
+    if (c >= total) break;
+    const uint32_t st = static_cast<uint32_t>(it % kCxStages);
+    int q;
+    uint64_t l0;
+    uint32_t cnt;
+    locate(c, q, l0, cnt);
+    mbar_wait(bars + 8 * st, static_cast<uint32_t>(it / kCxStages) & 1u);
+    const uint64_t g = a.begin[q] + l0;
+    const uint32_t even = cnt & ~1u;
+    if ((g & 1ull) == 0) {  // bulk stores need 16-byte aligned destinations
+      if (leader && even) {
+        bulk_s2g(a.spins + g, smem0 + st * (kTxChunk * 16), even * 8u);
+        bulk_s2g(a.psi + g, smem0 + st * (kTxChunk * 16) + kTxChunk * 8, even * 8u);
+      }
+    } else {  // a block that starts at an odd global position: the warp stores the chunk with plain 8-byte stores
+      const unsigned long long *sk = reinterpret_cast<const unsigned long long *>(cx_smem + st * (kTxChunk * 16));
+      for (uint32_t e = threadIdx.x; e < even; e += 32) {
+        a.spins[g + e] = sk[e];
+        reinterpret_cast<unsigned long long *>(a.psi)[g + e] = sk[kTxChunk + e];
+      }
+    }
+    if (leader) {
+      if (cnt & 1u) {  // odd tail of the block: not part of the bulk copy
+        a.spins[g + even] = ld_peer_u64(a.shard_spins[q] + l0 + even);
+        reinterpret_cast<unsigned long long *>(a.psi)[g + even] = ld_peer_u64(a.shard_psi[q] + l0 + even);
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the stores have read the stage
+    }
+    __syncwarp();  // ... and so have the lanes of the plain-store path: refill it
+    if (leader) load(it + kCxStages);
+  }
+  if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // every store has landed before the kernel ends
+}
+
 // ---- X1, copy-engine variant: the blocks are pulled by cudaMemcpyAsync (the copy engines move 700 GB/s over
 // NVLink, more than SM loads reach) and indexed block by block on the SMs while later blocks still travel.
 // A thread indexes two consecutive keys of the block [b0, b1); the block's first key owes its table entries
@@ -1094,10 +1182,14 @@ int fused_prepare_gather(const asp_operator *op, uint32_t world, uint32_t rank, 
   ASP_REQUIRE(world >= 1 && world <= static_cast<uint32_t>(kGxMaxRanks) && rank < world, "world size must be in 1..16");
   const uint64_t n_total = shard_begin[world];
   ASP_REQUIRE(shard_begin[0] == 0, "shard_begin[0] must be 0");
-  FusedWorkspace w = carve_fused(d_workspace, op, n_total, num_rows);
-  if (d_workspace == nullptr || workspace_bytes < w.bytes) {
-    set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
-    return ASP_ERR_WORKSPACE;
+  const bool copy_only = op == nullptr;  // asp_gather_blocks: gather_copy_tma_kernel, no index
+  FusedWorkspace w{};
+  if (!copy_only) {
+    w = carve_fused(d_workspace, op, n_total, num_rows);
+    if (d_workspace == nullptr || workspace_bytes < w.bytes) {
+      set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+      return ASP_ERR_WORKSPACE;
+    }
   }
   GatherArgs a{};
   a.world = static_cast<int>(world);
@@ -1130,6 +1222,13 @@ int fused_prepare_gather(const asp_operator *op, uint32_t world, uint32_t rank, 
   a.spins = d_spins;
   a.psi = d_psi;
   a.n = static_cast<uint32_t>(n_total);
+  if (copy_only) {
+    ASP_CUDA_CHECK(cudaFuncSetAttribute(gather_copy_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCxSmem)));
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(chunks, static_cast<uint64_t>(kNumSMs)));
+    gather_copy_tma_kernel<<<grid, 32, kCxSmem, s>>>(a);
+    ASP_LAUNCH_CHECK();
+    return ASP_OK;
+  }
   a.state_mask = op->state_mask;
   a.num_buckets = w.num_buckets;
   a.tshift = w.tshift;
@@ -1409,6 +1508,9 @@ int asp_gather_blocks(uint32_t world, uint32_t rank, uint64_t const *shard_begin
   ASP_REQUIRE(shard_begin && d_shard_spins && d_shard_psi, "NULL shard table");
   ASP_REQUIRE(world >= 1 && world <= 16, "world size must be in 1..16");
   ASP_REQUIRE(d_spins && d_psi, "NULL output buffer");
+  if (g_gather_mode != 0)  // one thread per CTA drives bulk copies in both directions (fits beside a resident extraction)
+    return fused_prepare_gather(nullptr, world, rank, shard_begin, d_shard_spins, d_shard_psi, d_ready, epoch, d_spins, d_psi, 0, nullptr, 0,
+                                static_cast<cudaStream_t>(stream), true);
   return fused_prepare_gather_ce(nullptr, world, rank, shard_begin, d_shard_spins, d_shard_psi, d_ready, epoch, d_spins, d_psi, 0, nullptr,
                                  0, static_cast<cudaStream_t>(stream));
 }

@@ -212,9 +212,11 @@ class PeerBasis:
                                      ptr(workspace, "void *"), workspace.numel(), stream()))
         return full_spins, full_psi
 
-    def gather_blocks(self, shard_begin, slot: int = 0):
-        """X1 by the copy engines alone (asp_gather_blocks): -> (full_spins, full_psi), not indexed.  Uses no SM, so
-        it overlaps completely with an extraction on another stream."""
+    def gather_blocks(self, shard_begin, slot: int = 0, engine: str = "ce"):
+        """X1 without the index (asp_gather_blocks): -> (full_spins, full_psi).  engine "ce" (default): the copy
+        engines pull the blocks -- no SM involved, so it overlaps completely with an extraction on another stream;
+        "tma": one thread per CTA drives bulk copies (faster alone, but measured to slow a concurrent extraction
+        down by more than it gains)."""
         from ._lib import check, ffi, lib, ptr, stream
 
         begins = [int(b) for b in shard_begin]
@@ -227,6 +229,7 @@ class PeerBasis:
             self._full[slot] = (torch.empty(n_total, dtype=torch.int64, device=self.device),
                                 torch.empty(n_total, dtype=torch.float64, device=self.device))
         full_spins, full_psi = self._full[slot]
+        lib().asp_set_gather_mode(0 if engine == "ce" else 2)
         check(lib().asp_gather_blocks(self.world, self.rank, ffi.new("uint64_t[]", begins), self._shard_spins, self._shard_psi,
                                       ffi.cast("uint64_t const *", self._own), self.epoch, ptr(full_spins, "uint64_t *"),
                                       ptr(full_psi, "double *"), stream()))

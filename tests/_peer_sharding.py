@@ -68,7 +68,7 @@ def main():
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            cp_s, cp_p = pb.gather_blocks(bounds, slot=1)
+            cp_s, cp_p = pb.gather_blocks(bounds, slot=1, engine="ce" if epoch % 2 else "tma")
             pb.release()
         torch.cuda.current_stream().wait_stream(side)
         assert torch.equal(cp_s, spins) and torch.equal(cp_p, psi), "epoch %d rank %d: gather_blocks differs" % (epoch, rank)

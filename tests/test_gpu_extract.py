@@ -226,6 +226,16 @@ def test_gather_index_kernel_over_emulated_shards_equals_the_unsharded_build():
         world = len(bounds) - 1
         parts_s = [spins[bounds[q]:bounds[q + 1]].clone() if bounds[q + 1] > bounds[q] else torch.zeros(2, dtype=torch.int64, device=DEV) for q in range(world)]
         parts_p = [psi[bounds[q]:bounds[q + 1]].clone() if bounds[q + 1] > bounds[q] else torch.zeros(2, dtype=torch.float64, device=DEV) for q in range(world)]
+        for rank, mode in [(0, 0), (world - 1, 2)]:  # copy only (asp_gather_blocks): copy engines / one TMA thread per CTA
+            lib().asp_set_gather_mode(mode)
+            full_s = torch.zeros(n, dtype=torch.int64, device=DEV)
+            full_p = torch.zeros(n, dtype=torch.float64, device=DEV)
+            common.check(lib().asp_gather_blocks(
+                world, rank, ffi.new("uint64_t[]", bounds),
+                ffi.new("uint64_t const *[]", [common.ptr(t, "uint64_t const *") for t in parts_s]),
+                ffi.new("double const *[]", [common.ptr(t, "double const *") for t in parts_p]),
+                ffi.NULL, 0, common.ptr(full_s, "uint64_t *"), common.ptr(full_p, "double *"), common.stream()))
+            assert torch.equal(full_s, spins) and torch.equal(full_p, psi), (bounds, rank, mode)
         for rank, mode in [(0, 0), (0, 2), (world - 1, 1), (world - 1, 2), (world // 2, 0), (world // 2, 1), (world // 2, 2)]:
             lib().asp_set_gather_mode(mode)  # 0 = copy engines + per-block index kernels, 1 = one SM kernel, 2 = one TMA kernel
             row_begin, num_rows = bounds[rank], bounds[rank + 1] - bounds[rank]
