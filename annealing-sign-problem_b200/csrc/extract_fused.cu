@@ -1100,7 +1100,6 @@ constexpr int kEvRing = 64;  // the last kEvRing launches keep their event pair
 static cudaEvent_t g_ev_begin[kEvRing] = {}, g_ev_end[kEvRing] = {};
 static uint64_t g_ev_launches = 0;
 static int g_filter_bits_delta = 0, g_table_bits_delta = 0, g_stage_a_mode = 0;
-static int g_overlap = 0;      // asp_set_overlap_mode: leave room on every SM for the other kernel of a two-deep pipeline
 static int g_gather_mode = 2;  // asp_gather_index: 2 = one TMA kernel (default), 1 = one kernel with plain loads, 0 = copy engines + per-block index kernels
 
 static FusedWorkspace carve_fused(void *base, const asp_operator *op, uint64_t n_total, uint64_t num_rows) {
@@ -1237,11 +1236,10 @@ int fused_prepare_gather(const asp_operator *op, uint32_t world, uint32_t rank, 
   a.filter = w.filter;
   ASP_CUDA_CHECK(cudaMemsetAsync(static_cast<char *>(d_workspace) + w.zero_offset, 0, w.zero_bytes, s));
   if (tma) {
-    // alone: 2 CTAs per SM; beside an extraction (overlap mode): 1 CTA per SM next to the extraction's 5
     a.stages = kTxStages;
     const size_t smem = kTxSmem;
     ASP_CUDA_CHECK(cudaFuncSetAttribute(gather_index_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTxSmem)));
-    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(chunks, static_cast<uint64_t>(kNumSMs) * (g_overlap ? 1 : kTxCtasPerSM)));
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(chunks, static_cast<uint64_t>(kNumSMs) * kTxCtasPerSM));
     gather_index_tma_kernel<<<grid, kTxThreads, smem, s>>>(a);
   } else {
     const uint64_t per_cta = static_cast<uint64_t>(kGxThreads) * kGxUnroll;
@@ -1378,8 +1376,7 @@ int fused_launch(const asp_operator *op, uint64_t n_total, const uint64_t *d_spi
   int per_sm = 0;
   ASP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, extract_csr_kernel, kFxThreads, smem));
   ASP_REQUIRE(per_sm >= 1, "fused extraction kernel does not fit on an SM");
-  // overlap mode: one CTA slot less per SM, so that a gather_index_tma_kernel CTA (64 KB, 256 threads, 40 registers) fits beside the extraction
-  const uint64_t resident = static_cast<uint64_t>(kNumSMs) * std::max(1, std::min(per_sm, kFxMaxCtasPerSM) - (g_overlap ? 1 : 0));
+  const uint64_t resident = static_cast<uint64_t>(kNumSMs) * std::min(per_sm, kFxMaxCtasPerSM);
   const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(std::min<uint64_t>(a.num_tiles, resident), w.scratch_ctas));
   const int ev_slot = static_cast<int>(g_ev_launches % kEvRing);
   if (g_time_kernel) {
@@ -1514,8 +1511,6 @@ int asp_gather_blocks(uint32_t world, uint32_t rank, uint64_t const *shard_begin
   return fused_prepare_gather_ce(nullptr, world, rank, shard_begin, d_shard_spins, d_shard_psi, d_ready, epoch, d_spins, d_psi, 0, nullptr,
                                  0, static_cast<cudaStream_t>(stream));
 }
-
-void asp_set_overlap_mode(int enable) { g_overlap = enable != 0; }
 
 void asp_set_gather_mode(int mode) { g_gather_mode = (mode == 0 || mode == 1) ? mode : 2; }
 

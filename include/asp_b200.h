@@ -288,11 +288,13 @@ int asp_gather_index(asp_operator const *op, uint32_t world, uint32_t rank,
                      double const *const *d_shard_psi, uint64_t const *d_ready, uint64_t epoch,
                      uint64_t *d_spins, double *d_psi, uint64_t num_rows, void *d_workspace,
                      size_t workspace_bytes, void *stream);
-/* X1 without the index: the copy engines pull every block into the private full copy (flags and
- * arguments as for asp_gather_index).  No SM is used, so the call overlaps completely with an
- * extraction running on another stream: a pipeline over independent extractions gathers basis
- * k+1 this way while basis k is extracted, then runs the ordinary asp_extract_csr (which
- * indexes) on it. */
+/* X1 without the index (flags and arguments as for asp_gather_index).  Gather mode 0: the copy
+ * engines pull every block into the private full copy -- no SM is used, so the call overlaps
+ * completely with an extraction running on another stream: a pipeline over independent
+ * extractions (one per cluster in the reference's experiment) gathers basis k+1 this way while
+ * basis k is indexed and extracted by the ordinary asp_extract_csr.  Gather mode 1/2: one thread per
+ * CTA drives bulk copies peer -> shared -> private copy (cp.async.bulk both ways); faster alone,
+ * but beside a resident extraction it costs more than it gains. */
 int asp_gather_blocks(uint32_t world, uint32_t rank, uint64_t const *shard_begin,
                       uint64_t const *const *d_shard_spins, double const *const *d_shard_psi,
                       uint64_t const *d_ready, uint64_t epoch, uint64_t *d_spins, double *d_psi,
@@ -314,12 +316,6 @@ int asp_extract_indexed_to_host(asp_operator const *op, uint64_t n_total, uint64
  * blocks (cudaMemcpyAsync on an internal stream) and every block is indexed on the SMs as soon as
  * it has landed. */
 void asp_set_gather_mode(int mode);
-/* Experiment, measured and not adopted: asp_gather_index of the NEXT basis on one
- * stream beside asp_extract_csr_indexed of the current one on another (separate private copies and
- * workspaces).  Both kernels are persistent, so neither would find room beside the other: with
- * overlap mode on, the extraction leaves one CTA slot per SM free and the gather kernel takes
- * exactly one. */
-void asp_set_overlap_mode(int enable);
 /* asp_extract_csr without its zero + index pass: the workspace was prepared by asp_gather_index
  * for the same (op, n_total, num_rows) on the same stream. */
 int asp_extract_csr_indexed(asp_operator const *op, uint64_t n_total, uint64_t const *d_spins,
