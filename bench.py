@@ -9,9 +9,13 @@ heisenberg_kagome_36-shaped U(1) basis (36 spins, 72 bonds), 10^7 sampled states
 (weak scaling: the global sorted basis has N x 10^7 states and every rank builds the CSR
 rows of its contiguous row block against the full basis), synthetic log-normal amplitudes,
 cluster-closed sampled subset (about a tenth of all candidates are hits).  A step is one
-pass: [N>1: all-gather of basis words + amplitudes] -> index (first-position table + Bloom
-filter) -> single-pass extraction kernel (bit-plane applicability, filter pre-sieve, exact search
-of the survivors, decoupled look-back, CSR written in place).
+pass: [N>1: exchange X1 of basis words + amplitudes over NVLink peer memory] -> index
+(first-position table + Bloom filter) -> single-pass extraction kernel (bit-plane applicability,
+filter pre-sieve, exact search of the survivors, decoupled look-back, CSR written in place).
+At N > 1 the steps are pipelined two deep by default (--pipeline 2): they are independent
+extractions (one per cluster in the reference's experiment), so the copy engines gather the basis
+of step k+1 while step k is indexed and extracted; --pipeline 1 runs exchange and extraction
+strictly one after the other with X1 fused into the index kernel (asp_gather_index).
 The annealing stage is timed separately on the same extracted model and reported under the
 "anneal" key.  One JSON line on stdout (rank 0).
 """
