@@ -3,7 +3,7 @@
 // The reference is single-process; its "exchange" is that every caller holds the whole basis
 // (annealing_sign_problem/common.py:146).  Sharded over GPUs, every rank must see all row blocks
 // of the sorted basis.  Instead of an NCCL all-gather followed by an index pass, the blocks stay in
-// peer-mapped buffers and ONE kernel (gather_index_kernel, extract_fused.cu) pulls them over
+// peer-mapped buffers and ONE kernel (gather_index_tma_kernel, exchange_kernels.cuh) pulls them over
 // NVLink while it indexes them.  This file holds the plumbing:
 //
 //   asp_peer_alloc / asp_peer_open / asp_peer_close / asp_peer_free

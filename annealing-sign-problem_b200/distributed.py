@@ -12,7 +12,7 @@ bit-identical to the single-GPU one (KAT-7).
 
 X1 has two implementations: ``all_gather_blocks`` (NCCL; gloo in CPU tests) and ``PeerBasis``
 (the row blocks stay in NVLink peer memory and ONE kernel pulls + indexes them:
-asp_gather_index, csrc/extract_fused.cu -- the fast path on a B200 node).
+asp_gather_index, csrc/exchange_kernels.cuh -- the fast path on a B200 node).
 """
 from __future__ import annotations
 
