@@ -814,8 +814,8 @@ int fused_prepare_gather(const asp_operator *op, uint32_t world, uint32_t rank, 
 // cudaMemcpyAsync keys + amplitudes into the private full copy] on a copy stream; on the caller's stream
 // the block is indexed as soon as its copies are done, while the next blocks travel.
 struct CopyLane {
-  cudaStream_t copy = nullptr;
-  cudaEvent_t start = nullptr, block[kGxMaxRanks] = {};
+  cudaStream_t copy = nullptr, copy2 = nullptr;  // keys on one copy engine, amplitudes on another
+  cudaEvent_t start = nullptr, flag = nullptr, block[kGxMaxRanks] = {}, block2[kGxMaxRanks] = {};
   int device = -1;
 };
 static CopyLane g_lane;
@@ -841,13 +841,17 @@ int fused_prepare_gather_ce(const asp_operator *op, uint32_t world, uint32_t ran
   if (g_lane.device != dev) {
     ASP_REQUIRE(g_lane.device < 0, "one device per process");
     ASP_CUDA_CHECK(cudaStreamCreateWithFlags(&g_lane.copy, cudaStreamNonBlocking));
+    ASP_CUDA_CHECK(cudaStreamCreateWithFlags(&g_lane.copy2, cudaStreamNonBlocking));
     ASP_CUDA_CHECK(cudaEventCreateWithFlags(&g_lane.start, cudaEventDisableTiming));
+    ASP_CUDA_CHECK(cudaEventCreateWithFlags(&g_lane.flag, cudaEventDisableTiming));
     for (auto &e : g_lane.block) ASP_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &e : g_lane.block2) ASP_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     g_lane.device = dev;
   }
   if (index) ASP_CUDA_CHECK(cudaMemsetAsync(static_cast<char *>(d_workspace) + w.zero_offset, 0, w.zero_bytes, s));
   ASP_CUDA_CHECK(cudaEventRecord(g_lane.start, s));  // the copies may overwrite the full copy only after the caller's earlier work
   ASP_CUDA_CHECK(cudaStreamWaitEvent(g_lane.copy, g_lane.start, 0));
+  ASP_CUDA_CHECK(cudaStreamWaitEvent(g_lane.copy2, g_lane.start, 0));
   SeamArgs seams{};
   for (uint32_t k = 0; k < world; ++k) {
     const uint32_t q = (rank + k) % world;  // own block first (no flag to wait for), then ring order
@@ -859,17 +863,24 @@ int fused_prepare_gather_ce(const asp_operator *op, uint32_t world, uint32_t ran
     if (d_ready != nullptr && q != rank) {
       wait_one_flag_kernel<<<1, 1, 0, g_lane.copy>>>(reinterpret_cast<const unsigned long long *>(d_ready) + q, epoch);
       ASP_LAUNCH_CHECK();
+      ASP_CUDA_CHECK(cudaEventRecord(g_lane.flag, g_lane.copy));  // the second engine starts on the same flag
+      ASP_CUDA_CHECK(cudaStreamWaitEvent(g_lane.copy2, g_lane.flag, 0));
     }
     ASP_CUDA_CHECK(cudaMemcpyAsync(d_spins + b0, d_shard_spins[q], len * sizeof(uint64_t), cudaMemcpyDeviceToDevice, g_lane.copy));
-    ASP_CUDA_CHECK(cudaMemcpyAsync(d_psi + b0, d_shard_psi[q], len * sizeof(double), cudaMemcpyDeviceToDevice, g_lane.copy));
-    ASP_CUDA_CHECK(cudaEventRecord(g_lane.block[k], g_lane.copy));
-    ASP_CUDA_CHECK(cudaStreamWaitEvent(s, g_lane.block[k], 0));
+    ASP_CUDA_CHECK(cudaMemcpyAsync(d_psi + b0, d_shard_psi[q], len * sizeof(double), cudaMemcpyDeviceToDevice, g_lane.copy2));
     if (!index) continue;
+    ASP_CUDA_CHECK(cudaEventRecord(g_lane.block[k], g_lane.copy));
+    ASP_CUDA_CHECK(cudaStreamWaitEvent(s, g_lane.block[k], 0));  // the keys of this block have landed: index them
     index_block_kernel<<<static_cast<unsigned>((len + 511) / 512), 256, 0, s>>>(d_spins, static_cast<uint32_t>(n_total), static_cast<uint32_t>(b0),
                                                                                static_cast<uint32_t>(b0 + len), op->state_mask, w.tshift,
                                                                                w.num_buckets, w.starts, w.fshift, w.filter);
     ASP_LAUNCH_CHECK();
   }
+  // everything (amplitudes included) has landed before the caller's stream goes on
+  ASP_CUDA_CHECK(cudaEventRecord(g_lane.block2[0], g_lane.copy));
+  ASP_CUDA_CHECK(cudaEventRecord(g_lane.block2[1], g_lane.copy2));
+  ASP_CUDA_CHECK(cudaStreamWaitEvent(s, g_lane.block2[0], 0));
+  ASP_CUDA_CHECK(cudaStreamWaitEvent(s, g_lane.block2[1], 0));
   if (index) {
     index_seam_kernel<<<1, 32, 0, s>>>(d_spins, static_cast<uint32_t>(n_total), seams, static_cast<int>(world), op->state_mask, w.tshift,
                                        w.num_buckets, w.starts);
