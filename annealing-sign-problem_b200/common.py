@@ -184,13 +184,15 @@ def extract_indexed_to_host(operator: ls.Operator, spins: torch.Tensor, psi: tor
     asp_gather_index, CSR rows written to the caller's (pinned) HOST tensors chunk by chunk while the next
     chunk is extracted.  -> number of couplings."""
     require_cuda()
-    assert h_indptr.dtype == torch.int64 and h_indices.dtype == torch.int32 and h_data.dtype == torch.float64
+    assert h_indptr.dtype in (torch.int64, torch.int32) and h_indices.dtype == torch.int32 and h_data.dtype == torch.float64
     assert h_indptr.numel() >= num_rows + 1 and h_indices.numel() == h_data.numel()
     nnz = ffi.new("uint64_t *")
-    check(lib().asp_extract_indexed_to_host(operator.handle, int(spins.shape[0]), ptr(spins, "uint64_t *"), ptr(psi, "double *"),
-                                            row_begin, num_rows, ptr(workspace, "void *"), workspace.numel(), h_indices.numel(),
-                                            ffi.cast("int64_t *", h_indptr.data_ptr()), ffi.cast("int32_t *", h_indices.data_ptr()),
-                                            ffi.cast("double *", h_data.data_ptr()), nnz, stream()))
+    narrow = h_indptr.dtype == torch.int32  # scipy's own index type below 2^31 couplings
+    call = lib().asp_extract_indexed_to_host_i32 if narrow else lib().asp_extract_indexed_to_host
+    check(call(operator.handle, int(spins.shape[0]), ptr(spins, "uint64_t *"), ptr(psi, "double *"),
+               row_begin, num_rows, ptr(workspace, "void *"), workspace.numel(), h_indices.numel(),
+               ffi.cast("int32_t *" if narrow else "int64_t *", h_indptr.data_ptr()), ffi.cast("int32_t *", h_indices.data_ptr()),
+               ffi.cast("double *", h_data.data_ptr()), nnz, stream()))
     return int(nnz[0])
 
 

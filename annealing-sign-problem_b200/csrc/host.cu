@@ -29,7 +29,7 @@ struct Arena {
   struct Buf {
     void *p = nullptr;
     size_t cap = 0;
-  } spins, psi, workspace, indptr, indices, data;
+  } spins, psi, workspace, indptr, indptr32, indices, data;
 
   int reserve(Buf &b, size_t bytes, bool headroom = true) {
     if (bytes <= b.cap) return ASP_OK;
@@ -55,7 +55,7 @@ struct Arena {
     return ASP_OK;
   }
   void release() {
-    for (Buf *b : {&spins, &psi, &workspace, &indptr, &indices, &data}) {
+    for (Buf *b : {&spins, &psi, &workspace, &indptr, &indptr32, &indices, &data}) {
       if (b->p) cudaFree(b->p);
       b->p = nullptr;
       b->cap = 0;
@@ -112,17 +112,37 @@ void release_busy(Arena &A) {
 // The chunked extraction + drain shared by the host entry points: chunk c+1 is extracted while chunk c's
 // rows travel back over PCIe.  The workspace is already zeroed and indexed; d_indptr/d_indices/d_data are
 // the arena's output buffers.
+// int64 -> int32 row starts (the index type scipy itself picks for nnz < 2^31, and what the reference's model dump
+// stores: common.py:762-763): halves the indptr bytes that cross PCIe.
+__global__ void narrow_indptr_kernel(const int64_t *__restrict__ in, int32_t *__restrict__ out, uint64_t count) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i < count) out[i] = static_cast<int32_t>(in[i]);
+}
+
 static int extract_chunks_to_host(Arena &A, asp_operator const *op, uint64_t n, const uint64_t *d_spins, const double *d_psi,
                                   uint64_t row_begin, uint64_t num_rows, uint64_t chunk_rows, int chunks, void *d_workspace,
                                   uint64_t dev_capacity, uint64_t capacity, int64_t *d_indptr, int32_t *d_indices, double *d_data,
-                                  unsigned long long *d_totals, int64_t *h_indptr, int32_t *h_indices, double *h_data, uint64_t *h_nnz) {
+                                  unsigned long long *d_totals, void *h_indptr_any, bool narrow, int32_t *h_indices, double *h_data,
+                                  uint64_t *h_nnz) {
   int rc = ASP_OK;
+  int64_t *const h_indptr = narrow ? nullptr : static_cast<int64_t *>(h_indptr_any);
+  int32_t *const h_indptr32 = narrow ? static_cast<int32_t *>(h_indptr_any) : nullptr;
+  int32_t *d_indptr32 = nullptr;
+  if (narrow) {
+    rc = A.reserve(A.indptr32, (num_rows + 1) * sizeof(int32_t));
+    if (rc != ASP_OK) return rc;
+    d_indptr32 = static_cast<int32_t *>(A.indptr32.p);
+  }
   {
     for (int c = 0; c < chunks; ++c) {
       const uint64_t begin = c * chunk_rows, rows = std::min(chunk_rows, num_rows - begin);
       rc = asp::fused_launch(op, n, d_spins, d_psi, row_begin, num_rows, c, begin, rows, d_workspace, dev_capacity, d_indptr,
                              d_indices, d_data, d_totals + c, A.compute);
       if (rc != ASP_OK) goto out;
+      if (narrow) {
+        narrow_indptr_kernel<<<static_cast<unsigned>((rows + 1 + 255) / 256), 256, 0, A.compute>>>(d_indptr + begin, d_indptr32 + begin, rows + 1);
+        asp::g_launches.fetch_add(1, std::memory_order_relaxed);
+      }
       HOST_CUDA(cudaEventRecord(A.ev_chunk[c], A.compute));
     }
     // drain: as soon as a chunk is done its rows go back while the next chunk is extracted
@@ -133,7 +153,10 @@ static int extract_chunks_to_host(Arena &A, asp_operator const *op, uint64_t n, 
       const unsigned long long total = *static_cast<volatile unsigned long long *>(A.h_totals + c);
       const uint64_t begin = c * chunk_rows, rows = std::min(chunk_rows, num_rows - begin);
       const uint64_t extra = (c == chunks - 1) ? 1 : 0;  // the closing indptr entry
-      HOST_CUDA(cudaMemcpyAsync(h_indptr + begin, d_indptr + begin, (rows + extra) * sizeof(int64_t), cudaMemcpyDeviceToHost, A.copy_out));
+      if (narrow)
+        HOST_CUDA(cudaMemcpyAsync(h_indptr32 + begin, d_indptr32 + begin, (rows + extra) * sizeof(int32_t), cudaMemcpyDeviceToHost, A.copy_out));
+      else
+        HOST_CUDA(cudaMemcpyAsync(h_indptr + begin, d_indptr + begin, (rows + extra) * sizeof(int64_t), cudaMemcpyDeviceToHost, A.copy_out));
       if (total > capacity) overflow = true;
       if (!overflow && total > done) {
         HOST_CUDA(cudaMemcpyAsync(h_indices + done, d_indices + done, (total - done) * sizeof(int32_t), cudaMemcpyDeviceToHost, A.copy_out));
@@ -143,6 +166,11 @@ static int extract_chunks_to_host(Arena &A, asp_operator const *op, uint64_t n, 
     }
     HOST_CUDA(cudaStreamSynchronize(A.copy_out));
     *h_nnz = done;
+    if (narrow && done > 0x7FFFFFFFull) {
+      asp::set_error("%llu couplings do not fit int32 row starts: use the int64 entry point", done);
+      rc = ASP_ERR_UNSUPPORTED;
+      goto out;
+    }
     if (overflow) {
       asp::set_error("output capacity too small: %llu couplings, room for %llu (h_indptr is complete; call again with the larger capacity)",
                      done, static_cast<unsigned long long>(capacity));
@@ -164,9 +192,9 @@ void asp_host_release(void) {
   if (!g_arena.busy) g_arena.release();
 }
 
-int asp_extract_host(asp_operator const *op, uint64_t n, uint64_t const *h_spins, double const *h_psi, uint64_t row_begin,
-                     uint64_t num_rows, uint64_t capacity, int64_t *h_indptr, int32_t *h_indices, double *h_data,
-                     uint64_t *h_nnz) {
+static int extract_host_impl(asp_operator const *op, uint64_t n, uint64_t const *h_spins, double const *h_psi, uint64_t row_begin,
+                             uint64_t num_rows, uint64_t capacity, void *h_indptr, bool narrow, int32_t *h_indices, double *h_data,
+                             uint64_t *h_nnz) {
   int rc = asp::fused_check_operator(op);
   if (rc != ASP_OK) return rc;
   ASP_REQUIRE(h_nnz && h_indptr, "NULL argument");
@@ -176,7 +204,10 @@ int asp_extract_host(asp_operator const *op, uint64_t n, uint64_t const *h_spins
   ASP_REQUIRE(row_begin + num_rows <= n, "row block exceeds the basis");
   *h_nnz = 0;
   if (num_rows == 0 || n == 0) {
-    h_indptr[0] = 0;
+    if (narrow)
+      static_cast<int32_t *>(h_indptr)[0] = 0;
+    else
+      static_cast<int64_t *>(h_indptr)[0] = 0;
     return ASP_OK;
   }
   Arena &A = g_arena;
@@ -216,7 +247,7 @@ int asp_extract_host(asp_operator const *op, uint64_t n, uint64_t const *h_spins
     if (rc != ASP_OK) goto out;
     HOST_CUDA(cudaStreamWaitEvent(A.compute, A.ev_psi, 0));
     rc = extract_chunks_to_host(A, op, n, d_spins, d_psi, row_begin, num_rows, chunk_rows, chunks, A.workspace.p, dev_capacity, capacity,
-                                d_indptr, d_indices, d_data, d_totals, h_indptr, h_indices, h_data, h_nnz);
+                                d_indptr, d_indices, d_data, d_totals, h_indptr, narrow, h_indices, h_data, h_nnz);
   }
 out:
   if (rc == ASP_ERR_CUDA) cudaDeviceSynchronize();  // leave no work in flight behind a failed call
@@ -224,9 +255,21 @@ out:
   return rc;
 }
 
-int asp_extract_indexed_to_host(asp_operator const *op, uint64_t n, uint64_t const *d_spins, double const *d_psi, uint64_t row_begin,
-                                uint64_t num_rows, void *d_workspace, size_t workspace_bytes, uint64_t capacity, int64_t *h_indptr,
-                                int32_t *h_indices, double *h_data, uint64_t *h_nnz, void *stream) {
+int asp_extract_host(asp_operator const *op, uint64_t n, uint64_t const *h_spins, double const *h_psi, uint64_t row_begin,
+                     uint64_t num_rows, uint64_t capacity, int64_t *h_indptr, int32_t *h_indices, double *h_data,
+                     uint64_t *h_nnz) {
+  return extract_host_impl(op, n, h_spins, h_psi, row_begin, num_rows, capacity, h_indptr, false, h_indices, h_data, h_nnz);
+}
+
+int asp_extract_host_i32(asp_operator const *op, uint64_t n, uint64_t const *h_spins, double const *h_psi, uint64_t row_begin,
+                         uint64_t num_rows, uint64_t capacity, int32_t *h_indptr, int32_t *h_indices, double *h_data,
+                         uint64_t *h_nnz) {
+  return extract_host_impl(op, n, h_spins, h_psi, row_begin, num_rows, capacity, h_indptr, true, h_indices, h_data, h_nnz);
+}
+
+static int extract_indexed_to_host_impl(asp_operator const *op, uint64_t n, uint64_t const *d_spins, double const *d_psi, uint64_t row_begin,
+                                        uint64_t num_rows, void *d_workspace, size_t workspace_bytes, uint64_t capacity, void *h_indptr,
+                                        bool narrow, int32_t *h_indices, double *h_data, uint64_t *h_nnz, void *stream) {
   int rc = asp::fused_check_operator(op);
   if (rc != ASP_OK) return rc;
   ASP_REQUIRE(h_nnz && h_indptr, "NULL argument");
@@ -235,7 +278,10 @@ int asp_extract_indexed_to_host(asp_operator const *op, uint64_t n, uint64_t con
   ASP_REQUIRE(row_begin + num_rows <= n, "row block exceeds the basis");
   *h_nnz = 0;
   if (num_rows == 0 || n == 0) {
-    h_indptr[0] = 0;
+    if (narrow)
+      static_cast<int32_t *>(h_indptr)[0] = 0;
+    else
+      static_cast<int64_t *>(h_indptr)[0] = 0;
     return ASP_OK;
   }
   ASP_REQUIRE(d_spins && d_psi && d_workspace, "NULL device buffer");
@@ -261,7 +307,7 @@ int asp_extract_indexed_to_host(asp_operator const *op, uint64_t n, uint64_t con
     HOST_CUDA(cudaStreamWaitEvent(A.compute, A.ev_spins, 0));
     rc = extract_chunks_to_host(A, op, n, d_spins, d_psi, row_begin, num_rows, chunk_rows, chunks, d_workspace, dev_capacity, capacity,
                                 static_cast<int64_t *>(A.indptr.p), static_cast<int32_t *>(A.indices.p), static_cast<double *>(A.data.p),
-                                d_totals, h_indptr, h_indices, h_data, h_nnz);
+                                d_totals, h_indptr, narrow, h_indices, h_data, h_nnz);
     // the caller's stream must not reuse the workspace or the basis before the chunks are done
     if (rc == ASP_OK) {
       HOST_CUDA(cudaEventRecord(A.ev_psi, A.compute));
@@ -272,6 +318,20 @@ out:
   if (rc == ASP_ERR_CUDA) cudaDeviceSynchronize();
   release_busy(A);
   return rc;
+}
+
+int asp_extract_indexed_to_host(asp_operator const *op, uint64_t n, uint64_t const *d_spins, double const *d_psi, uint64_t row_begin,
+                                uint64_t num_rows, void *d_workspace, size_t workspace_bytes, uint64_t capacity, int64_t *h_indptr,
+                                int32_t *h_indices, double *h_data, uint64_t *h_nnz, void *stream) {
+  return extract_indexed_to_host_impl(op, n, d_spins, d_psi, row_begin, num_rows, d_workspace, workspace_bytes, capacity, h_indptr, false,
+                                      h_indices, h_data, h_nnz, stream);
+}
+
+int asp_extract_indexed_to_host_i32(asp_operator const *op, uint64_t n, uint64_t const *d_spins, double const *d_psi, uint64_t row_begin,
+                                    uint64_t num_rows, void *d_workspace, size_t workspace_bytes, uint64_t capacity, int32_t *h_indptr,
+                                    int32_t *h_indices, double *h_data, uint64_t *h_nnz, void *stream) {
+  return extract_indexed_to_host_impl(op, n, d_spins, d_psi, row_begin, num_rows, d_workspace, workspace_bytes, capacity, h_indptr, true,
+                                      h_indices, h_data, h_nnz, stream);
 }
 
 int asp_extract_host_begin(asp_operator const *op, uint64_t n, uint64_t const *h_spins, double const *h_psi,

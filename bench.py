@@ -456,7 +456,7 @@ def run_ours(args):
     if not args.skip_e2e:
         h_spins = spins.cpu().pin_memory()
         h_psi = psi.cpu().pin_memory()
-        h_indptr = torch.empty(num_rows + 1, dtype=torch.int64).pin_memory()
+        h_indptr = torch.empty(num_rows + 1, dtype=torch.int32).pin_memory()  # scipy's index type below 2^31 couplings
         h_indices = torch.empty(capacity, dtype=torch.int32).pin_memory()
         h_data = torch.empty(capacity, dtype=torch.float64).pin_memory()
 
@@ -477,10 +477,10 @@ def run_ours(args):
 
         def host_pass_full():
             nnz = ffi.new("uint64_t *")
-            common.check(lib().asp_extract_host(op.handle, n_total, ffi.cast("uint64_t *", h_spins.data_ptr()),
-                                                ffi.cast("double *", h_psi.data_ptr()), row_begin, num_rows, capacity,
-                                                ffi.cast("int64_t *", h_indptr.data_ptr()), ffi.cast("int32_t *", h_indices.data_ptr()),
-                                                ffi.cast("double *", h_data.data_ptr()), nnz))
+            common.check(lib().asp_extract_host_i32(op.handle, n_total, ffi.cast("uint64_t *", h_spins.data_ptr()),
+                                                    ffi.cast("double *", h_psi.data_ptr()), row_begin, num_rows, capacity,
+                                                    ffi.cast("int32_t *", h_indptr.data_ptr()), ffi.cast("int32_t *", h_indices.data_ptr()),
+                                                    ffi.cast("double *", h_data.data_ptr()), nnz))
             assert int(nnz[0]) == nnz_mine
 
         host_pass = host_pass_sharded if peer is not None else host_pass_full
@@ -496,12 +496,12 @@ def run_ours(args):
         assert int(h_indptr[-1]) == nnz_mine
         e2e = {"value": nnz_total * e2e_steps / e2e_s, "unit": "couplings/s",
                "h2d_bytes_per_step": int((num_rows if peer is not None else n_total) * 16),
-               "d2h_bytes_per_step": int((num_rows + 1) * 8 + nnz_mine * 12),
+               "d2h_bytes_per_step": int((num_rows + 1) * 4 + nnz_mine * 12),
                "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
-               "api": ("per rank: own row block pinned host -> peer buffer, asp_gather_index over NVLink, asp_extract_indexed_to_host "
+               "api": ("per rank: own row block pinned host -> peer buffer, asp_gather_index over NVLink, asp_extract_indexed_to_host_i32 "
                        "(row chunks copied back while the next chunk is extracted); bytes are per rank" if peer is not None else
-                       "asp_extract_host (include/asp_b200.h), pinned host buffers, row chunks copied back while the next chunk is "
-                       "extracted" + ("; every rank uploads the full basis; bytes are per rank" if world > 1 else ""))}
+                       "asp_extract_host_i32 (include/asp_b200.h; int32 row starts and columns, f64 values: scipy's CSR types), pinned host "
+                       "buffers, row chunks copied back while the next chunk is extracted" + ("; every rank uploads the full basis; bytes are per rank" if world > 1 else ""))}
         del h_spins, h_psi, h_indptr, h_indices, h_data
 
     # ---- annealing stage on the extracted model (replicas shard over ranks) ------------------

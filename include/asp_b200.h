@@ -179,6 +179,14 @@ int asp_csr_symmetrize(uint64_t n, int64_t const *d_indptr, int32_t const *d_ind
 int asp_extract_host(asp_operator const *op, uint64_t n_total, uint64_t const *h_spins,
                      double const *h_psi, uint64_t row_begin, uint64_t num_rows, uint64_t capacity,
                      int64_t *h_indptr, int32_t *h_indices, double *h_data, uint64_t *h_nnz);
+/* Same with int32 row starts -- the index type scipy itself picks for both CSR index arrays when
+ * nnz < 2^31 and what the reference's model dump stores (common.py:762-763): csr_matrix((data,
+ * indices, indptr)) then adopts the buffers without a copy, and 4 bytes per row less cross PCIe.
+ * ASP_ERR_UNSUPPORTED when the couplings do not fit. */
+int asp_extract_host_i32(asp_operator const *op, uint64_t n_total, uint64_t const *h_spins,
+                         double const *h_psi, uint64_t row_begin, uint64_t num_rows,
+                         uint64_t capacity, int32_t *h_indptr, int32_t *h_indices, double *h_data,
+                         uint64_t *h_nnz);
 /* Two calls, exact-size outputs: begin = H2D + extraction (returns nnz), finish = D2H into
  * caller buffers (h_indptr[num_rows+1], h_indices/h_data[nnz]), then frees the job. */
 int asp_extract_host_begin(asp_operator const *op, uint64_t n_total, uint64_t const *h_spins,
@@ -308,6 +316,11 @@ int asp_extract_indexed_to_host(asp_operator const *op, uint64_t n_total, uint64
                                 void *d_workspace, size_t workspace_bytes, uint64_t capacity,
                                 int64_t *h_indptr, int32_t *h_indices, double *h_data, uint64_t *h_nnz,
                                 void *stream);
+int asp_extract_indexed_to_host_i32(asp_operator const *op, uint64_t n_total, uint64_t const *d_spins,
+                                    double const *d_psi, uint64_t row_begin, uint64_t num_rows,
+                                    void *d_workspace, size_t workspace_bytes, uint64_t capacity,
+                                    int32_t *h_indptr, int32_t *h_indices, double *h_data,
+                                    uint64_t *h_nnz, void *stream);
 /* asp_gather_index has three implementations of the same contract (measured within 5 % of each
  * other and of NCCL's all-gather alone, ~510 GB/s pulled per rank on 4 GPUs -- the fabric, not the
  * kernel, sets the pace): 2 (default) = ONE persistent kernel, cp.async.bulk (TMA) keeps 128 KB per

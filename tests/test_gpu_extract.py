@@ -264,11 +264,11 @@ def test_gather_index_kernel_over_emulated_shards_equals_the_unsharded_build():
                     ffi.new("double const *[]", [common.ptr(t, "double const *") for t in parts_p]),
                     ffi.NULL, 0, common.ptr(full_s, "uint64_t *"), common.ptr(full_p, "double *"), num_rows,
                     common.ptr(workspace, "void *"), need, common.stream()))
-                h_indptr = torch.empty(num_rows + 1, dtype=torch.int64).pin_memory()
+                h_indptr = torch.empty(num_rows + 1, dtype=torch.int32 if rank else torch.int64).pin_memory()
                 h_indices = torch.empty(hi - lo + 5, dtype=torch.int32).pin_memory()
                 h_data = torch.empty(hi - lo + 5, dtype=torch.float64).pin_memory()
                 m = common.extract_indexed_to_host(op, full_s, full_p, row_begin, num_rows, workspace, h_indptr, h_indices, h_data)
-                assert m == hi - lo and torch.equal(h_indptr, indptr.cpu())
+                assert m == hi - lo and torch.equal(h_indptr.to(torch.int64), indptr.cpu())
                 assert torch.equal(h_indices[:m], indices.cpu()) and torch.equal(h_data[:m], data.cpu())
     lib().asp_set_gather_mode(2)
 
@@ -514,6 +514,15 @@ def test_one_call_host_pipeline_with_row_chunks():
         rc = lib().asp_extract_host(op.handle, n, c(h_spins, "uint64_t *"), c(h_psi, "double *"), lo, rows, m // 2,
                                     c(hp, "int64_t *"), c(hi, "int32_t *"), c(hd, "double *"), nnz)
         assert rc == lib().ASP_ERR_WORKSPACE and int(nnz[0]) == m and np.array_equal(hp, indptr.cpu().numpy())
+        # int32 row starts (scipy's own index type below 2^31 couplings): the buffers drop into csr_matrix without a copy
+        hp32 = np.full(rows + 1, -1, dtype=np.int32)
+        hi[:] = -1
+        rc = lib().asp_extract_host_i32(op.handle, n, c(h_spins, "uint64_t *"), c(h_psi, "double *"), lo, rows, cap,
+                                        c(hp32, "int32_t *"), c(hi, "int32_t *"), c(hd, "double *"), nnz)
+        assert rc == 0 and int(nnz[0]) == m and np.array_equal(hp32, indptr.cpu().numpy().astype(np.int32))
+        assert np.array_equal(hi[:m], indices.cpu().numpy()) and np.array_equal(hd[:m], data.cpu().numpy())
+        block = scipy.sparse.csr_matrix((hd[:m], hi[:m], hp32), shape=(rows, n))
+        assert block.indptr.dtype == np.int32 and np.shares_memory(block.indptr, hp32) and np.shares_memory(block.data, hd)
 
 
 def _golden_log_psi(spins):
