@@ -55,6 +55,8 @@ def parse_args():
                         "reference's experiment): the copy engines gather the basis of step k+1 (asp_gather_blocks, no SM) while "
                         "step k is indexed and extracted; 1 = strictly serial, X1 fused with the index build in one kernel "
                         "(asp_gather_index)")
+    p.add_argument("--pipeline-slots", type=int, default=2, choices=[2, 3],
+                   help="private copies of the basis in the pipelined exchange: the exchange runs up to slots - 1 steps ahead")
     p.add_argument("--skip-anneal", action="store_true")
     p.add_argument("--skip-cpu", action="store_true")
     p.add_argument("--skip-e2e", action="store_true")
@@ -332,47 +334,50 @@ def run_ours(args):
         s_exchange, s_compute = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
 
     def run_pipelined(count, timers=None):
-        """Two-deep software pipeline over `count` independent steps (in the reference's experiment: one extraction per
-        cluster).  Exchange stream: [begin_epoch, publish, asp_gather_blocks, release] of step k+1 -- the copy engines pull
-        the row blocks over NVLink, no SM involved -- while the compute stream runs asp_extract_csr (index + extraction) of
-        step k.  Two private copies of the basis; a copy is gathered into again only after the extraction that read it."""
-        gathered = [torch.cuda.Event() for _ in range(2)]
-        extracted = [None, None]
-        fulls = [None, None]
+        """Software pipeline over `count` independent steps (in the reference's experiment: one extraction per cluster).
+        Exchange stream: [begin_epoch, publish, asp_gather_blocks, release] of the steps ahead -- the copy engines pull
+        the row blocks over NVLink, no SM involved -- while the compute stream runs asp_extract_csr (index + extraction)
+        of step k.  `depth` private copies of the basis; a copy is gathered into again only after the extraction that
+        read it, so the exchange runs up to depth - 1 steps ahead of the extraction."""
+        depth = args.pipeline_slots
+        gathered = [torch.cuda.Event() for _ in range(depth)]
+        extracted = [None] * depth
+        fulls = [None] * depth
         here = torch.cuda.current_stream()
         s_exchange.wait_stream(here)
         s_compute.wait_stream(here)
 
         def exchange_step(k):
             with torch.cuda.stream(s_exchange):
-                if extracted[k % 2] is not None:
-                    s_exchange.wait_event(extracted[k % 2])
+                if extracted[k % depth] is not None:
+                    s_exchange.wait_event(extracted[k % depth])
                 ex = [torch.cuda.Event(enable_timing=True) for _ in range(2)] if timers is not None else None
                 peer.begin_epoch()
                 peer.publish()
                 if ex:
                     ex[0].record()
-                fulls[k % 2] = peer.gather_blocks(bounds, slot=k % 2)
+                fulls[k % depth] = peer.gather_blocks(bounds, slot=k % depth)
                 if ex:
                     ex[1].record()
                     exchange.append(ex)
                 peer.release()
-                gathered[k % 2].record()
+                gathered[k % depth].record()
 
         out = None
-        exchange_step(0)
+        for k in range(min(depth - 1, count)):
+            exchange_step(k)
         for k in range(count):
-            if k + 1 < count:
-                exchange_step(k + 1)  # queued first: its flag kernels must not wait behind the extraction
+            if k + depth - 1 < count:
+                exchange_step(k + depth - 1)  # queued first: its flag kernels must not wait behind the extraction
             with torch.cuda.stream(s_compute):
-                s_compute.wait_event(gathered[k % 2])
+                s_compute.wait_event(gathered[k % depth])
                 ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)] if timers is not None else None
                 indptr = torch.empty(num_rows + 1, dtype=torch.int64, device=dev)
                 indices = torch.empty(capacity, dtype=torch.int32, device=dev)
                 data = torch.empty(capacity, dtype=torch.float64, device=dev)
                 if ev:
                     ev[0].record()
-                full_spins, full_psi = fulls[k % 2]
+                full_spins, full_psi = fulls[k % depth]
                 common.check(lib().asp_extract_csr(op.handle, n_total, common.ptr(full_spins, "uint64_t *"), common.ptr(full_psi, "double *"),
                                                    row_begin, num_rows, common.ptr(workspace, "void *"), workspace.numel(), capacity,
                                                    common.ptr(indptr, "int64_t *"), common.ptr(indices, "int32_t *"),
@@ -380,8 +385,8 @@ def run_ours(args):
                 if ev:
                     ev[1].record()
                     timers.append(ev)
-                extracted[k % 2] = torch.cuda.Event()
-                extracted[k % 2].record()
+                extracted[k % depth] = torch.cuda.Event()
+                extracted[k % depth].record()
                 out = (indptr, indices, data)
         here.wait_stream(s_compute)
         here.wait_stream(s_exchange)
