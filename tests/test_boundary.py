@@ -125,3 +125,41 @@ def test_two_rank_sharding_plan_over_gloo(tmp_path):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "SHARDING_OK" in out.stdout
+
+
+def test_error_convention_of_the_exchange_and_sampling_entry_points(asp):
+    """ADDITION to the reference (which has no error channel): every `int` entry point answers a bad argument with
+    ASP_ERR_ARG and a message in asp_last_error() before it touches the device -- checked here without a GPU for the
+    entry points of the exchange step X1 and of the sampling front-end."""
+    from annealing_sign_problem_b200._lib import ffi, lib
+
+    L = lib()
+    NULL = ffi.NULL
+    two = ffi.new("uint64_t *[]", [ffi.cast("uint64_t *", 256), ffi.cast("uint64_t *", 512)])
+    keys = ffi.new("uint64_t const *[]", [ffi.cast("uint64_t const *", 256), ffi.cast("uint64_t const *", 512)])
+    amps = ffi.new("double const *[]", [ffi.cast("double const *", 256), ffi.cast("double const *", 512)])
+    begin = ffi.new("uint64_t[]", [0, 10, 20])
+
+    def message():
+        return ffi.string(L.asp_last_error()).decode()
+
+    assert L.asp_peer_signal(0, two, 0, 1, NULL) == L.ASP_ERR_ARG and "1..16" in message()
+    assert L.asp_peer_signal(17, two, 0, 1, NULL) == L.ASP_ERR_ARG
+    assert L.asp_peer_wait(2, NULL, 1, NULL) == L.ASP_ERR_ARG
+    assert L.asp_peer_alloc(0, ffi.new("void **"), ffi.new("unsigned char[64]")) == L.ASP_ERR_ARG
+    assert L.asp_peer_open(NULL, ffi.new("void **")) == L.ASP_ERR_ARG
+    assert L.asp_peer_close(NULL) == L.ASP_OK and L.asp_peer_free(NULL) == L.ASP_OK  # like free(NULL)
+    assert L.asp_gather_blocks(0, 0, begin, keys, amps, NULL, 0, ffi.cast("uint64_t *", 256), ffi.cast("double *", 256), NULL) == L.ASP_ERR_ARG
+    assert L.asp_gather_blocks(2, 0, begin, keys, amps, NULL, 0, NULL, NULL, NULL) == L.ASP_ERR_ARG and "NULL output" in message()
+    assert L.asp_gather_blocks(2, 0, NULL, keys, amps, NULL, 0, ffi.cast("uint64_t *", 256), ffi.cast("double *", 256), NULL) == L.ASP_ERR_ARG
+    assert L.asp_gather_index(NULL, 2, 0, begin, keys, amps, NULL, 0, ffi.cast("uint64_t *", 256), ffi.cast("double *", 256), 10, NULL, 0,
+                              NULL) == L.ASP_ERR_ARG and "operator is NULL" in message()
+    assert L.asp_extract_csr_indexed(NULL, 20, NULL, NULL, 0, 10, NULL, 0, 0, NULL, NULL, NULL, NULL, NULL) == L.ASP_ERR_ARG
+    assert L.asp_extract_host_i32(NULL, 20, NULL, NULL, 0, 10, 0, NULL, NULL, NULL, NULL) == L.ASP_ERR_ARG
+    assert L.asp_extract_indexed_to_host_i32(NULL, 20, NULL, NULL, 0, 10, NULL, 0, 0, NULL, NULL, NULL, NULL, NULL) == L.ASP_ERR_ARG
+    assert L.asp_sample_indices(0, NULL, 2.0, 0, NULL, NULL, NULL, NULL) == L.ASP_ERR_ARG and "empty distribution" in message()
+    assert L.asp_sample_indices(5, ffi.cast("double *", 256), 2.0, 3, NULL, NULL, NULL, NULL) == L.ASP_ERR_ARG
+    assert L.asp_batched_index(5, NULL, 0, NULL, NULL, NULL, NULL) == L.ASP_ERR_ARG
+    assert L.asp_batched_index(5, ffi.cast("uint64_t *", 256), 3, NULL, NULL, NULL, NULL) == L.ASP_ERR_ARG
+    L.asp_set_gather_mode(7)  # unknown modes select the default, never an undefined path
+    L.asp_set_gather_mode(2)
