@@ -244,6 +244,7 @@ def main():
     known_answers(os.path.join(HERE, "known_answers.json"))
     extension_case(ref_common, "heisenberg_kagome_16", 120, 4, 2e-2, os.path.join(HERE, "n2_heisenberg_kagome_16.npz"))
     extension_case(ref_common, "j1j2_square_4x4", 80, 5, 5e-2, os.path.join(HERE, "n2_j1j2_square_4x4.npz"))
+    extension_case(ref_common, "heisenberg_kagome_18", 100, 7, 2e-2, os.path.join(HERE, "n2_heisenberg_kagome_18.npz"))  # spin-inversion basis
 
 
 if __name__ == "__main__":

@@ -533,7 +533,7 @@ def _golden_log_psi(spins):
     return 4.0 * (u - 0.5) + 1j * np.pi * v
 
 
-@pytest.mark.parametrize("name", ["n2_heisenberg_kagome_16", "n2_j1j2_square_4x4"])
+@pytest.mark.parametrize("name", ["n2_heisenberg_kagome_16", "n2_j1j2_square_4x4", "n2_heisenberg_kagome_18"])
 def test_cluster_extension_and_sparsification_match_the_reference(golden_dir, name):
     """SURVEY 8f N2 against vectors produced by the reference's OWN make_hamiltonian_extension
     (common.py:516-522), get_strongest_off_diag (:539-541) and sparsify_using_global_cutoff
