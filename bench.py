@@ -140,13 +140,20 @@ def u1_operator(asp):
 # ------------------------------------------------------------------------------------------
 # CPU legs (rank 0): the reference's own C (oracle/_ref) on a bounded sample
 # ------------------------------------------------------------------------------------------
-def cpu_sample_inputs(asp, op, cfg, n_sample, dev):
-    from annealing_sign_problem_b200 import synthetic
-    from oracle.operator_np import OperatorNP
+def cpu_sample_inputs(n_sample):
+    """Inputs of the CPU legs, made WITHOUT the product: the oracle's numpy operator and its numpy twin of the
+    synthetic generator (oracle/synthetic_np.py) -- same shape of workload (kagome_36 bond list on the U(1) basis,
+    cluster-closed subset, ~12 % of the candidates are hits), smaller sample."""
+    from oracle import synthetic_np
+    from oracle.operator_np import OperatorNP, load_config, system_path
 
-    spins = synthetic.cluster_closed_states(op, n_sample, 1234, dev).cpu().numpy().view(np.uint64)
-    psi = synthetic.synthetic_amplitudes(spins.shape[0], 1234).numpy()
-    other_spins, other_coeffs, other_counts = OperatorNP.from_config(cfg).apply_u64(spins)
+    cfg = load_config(system_path(SYSTEM))
+    cfg["basis"]["symmetries"] = []
+    cfg["basis"]["spin_inversion"] = None
+    op_np = OperatorNP.from_config(cfg)
+    spins = synthetic_np.cluster_closed_states(op_np, n_sample, 1234)
+    psi = synthetic_np.synthetic_amplitudes(spins.shape[0], 1234)
+    other_spins, other_coeffs, other_counts = op_np.apply_u64(spins)
     idx = np.clip(np.searchsorted(spins, other_spins), 0, spins.shape[0] - 1)
     other_psi = np.where(spins[idx] == other_spins, psi[idx], 0.0)
     return spins, psi, other_spins, other_coeffs, other_counts, other_psi
@@ -188,19 +195,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
-
-    import annealing_sign_problem_b200 as asp
-    from oracle import capi
+    from oracle import capi  # nothing of the product is imported on this arm
 
     capi.build()
     impl = "ref" if capi.have_ref() else "port"
-    dev = torch.device("cuda", 0) if torch.cuda.is_available() else None
-    if dev is None:
-        print(json.dumps({"impl": "reference", "unavailable": "sample generation needs the CUDA operator; no GPU"}))
-        return
-    op, cfg = u1_operator(asp)
-    inputs = cpu_sample_inputs(asp, op, cfg, args.cpu_sample, dev)
+    inputs = cpu_sample_inputs(args.cpu_sample)
     nnz, times = 0, []
     for step in range(args.warmup + args.steps):
         nnz, dt = cpu_extract_once(capi, inputs, impl)
@@ -574,7 +573,7 @@ def run_ours(args):
 
         capi.build()
         impl = "ref" if capi.have_ref() else "port"
-        inputs = cpu_sample_inputs(asp, op, cfg, args.cpu_sample, dev)
+        inputs = cpu_sample_inputs(args.cpu_sample)
         nnz_s, dt = cpu_extract_once(capi, inputs, impl)
         flips_s, cores, reps = cpu_anneal_once(capi, inputs, 4)
         cpu = {"value": nnz_s / dt, "unit": "couplings/s", "cores": 1, "kind": "reference" if impl == "ref" else "port",
