@@ -466,25 +466,21 @@ def solve_ising_model(
     repetitions: int = 64,
     only_best: bool = True,
 ):
-    if mode == "sa":
-        x, _ = sa.anneal(
-            model.ising_hamiltonian,
-            seed=seed,
-            number_sweeps=number_sweeps,
-            repetitions=repetitions,
-            only_best=only_best,
-        )
-    elif mode == "greedy":
-        x, _ = sa.greedy_solve(model.ising_hamiltonian)
-    else:
+    """Signs of the model's spins by replica annealing (``mode="sa"``) or by the greedy solver (``"greedy"``), as
+    packed bits; with ``frozen_spins`` only the signs of those states, in their order (reference: common.py:232-261,
+    same defaults and the same ValueError for an unknown mode)."""
+    solvers = {
+        "sa": lambda: sa.anneal(model.ising_hamiltonian, seed=seed, number_sweeps=number_sweeps, repetitions=repetitions,
+                                only_best=only_best),
+        "greedy": lambda: sa.greedy_solve(model.ising_hamiltonian),
+    }
+    if mode not in solvers:
         raise ValueError("invalid mode specified: '{}'; expected either 'sa' or 'greedy'".format(mode))
-
-    if frozen_spins is not None:
-        frozen_indices = binary_search(model.spins, frozen_spins)
-        frozen_signs = sa.bits_to_signs(x, count=model.spins.size)
-        frozen_signs = frozen_signs[frozen_indices]
-        x = sa.signs_to_bits(frozen_signs)
-    return x
+    x, _ = solvers[mode]()
+    if frozen_spins is None:
+        return x
+    positions = binary_search(model.spins, frozen_spins)  # asserts that every frozen spin is part of the model
+    return sa.signs_to_bits(sa.bits_to_signs(x, count=model.spins.size)[positions])
 
 
 # ---------------------------------------------------------------------------------------
@@ -528,66 +524,62 @@ def determine_exact_solution(spins, quantum_hamiltonian, ground_state):  # commo
 
 
 def create_small_cluster_around_point(s0: int, hamiltonian, required_size: int = 20, keep_probability: float = 0.5):
-    """common.py:481-513: random breadth-first growth around ``s0`` (sequential by construction: one
-    np.random.rand() per not-yet-visited child, in the operator's neighbour order)."""
-    assert hamiltonian.basis.number_spins <= 64
-    s0 = int(s0)
-    spins = {s0}
+    """Random breadth-first growth of a cluster around ``s0`` (reference: common.py:481-513).  Sequential by
+    construction: ONE ``np.random.rand()`` is consumed per neighbour that is not yet a member, in the order in
+    which the operator lists the neighbours, and the frontier of the next generation is a Python ``set`` -- both
+    are part of the behaviour (a seeded run must grow the reference's cluster), so they are kept exactly."""
+    if hamiltonian.basis.number_spins > 64:
+        raise AssertionError("only works with up to 64 spins")
+    members = {int(s0)}
 
-    def children_of(s):
-        xs, _ = hamiltonian.apply(s)
-        if xs.ndim > 1:
-            xs = xs[:, 0]
-        children = []
-        for x in xs:
-            if x in spins:
-                continue
-            if np.random.rand() <= keep_probability:
-                children.append(int(x))
-        return children
+    def kept_neighbours(state):
+        images, _ = hamiltonian.apply(state)
+        images = images[:, 0] if images.ndim > 1 else images
+        kept = []
+        for image in images:
+            if image not in members and np.random.rand() <= keep_probability:
+                kept.append(int(image))
+        return kept
 
-    children = children_of(s0)
-    while len(spins) < required_size and len(children) > 0:
-        new_children = set()
-        for child in children:
-            spins.add(child)
-            if len(spins) >= required_size:
+    frontier = kept_neighbours(int(s0))
+    while frontier and len(members) < required_size:
+        upcoming = set()
+        for state in frontier:
+            members.add(state)
+            if len(members) >= required_size:
                 break
-            new_children |= set(children_of(child))
-        children = new_children
-    return sorted(list(spins))
+            upcoming |= set(kept_neighbours(state))
+        frontier = upcoming
+    return sorted(members)
 
 
 def ground_state_to_log_coeff_fn(ground_state: np.ndarray, basis: ls.SpinBasis):
-    """common.py:806-823: spins -> log|psi| + i*pi*[psi < 0], looked up in the full basis (device
-    search, asp_batched_index)."""
-    ground_state = np.asarray(ground_state, dtype=np.float64, order="C")
-    assert ground_state.ndim == 1
+    """Closure ``spins -> log|psi| + i*pi*[psi < 0]`` over a ground state given on the full basis (reference:
+    common.py:806-823); the lookup of the states is the device search ``asp_batched_index``."""
+    psi = np.ascontiguousarray(ground_state, dtype=np.float64)
+    if psi.ndim != 1:
+        raise AssertionError("'ground_state' must be a vector")
     with np.errstate(divide="ignore"):
-        log_amplitudes = np.log(np.abs(ground_state))
-    phases = np.where(ground_state >= 0, 0, np.pi)
+        table = np.log(np.abs(psi)) + 1j * np.where(psi >= 0, 0.0, np.pi)
 
     def log_coeff_fn(spins: np.ndarray) -> np.ndarray:
-        spins = np.asarray(spins, dtype=np.uint64, order="C")
-        if spins.ndim > 1:
-            spins = spins[:, 0]
-        indices = ls.batched_index(basis, spins)
-        a = log_amplitudes[indices]
-        b = phases[indices]
-        return a + 1j * b
+        words = np.asarray(spins, dtype=np.uint64, order="C")
+        if words.ndim > 1:  # the [n, 8] form: only word 0 is used below 65 spins
+            words = words[:, 0]
+        return table[ls.batched_index(basis, words)]
 
     return log_coeff_fn
 
 
-def add_noise_to_amplitudes(ground_state, eps: float):  # common.py:826-838
-    ground_state = np.asarray(ground_state, dtype=np.float64, order="C")
-    assert ground_state.ndim == 1
-    log_amplitudes = np.log(np.abs(ground_state))
-    signs = np.sign(ground_state)
-    noise = eps * 2 * (np.random.rand(log_amplitudes.size) - 0.5)
-    noisy_ground_state = signs * np.exp(log_amplitudes + noise)
-    noisy_ground_state /= np.linalg.norm(noisy_ground_state)
-    return noisy_ground_state
+def add_noise_to_amplitudes(ground_state, eps: float):
+    """|psi_i| -> |psi_i| * exp(eps * u_i), u_i uniform in (-1, 1) from numpy's global stream, signs kept,
+    renormalised (reference: common.py:826-838)."""
+    psi = np.ascontiguousarray(ground_state, dtype=np.float64)
+    if psi.ndim != 1:
+        raise AssertionError("'ground_state' must be a vector")
+    kick = eps * 2 * (np.random.rand(psi.size) - 0.5)
+    noisy = np.sign(psi) * np.exp(np.log(np.abs(psi)) + kick)
+    return noisy / np.linalg.norm(noisy)
 
 
 def amplitude_overlap(cluster, ground_state, noisy_ground_state, basis):  # sampled_connected_components.py:719-723
