@@ -12,10 +12,15 @@ Contents (each module cites the reference file:line it restates):
                     (third-party, un-vendored, pinned =0.8.3; PARITY UNPINNED at this
                     boundary, anchored on the reference call sites common.py:85-106).
 * ``extract_port.c``  C restatement of ``cbits/build_matrix.c`` (+ canonical CSR).
-* ``live_path``     numpy/scipy restatement of ``common.py:make_ising_model``.
+* ``live_path``     numpy/scipy restatement of ``common.py:make_ising_model``, of the reductions and of the
+                    sampling front-end (``sample_indices``, ``batched_index``, ``log_coeff``); PINNED by golden
+                    vectors the reference itself produced (``tests/golden/make_golden.py``).
 * ``anneal_port.c`` C restatement of the replica Metropolis annealer
                     (``ising_glass_annealer.anneal``; third-party, un-vendored, pinned
                     =0.4.1.2; PARITY UNPINNED, anchored on outcomes: E0, bit layout).
+* ``greedy_port.c`` Kruskal restatement of ``ising_glass_annealer.greedy_solve`` from the Python the
+                    reference preserves at common.py:298-438 (PARITY UNPINNED).
+* ``synthetic_np``  numpy generator of the CPU legs' inputs (the reference arm of bench.py uses nothing else).
 * ``_ref/``         the reference's own ``cbits/build_matrix.c`` compiled where it lies
                     (git-ignored; built by ``oracle/Makefile``).
 """
