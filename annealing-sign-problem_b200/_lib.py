@@ -5,7 +5,7 @@ import os
 
 import torch
 
-from .build_extension import LIBRARY, build, ffibuilder
+from .build_extension import LIBRARY, ffibuilder
 
 ffi = ffibuilder
 _lib = None

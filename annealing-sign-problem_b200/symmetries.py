@@ -13,7 +13,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 import torch
 
-from ._lib import AspError, check, ffi, lib, ptr, require_cuda, stream
+from ._lib import check, ffi, lib, ptr, require_cuda, stream
 
 SYSTEMS_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "systems")
 

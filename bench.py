@@ -22,7 +22,6 @@ The annealing stage is timed separately on the same extracted model and reported
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time

@@ -16,7 +16,7 @@ tests/golden/make_golden.py -> tests/golden/*.npz -> tests/test_oracle.py.
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Optional, Tuple
+from typing import Tuple
 
 import numpy as np
 import scipy.sparse
