@@ -188,6 +188,26 @@ def cpu_anneal_once(capi, inputs, sweeps):
     return reps * sweeps * n / dt, cores, reps
 
 
+def cpu_live_path_once(inputs):
+    """The reference's LIVE extraction path (common.py:131-208: batched_apply -> searchsorted -> couplings -> scipy
+    0.5 (M + M^T) -> COO) in the oracle's numpy/scipy restatement, neighbour generation included -- the second CPU
+    figure BASELINE.md section 3 plans.  The reference's own file needs numba and /root/reference, neither of which is
+    on the GPU box, so this is labelled "port"."""
+    from oracle import live_path
+    from oracle.operator_np import OperatorNP, load_config, system_path
+
+    cfg = load_config(system_path(SYSTEM))
+    cfg["basis"]["symmetries"] = []
+    cfg["basis"]["spin_inversion"] = None
+    op_np = OperatorNP.from_config(cfg)
+    spins, psi = inputs[0], inputs[1]
+    t0 = time.perf_counter()
+    with np.errstate(divide="ignore"):
+        model = live_path.make_ising_model(spins, op_np, log_psi=np.log(psi.astype(np.complex128)))
+    dt = time.perf_counter() - t0
+    return int(model.exchange.nnz), dt
+
+
 def run_reference(args):
     """`--impl reference`: the reference's own CPU implementation of the path (cbits/build_matrix.c
     compiled where it lies, oracle/_ref) on a bounded sample of the same workload."""
@@ -581,6 +601,13 @@ def run_ours(args):
                "candidates_per_sec": inputs[2].shape[0] / dt,
                "anneal": {"value": flips_s, "unit": "proposals/s", "cores": cores, "kind": "port",
                           "sample": "oracle/anneal_port.c, %d replicas x 4 sweeps on the %d-spin sample model" % (reps, inputs[0].shape[0])}}
+        try:  # an extra figure: it must never cost the headline
+            nnz_l, dt_l = cpu_live_path_once(inputs)
+            cpu["live_path"] = {"value": nnz_l / dt_l, "unit": "couplings/s", "cores": 1, "kind": "port",
+                                "sample": "oracle/live_path.py (numpy/scipy restatement of common.py:131-208) on the same %d states, "
+                                          "neighbour generation included" % inputs[0].shape[0]}
+        except Exception as exc:  # noqa: BLE001
+            cpu["live_path"] = {"error": repr(exc)}
 
     if rank == 0:
         line = {
