@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(kTileRows) extract_sorted_kernel(const Extract
         if (pos < 0) continue;
         if (kFill) {
           a.indices[out + count] = static_cast<int32_t>(pos);
-          a.data[out + count] = mv.coef * (a_i * fabs(__ldg(&a.psi[pos])));
+          a.data[out + count] = __dmul_rn(__dmul_rn(mv.coef, fabs(__ldg(&a.psi[pos]))), a_i);  // (c |psi_j|) |psi_i|: common.py:71-82
         }
         ++count;
       }
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(kTileRows) extract_sorted_kernel(const Extract
           d += db.d[idx];
         }
         a.indices[out + count] = static_cast<int32_t>(row);
-        a.data[out + count] = d * (a_i * a_i);
+        a.data[out + count] = __dmul_rn(__dmul_rn(d, a_i), a_i);
       }
       ++count;
       for (int m = a.n_down; m < a.n_moves; ++m) {
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(kTileRows) extract_sorted_kernel(const Extract
         if (pos < 0) continue;
         if (kFill) {
           a.indices[out + count] = static_cast<int32_t>(pos);
-          a.data[out + count] = mv.coef * (a_i * fabs(__ldg(&a.psi[pos])));
+          a.data[out + count] = __dmul_rn(__dmul_rn(mv.coef, fabs(__ldg(&a.psi[pos]))), a_i);  // (c |psi_j|) |psi_i|: common.py:71-82
         }
         ++count;
       }

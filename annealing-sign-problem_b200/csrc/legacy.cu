@@ -229,4 +229,16 @@ uint64_t asp_build_matrix(uint64_t num_spins, asp_bits512 const spins[], int64_t
   return nnz;
 }
 
+// The reference's own symbol names (cbits/build_matrix.h:7-14): its literal cdef binds this library unchanged.
+static_assert(sizeof(ls_bits512) == sizeof(asp_bits512), "key types must match");
+uint64_t build_matrix(uint64_t num_spins, ls_bits512 const spins[], int64_t const *counts, double const *psi,
+                      ls_bits512 const *other_spins, double const *other_coeffs, int64_t const *other_counts,
+                      double const *other_psi, uint32_t *row_indices, uint32_t *col_indices, double *elements, double *field) {
+  return asp_build_matrix(num_spins, reinterpret_cast<asp_bits512 const *>(spins), counts, psi,
+                          reinterpret_cast<asp_bits512 const *>(other_spins), other_coeffs, other_counts, other_psi, row_indices,
+                          col_indices, elements, field);
+}
+
+void extract_signs(uint64_t num_spins, double const *psi, uint64_t *signs) { asp_extract_signs(num_spins, psi, signs); }
+
 }  // extern "C"

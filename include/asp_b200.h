@@ -61,6 +61,18 @@ uint64_t asp_build_matrix(uint64_t num_spins, asp_bits512 const spins[], int64_t
 
 void asp_extract_signs(uint64_t num_spins, double const *psi, uint64_t *signs);
 
+/* The same two under the reference's own names and key type (cbits/build_matrix.h:3-14), so that the
+ * reference's literal cdef (annealing_sign_problem/build_extension.py:5-21) binds this library with
+ * ffi.dlopen and no edit: build_matrix == asp_build_matrix, extract_signs == asp_extract_signs. */
+typedef struct ls_bits512 {
+  uint64_t words[8];
+} ls_bits512;
+uint64_t build_matrix(uint64_t num_spins, ls_bits512 const spins[], int64_t const *counts, double const *psi,
+                      ls_bits512 const *other_spins, double const *other_coeffs, int64_t const *other_counts,
+                      double const *other_psi, uint32_t *row_indices, uint32_t *col_indices, double *elements,
+                      double *field);
+void extract_signs(uint64_t num_spins, double const *psi, uint64_t *signs);
+
 /* Same two on DEVICE pointers with 64-bit keys (the reference's glue only fills words[0],
  * common.py:58-68,100), for the row block [row_begin, row_begin+num_rows) of the basis.
  * d_spins, d_psi: the FULL basis [n_total].  d_counts (NULL = all 1), d_offsets, d_field:
@@ -141,12 +153,18 @@ int asp_extract_csr(asp_operator const *op, uint64_t n_total, uint64_t const *d_
                     double const *d_psi, uint64_t row_begin, uint64_t num_rows, void *d_workspace,
                     size_t workspace_bytes, uint64_t capacity, int64_t *d_indptr,
                     int32_t *d_indices, double *d_data, uint64_t *h_nnz, void *stream);
-/* Test hooks.  Survivor-list entries per warp of the single-pass kernel (0 = automatic, 512):
- * small values force many exact-search rounds per tile.  Tuning: change the log2 size of the
- * Bloom filter / first-position table relative to the automatic choice, stage_a_mode 1 = test
- * move applicability lane by lane instead of on bit planes. */
+/* Test hooks.  Entries of one shared-memory hit list of a warp of the single-pass kernel
+ * (0 = automatic): small values force the spill path.  Tuning: bucket_bits_delta changes the
+ * log2 number of index buckets relative to the automatic choice (coarse buckets send most
+ * candidates to the exact search and make it bisect), diag_mode 1 = sum the diagonal bond by
+ * bond instead of in closed form. */
 void asp_debug_set_hit_list_capacity(int entries_per_warp);
-void asp_debug_set_extract_tuning(int filter_bits_delta, int table_bits_delta, int stage_a_mode);
+/* The operator's slots as the single-pass kernel walks them (|delta| ascending; a slot = the down
+ * and the up move that share one flip mask; need = ~0: no move in that direction).  Returns the
+ * number of slots; fills at most `capacity` entries of every non-NULL array. */
+uint32_t asp_debug_operator_slots(asp_operator const *op, uint32_t capacity, uint64_t *flip, uint64_t *mask,
+                                  uint64_t *need_down, uint64_t *need_up, double *coef_down, double *coef_up);
+void asp_debug_set_extract_tuning(int bucket_bits_delta, int reserved, int diag_mode);
 /* Measurement hook: when enabled, every launch of the single-pass extraction kernel is bracketed by
  * CUDA events on its own stream; the second call returns the device time of the LAST such launch
  * (milliseconds; synchronises on it; -1 if none). */

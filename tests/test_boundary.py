@@ -36,6 +36,38 @@ def test_library_exports_every_declared_symbol(asp):
     assert handle.asp_version() >= 100
 
 
+REFERENCE_CDEF = """
+    typedef struct ls_bits512 { uint64_t words[8]; } ls_bits512;
+    uint64_t build_matrix(uint64_t num_spins, ls_bits512 const spins[], int64_t const *counts, double const *psi,
+                          ls_bits512 const *other_spins, double const *other_coeffs, int64_t const *other_counts,
+                          double const *other_psi, uint32_t *row_indices, uint32_t *col_indices, double *elements,
+                          double *field);
+    void extract_signs(uint64_t num_spins, double const *psi, uint64_t *signs);
+"""
+
+
+def reference_cdef():
+    """The declarations the reference binds (annealing_sign_problem/build_extension.py:5-21): read from the reference
+    itself where it is present (this container), else the equivalent text above (the GPU box has no /root/reference)."""
+    path = "/root/reference/annealing_sign_problem/build_extension.py"
+    if os.path.exists(path):
+        m = re.search(r'ffibuilder\.cdef\(\s*"""(.*?)"""', open(path).read(), flags=re.S)
+        if m:
+            return m.group(1)
+    return REFERENCE_CDEF
+
+
+def test_reference_cdef_binds_the_library_unchanged(asp):
+    """Drop-in at the reference's own FFI seam: its cdef, fed to ffi.dlopen of OUR library, finds both symbols."""
+    from cffi import FFI
+
+    ffi = FFI()
+    ffi.cdef(reference_cdef())
+    handle = ffi.dlopen(os.path.join(ROOT, "annealing-sign-problem_b200", "libasp_b200.so"))
+    assert handle.build_matrix is not None and handle.extract_signs is not None
+    assert ffi.sizeof("ls_bits512") == 64
+
+
 def test_library_is_built_for_sm_100a():
     lib_path = os.path.join(ROOT, "annealing-sign-problem_b200", "libasp_b200.so")
     out = subprocess.run(["cuobjdump", "--list-elf", lib_path], capture_output=True, text=True)

@@ -309,6 +309,39 @@ def test_greedy_port_matches_plain_python_and_is_a_local_minimum(oracle_capi):
     assert abs(s @ (j @ s) + 2.0 * np.abs(w).sum()) < 1e-12 and spin[0] == 1
 
 
+def test_greedy_deviation_from_the_preserved_algorithm_is_bounded(oracle_capi):
+    """The product's greedy solver (csrc/greedy.cu == oracle/greedy_port.c bit for bit) deviates from the Python the
+    reference preserves at common.py:298-438 in two documented rules (single-spin joins, descent order).
+    oracle/greedy_reference.py follows the preserved rules exactly; on full-basis models with their exact ground
+    states the two agree where the greedy solution is exact, and ours is not worse on the frustrated SK instance
+    (measured: sk_16_3  preserved E = -58.2391, accuracy 0.942, overlap 0.881;  ours E = -59.8851, 0.978, 0.947)."""
+    from oracle.greedy_reference import greedy_reference
+    from oracle.operator_np import OperatorNP, ground_state, system_path
+
+    for system, exact_expected in [("heisenberg_kagome_16", True), ("sk_16_3", False)]:
+        op = OperatorNP.load(system_path(system))
+        e0, psi, _ = ground_state(op)
+        with np.errstate(divide="ignore"):
+            model = live_path.make_ising_model(op.basis.states, op, log_psi=np.log(psi.astype(np.complex128)))
+        j = model.exchange.tocsr()
+        j.sort_indices()
+        exact = np.where(psi > 0, 1.0, -1.0)
+        weights = psi ** 2
+
+        def stats(spin):
+            spin = spin.astype(np.float64)
+            p = np.mean(spin == exact)
+            return float(spin @ (j @ spin)), max(p, 1 - p), abs(np.sum(spin * exact * weights)) / weights.sum()
+
+        e_ref, acc_ref, ov_ref = stats(greedy_reference(j)[0])
+        e_ours, acc_ours, ov_ours = stats(oracle_capi.greedy(j.indptr, j.indices, j.data, None)[0])
+        if exact_expected:
+            assert abs(e_ref - e0) < 1e-9 and abs(e_ours - e0) < 1e-9 and acc_ref == 1.0 and acc_ours == 1.0
+        else:
+            assert e_ours <= e_ref + 1e-9 and acc_ours >= acc_ref and ov_ours >= ov_ref
+            assert e_ours >= e0 - 1e-9 and acc_ours > 0.95
+
+
 def test_sampling_front_end_restatement_is_the_reference(golden_dir):
     """N3: oracle restatements of monte_carlo_sampling / ground_state_to_log_coeff_fn /
     determine_exact_solution against outputs of the reference's own functions."""
