@@ -1,9 +1,8 @@
 // Kernels of the exchange step X1 and of the index over the sorted basis.  Included by
-// extract_fused.cu (after Record, index_sub / index_bits and the shared-memory helpers, inside namespace asp);
+// extract_fused.cu (after filter_hash / filter_bits and the shared-memory helpers, inside namespace asp);
 // the host side (fused_prepare*, asp_gather_index, asp_gather_blocks) lives there too.
 //
-//   index_block_kernel        index words (first position + presence bits per bucket) and {key, |psi|} records of a
-//                             block of the basis (2 keys per thread)
+//   index_block_kernel        first-position table + Bloom filter of a block of the basis (2 keys per thread)
 //   gather_index_kernel       X1 + index in one kernel, plain 16-byte loads over NVLink peer memory
 //   gather_index_tma_kernel   the same on the TMA: cp.async.bulk into shared memory, mbarrier pipeline (default)
 //   gather_copy_tma_kernel    X1 alone, bulk copies in both directions, one thread per CTA
@@ -14,7 +13,8 @@
 // One kernel replaces ncclAllGather(keys) + ncclAllGather(amplitudes) + the index pass: the blocks
 // of the sorted basis live in buffers the other processes of the node have mapped (CUDA IPC);
 // a thread pulls two consecutive keys and amplitudes of one block with 16-byte loads (several in
-// flight), writes the rank's private full copy and indexes the keys (index words + records) while the next loads travel.  Blocks are visited in ring order rank+1, rank+2, ... so that
+// flight), writes the rank's private full copy and indexes the keys (first-position table + Bloom
+// filter) while the next loads travel.  Blocks are visited in ring order rank+1, rank+2, ... so that
 // at any time the ranks pull from different peers.  A CTA waits (system-scope acquire) for the
 // "ready" flag of the blocks it touches; 10 s without it is a dead peer -> trap (never hang the box).
 constexpr int kGxMaxRanks = 16;
@@ -36,9 +36,9 @@ struct GatherArgs {
   double *psi;
   uint32_t n;
   uint64_t state_mask, num_buckets;
-  int bshift, oshift;
-  uint2 *index;  // [num_buckets + 1] {first position, presence bits}; NULL: copy only
-  Record *rec;   // [n] {key, |psi|}
+  int tshift, fshift;
+  uint32_t *starts;
+  uint2 *filter;
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
@@ -73,42 +73,39 @@ __device__ __forceinline__ unsigned long long ld_peer_u64(const void *p) {
   return v;
 }
 
-// First positions owed by key i (predecessor pk): buckets (bucket(pk), bucket(key)].
+// First-position table entries owed by key i (predecessor pk): buckets (bucket(pk), bucket(key)].
 __device__ __forceinline__ void index_table(const GatherArgs &a, uint64_t i, uint64_t key, bool has_prev, uint64_t pk) {
   const uint64_t last = a.num_buckets;
-  const uint64_t b = (key & ~a.state_mask) ? last : key >> a.bshift;
-  const uint64_t prev = has_prev ? ((pk & ~a.state_mask) ? last : pk >> a.bshift) + 1 : 0;
-  for (uint64_t k = prev; k <= b && k <= last; ++k) a.index[k].x = static_cast<uint32_t>(i);
+  const uint64_t b = (key & ~a.state_mask) ? last : key >> a.tshift;
+  const uint64_t prev = has_prev ? ((pk & ~a.state_mask) ? last : pk >> a.tshift) + 1 : 0;
+  for (uint64_t k = prev; k <= b && k <= last; ++k) a.starts[k] = static_cast<uint32_t>(i);
   if (i == a.n - 1)
-    for (uint64_t k = b + 1; k <= last; ++k) a.index[k].x = a.n;
+    for (uint64_t k = b + 1; k <= last; ++k) a.starts[k] = a.n;
 }
 
 // Private copy + index of one or two consecutive keys (global positions g, g + 1).
 __device__ __forceinline__ void emit_pair(const GatherArgs &a, uint64_t g, uint32_t cnt, ulonglong2 keys, ulonglong2 amps, bool has_prev,
                                           uint64_t pk) {
-  constexpr unsigned long long kAbs = 0x7FFFFFFFFFFFFFFFull;  // |psi|: clear the sign bit
   a.spins[g] = keys.x;
   reinterpret_cast<unsigned long long *>(a.psi)[g] = amps.x;
-  *reinterpret_cast<ulonglong2 *>(a.rec + g) = make_ulonglong2(keys.x, amps.x & kAbs);
   index_table(a, g, keys.x, has_prev, pk);
   const bool in0 = (keys.x & ~a.state_mask) == 0;
-  const uint64_t w0 = keys.x >> a.bshift;
-  uint32_t bits0 = index_bits(index_sub(keys.x, a.oshift));
+  const uint64_t w0 = keys.x >> a.fshift;
+  unsigned long long bits0 = filter_bits(filter_hash(keys.x));
   if (cnt == 2) {
     a.spins[g + 1] = keys.y;
     reinterpret_cast<unsigned long long *>(a.psi)[g + 1] = amps.y;
-    *reinterpret_cast<ulonglong2 *>(a.rec + g + 1) = make_ulonglong2(keys.y, amps.y & kAbs);
     index_table(a, g + 1, keys.y, true, keys.x);
     if ((keys.y & ~a.state_mask) == 0) {
-      const uint64_t w1 = keys.y >> a.bshift;
-      const uint32_t bits1 = index_bits(index_sub(keys.y, a.oshift));
+      const uint64_t w1 = keys.y >> a.fshift;
+      const unsigned long long bits1 = filter_bits(filter_hash(keys.y));
       if (in0 && w1 == w0)
-        bits0 |= bits1;  // sorted keys: neighbours often share a bucket -> one atomic for both
+        bits0 |= bits1;  // sorted keys: neighbours often share a filter word -> one atomic for both
       else
-        atomicOr(&a.index[w1].y, bits1);
+        atomicOr(reinterpret_cast<unsigned long long *>(a.filter + w1), bits1);
     }
   }
-  if (in0) atomicOr(&a.index[w0].y, bits0);
+  if (in0) atomicOr(reinterpret_cast<unsigned long long *>(a.filter + w0), bits0);
 }
 
 __global__ void __launch_bounds__(kGxThreads) gather_index_kernel(const GatherArgs a) {
@@ -395,61 +392,60 @@ __global__ void __launch_bounds__(32) gather_copy_tma_kernel(const GatherArgs a)
 
 // ---- X1, copy-engine variant: the blocks are pulled by cudaMemcpyAsync (the copy engines move 700 GB/s over
 // NVLink, more than SM loads reach) and indexed block by block on the SMs while later blocks still travel.
-// A thread indexes two consecutive keys of the block [b0, b1) and writes their {key, |psi|} records; the block's
-// first key owes its first-position entries to a key of ANOTHER block (which may not have arrived): the seam
-// kernel adds them at the end.
-__global__ void __launch_bounds__(256) index_block_kernel(const uint64_t *__restrict__ spins, const double *__restrict__ psi, uint32_t n,
-                                                          uint32_t b0, uint32_t b1, uint64_t state_mask, int bshift, int oshift,
-                                                          uint64_t num_buckets, uint2 *__restrict__ index, Record *__restrict__ rec) {
+// A thread indexes two consecutive keys of the block [b0, b1); the block's first key owes its table entries
+// to a key of ANOTHER block (which may not have arrived): the seam kernel adds them at the end.
+__global__ void __launch_bounds__(256) index_block_kernel(const uint64_t *__restrict__ spins, uint32_t n, uint32_t b0, uint32_t b1,
+                                                          uint64_t state_mask, int tshift, uint64_t num_buckets,
+                                                          uint32_t *__restrict__ starts, int fshift, uint2 *__restrict__ filter) {
   const uint32_t i = b0 + 2u * (blockIdx.x * 256u + threadIdx.x);
   if (i >= b1) return;
   const uint64_t last = num_buckets;
   const bool two = i + 1 < b1;
   const uint64_t k0 = spins[i], k1 = two ? spins[i + 1] : 0ull;
-  rec[i] = Record{k0, fabs(psi[i])};
-  if (two) rec[i + 1] = Record{k1, fabs(psi[i + 1])};
-  const uint64_t bk0 = (k0 & ~state_mask) ? last : k0 >> bshift;
+  const uint64_t bk0 = (k0 & ~state_mask) ? last : k0 >> tshift;
   if (i > b0 || i == 0) {
     uint64_t prev = 0;
     if (i > 0) {
       const uint64_t pk = spins[i - 1];
-      prev = ((pk & ~state_mask) ? last : pk >> bshift) + 1;
+      prev = ((pk & ~state_mask) ? last : pk >> tshift) + 1;
     }
-    for (uint64_t k = prev; k <= bk0 && k <= last; ++k) index[k].x = i;
+    for (uint64_t k = prev; k <= bk0 && k <= last; ++k) starts[k] = i;
   }
   uint64_t b_last = bk0;
   if (two) {
-    const uint64_t bk1 = (k1 & ~state_mask) ? last : k1 >> bshift;
-    for (uint64_t k = bk0 + 1; k <= bk1 && k <= last; ++k) index[k].x = i + 1;
+    const uint64_t bk1 = (k1 & ~state_mask) ? last : k1 >> tshift;
+    for (uint64_t k = bk0 + 1; k <= bk1 && k <= last; ++k) starts[k] = i + 1;
     b_last = bk1;
   }
   if ((two ? i + 1 : i) == n - 1)
-    for (uint64_t k = b_last + 1; k <= last; ++k) index[k].x = n;
+    for (uint64_t k = b_last + 1; k <= last; ++k) starts[k] = n;
   const bool in0 = (k0 & ~state_mask) == 0, in1 = two && (k1 & ~state_mask) == 0;
-  uint32_t bits0 = index_bits(index_sub(k0, oshift));
+  unsigned long long bits0 = filter_bits(filter_hash(k0));
+  const uint64_t w0 = k0 >> fshift;
   if (in1) {
-    const uint32_t bits1 = index_bits(index_sub(k1, oshift));
-    if (in0 && bk0 == (k1 >> bshift))
+    const uint64_t w1 = k1 >> fshift;
+    const unsigned long long bits1 = filter_bits(filter_hash(k1));
+    if (in0 && w1 == w0)
       bits0 |= bits1;
     else
-      atomicOr(&index[k1 >> bshift].y, bits1);
+      atomicOr(reinterpret_cast<unsigned long long *>(filter + w1), bits1);
   }
-  if (in0) atomicOr(&index[bk0].y, bits0);
+  if (in0) atomicOr(reinterpret_cast<unsigned long long *>(filter + w0), bits0);
 }
 
 struct SeamArgs {
   uint32_t first[kGxMaxRanks];  // first key of every non-empty block but the one that starts at 0 (n: none)
 };
 __global__ void index_seam_kernel(const uint64_t *__restrict__ spins, uint32_t n, const SeamArgs seams, int world, uint64_t state_mask,
-                                  int bshift, uint64_t num_buckets, uint2 *__restrict__ index) {
+                                  int tshift, uint64_t num_buckets, uint32_t *__restrict__ starts) {
   const int q = threadIdx.x;
   if (q >= world) return;
   const uint32_t i = seams.first[q];
   if (i == 0 || i >= n) return;
   const uint64_t last = num_buckets;
   const uint64_t key = spins[i], pk = spins[i - 1];
-  const uint64_t b = (key & ~state_mask) ? last : key >> bshift;
-  for (uint64_t k = ((pk & ~state_mask) ? last : pk >> bshift) + 1; k <= b && k <= last; ++k) index[k].x = i;
+  const uint64_t b = (key & ~state_mask) ? last : key >> tshift;
+  for (uint64_t k = ((pk & ~state_mask) ? last : pk >> tshift) + 1; k <= b && k <= last; ++k) starts[k] = i;
 }
 
 __global__ void wait_one_flag_kernel(const unsigned long long *flag, unsigned long long value) { wait_flag_or_trap(flag, value); }

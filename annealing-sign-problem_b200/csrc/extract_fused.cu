@@ -7,28 +7,25 @@
 //   _make_ising_model_compute_elements             (common.py:71-82)
 //   csr_matrix(...) + sort_indices                 (common.py:193-195)
 //
-// Organisation.  ~37 candidates are generated and looked up per row and only a
-// tenth of them are couplings, so the kernel is built around the cost of a MISS:
-//   * one lane = one row, one warp = a tile of 32 CONSECUTIVE rows of the sorted basis; the warp
-//     walks the operator's slots (operator.cuh: Slot, |delta|-sorted) together.  All lanes probe
-//     the same slot at the same time, so their candidates s_r ^ flip = s_r +- |delta| are an
-//     ascending run that lands in one short window of the index: the 32 probes of a step touch a
-//     handful of 128-byte lines instead of 32;
-//   * the index is ONE 8-byte word per bucket of the top key bits: {first position of the bucket,
-//     16 order-preserving + 16 hashed presence bits}.  Both bit positions are GF(2)-linear in the
-//     key, so a candidate costs two XORs on per-row / per-slot constants, one 8-byte load and two
-//     funnel shifts; ~98 % of the misses end there;
-//   * survivors are queued in shared memory and verified 32 at a time against the interleaved
-//     {key, |psi|} records: the word's order bits give the position inside the bucket, so a hit is
-//     normally ONE 16-byte load that also brings the amplitude's sector into L2;
-//   * hits of a row arrive outward from the diagonal (down images descending, up images
-//     ascending), so a hit's place in the row is its running count on its side; the tile's hit
-//     list stays in shared memory (overflow spills to an L2-resident scratch list);
-//   * a tile publishes its coupling count (never waits), fetches its CSR offset one tile late by a
-//     two-level decoupled look-back (tile counts inside a group of 32 tiles, group totals across
-//     groups) and writes indptr / indices / data in place.
-// Values are (coef * |psi_j|) * |psi_i| and (d * |psi_i|) * |psi_i|: the association of the reference's
-// live path (common.py:71-82), so pre-symmetrisation entries are bitwise the reference's.
+// The path is bound by instruction issue, not by HBM: ~37 candidates are
+// generated and looked up per row and only a tenth of them are couplings.  The kernel therefore
+// spends its instructions where the candidates are:
+//   A. applicability of all moves for the 32 rows of a warp is computed on bit planes (the
+//      32 x N key matrix transposed with warp shuffles): one LOP3 decides a move for 32 rows;
+//      transposed back, every lane holds the bit mask of the moves that apply to ITS row;
+//   B. every lane walks its own mask (all 32 lanes busy) and pre-sieves each candidate in an
+//      order-preserving blocked Bloom filter (one 8-byte word per candidate, two hashed bits:
+//      ~2 % false positives) -- nine misses in ten end here, after ~25 instructions;
+//   C. survivors are re-dealt evenly over the lanes, searched exactly (4-byte first-position
+//      table over the top key bits + a short scan of the keys) and appended, with their in-row
+//      rank, to the warp's hit list (global scratch, L2-resident);
+//   D. a tile (the 32 rows of a warp; warps never synchronise with each other) publishes its
+//      coupling count, obtains its CSR offset by decoupled look-back over earlier tiles (tiles
+//      are handed out by an atomic ticket, so a tile only waits for tiles that already run) and
+//      writes indptr / indices / data in place.
+// Every lane enumerates its moves in ascending key-delta order, so hits get ascending columns;
+// positions are exact indices into the sorted basis (bit-exact CSR) and values are
+// (coef * |psi_j|) * |psi_i|, the association of the reference's live path (common.py:71-82), as in extract.cu.
 #include "fused.cuh"
 
 namespace asp {
@@ -37,13 +34,14 @@ constexpr int kFxWarps = 8;
 constexpr int kFxThreads = kFxWarps * 32;
 constexpr int kFxTileRows = 32;  // a tile is the 32 rows of one warp
 static_assert(kFxTileRows == kFusedTileRows, "fused.cuh out of sync");
-constexpr uint32_t kFxMaxSlots = 1023;  // hit tag: (slot * 2 + down) 11 bits | row lane 5 bits | count on its side 16 bits
-constexpr int kFxUnroll = 4;            // slots probed together (index loads in flight per lane)
-constexpr int kFxQueue = 64;            // survivor queue entries per warp (verified 32 at a time)
-constexpr int kFxGroupTiles = 32;       // tiles per look-back group
+constexpr uint32_t kFxMaxMoves = 2046;  // tag layout: move 11 bits | row lane 5 bits | in-row rank 12 bits
+constexpr int kFxSurvSlotsDefault = 24; // survivor slots per lane between two exact-search rounds
 constexpr int kFxMaxCtasPerSM = 8;
+#ifndef ASP_FX_IN_FLIGHT
+#define ASP_FX_IN_FLIGHT 4  // filter words a lane has in flight in the candidate walk (4 or 2)
+#endif
 #ifndef ASP_FX_BACKOFF_NS
-#define ASP_FX_BACKOFF_NS 32  // first sleep of a look-back that finds an unpublished count
+#define ASP_FX_BACKOFF_NS 32  // first sleep of a look-back that finds an unpublished tile
 #endif
 #ifndef ASP_FX_LAG
 #define ASP_FX_LAG 1
@@ -52,64 +50,47 @@ constexpr int kFxMaxCtasPerSM = 8;
 #define ASP_FX_SCRATCH_MB 512
 #endif
 constexpr int kFxLag = ASP_FX_LAG;  // tiles a warp counts ahead of the tile whose CSR offset it fetches
-static_assert(kFxLag == 1, "the hit lists are double-buffered for a lag of one tile");
-constexpr size_t kFxScratchBudget = static_cast<size_t>(ASP_FX_SCRATCH_MB) << 20;  // spill lists never exceed this
+constexpr size_t kFxScratchBudget = static_cast<size_t>(ASP_FX_SCRATCH_MB) << 20;  // hit-list scratch never exceeds this
 
-constexpr unsigned long long kPrefixValid = 1ull << 63;
-constexpr int kGroupCountShift = 48;  // group word: tiles published << 48 | couplings
+constexpr unsigned long long kFlagAggregate = 1ull << 62;
+constexpr unsigned long long kFlagPrefix = 2ull << 62;
+constexpr unsigned long long kValueMask = (1ull << 62) - 1;
 
-#ifdef ASP_FX_DEBUG  // bounds checks of every computed address (compute-sanitizer is not available on the GPU pool)
-#define FX_CHECK(cond, code, value)                                                                                          \
-  do {                                                                                                                       \
-    if (!(cond)) {                                                                                                           \
-      printf("FX_CHECK %d failed: value %llu (block %d thread %d)\n", code, static_cast<unsigned long long>(value), blockIdx.x, \
-             threadIdx.x);                                                                                                   \
-      __trap();                                                                                                              \
-    }                                                                                                                        \
-  } while (0)
-#else
-#define FX_CHECK(cond, code, value) \
-  do {                              \
-  } while (0)
-#endif
-
-struct __align__(16) Record {  // the sorted basis as the kernel reads it: key and |psi| share a sector
-  uint64_t key;
-  double amp;
-};
-
-// Shared-memory layout.  CTA-wide slot tables, then one block per warp.
+// Shared-memory layout.  CTA-wide tables, then one block per warp; inside a warp's block the
+// bit planes (stage A) share their bytes with the survivor slots (stages B/C) and the apply
+// masks (A/B) with the row offsets and amplitudes of the write phase.
 struct FxLayout {
-  uint32_t probe, side, flip, coef, groups, diag;  // byte offsets of the tables
-  uint32_t tables;                                 // bytes of all tables
-  uint32_t w_queue, w_key, w_cnt, w_pend, w_list;  // byte offsets inside a warp's block
-  uint32_t list_entries;                           // entries of ONE of the two hit lists
+  uint32_t cand, flip, coef, desc, mask, need, groups, diag;  // byte offsets of the tables
+  uint32_t tables;                                            // bytes of all tables
+  uint32_t w_surv, w_amask, w_pre, w_cnt, w_pend;             // byte offsets inside a warp's block
   uint32_t per_warp;
 };
 
 struct FusedArgs {
   FxLayout layout;         // computed on the host: the kernel reads the offsets from constant memory
-  const Record *rec;       // [n_total] ascending, unique keys + |amplitude|
-  const uint2 *index;      // [2^bbits + 1] {first position of the bucket, presence bits}
-  int bshift, oshift;      // bucket = key >> bshift; order bit = (key >> oshift) & 15
+  const uint64_t *spins;   // [n_total] ascending, unique
+  const double *psi;
+  const uint32_t *starts;  // [2^tbits + 1] first position with key >= bucket << tshift
+  int tshift;
+  const uint2 *filter;     // [2^fbits] blocked Bloom filter, word = key >> fshift
+  int fshift;
   uint64_t state_mask;     // keys with bits outside are never candidates
   uint32_t n_total;
   uint64_t row_begin, num_rows, num_tiles;
-  const Slot *slots;
-  int n_slots, n_slots_padded;
+  const Move *moves;
+  int n_moves, n_down, n_words;
   const DiagBond *diag;
   int n_diag;
   const DiagGroup *groups; // closed form of the diagonal (n_groups < 0: use the bond loop)
   int n_groups, diag_scale;
   long long diag_c0;
-  uint2 *scratch;          // [gridDim.x * kFxWarps][2][scratch_per_warp] spilled hits {position, tag}
+  int surv_slots;          // survivor slots per lane
+  int planes_ok;           // every move mask has exactly two bits: stage A on bit planes
+  uint2 *scratch;          // [gridDim.x * kFxWarps][kFxLag + 1][scratch_per_warp] hit lists {position, tag}
   uint32_t scratch_per_warp;
-  uint32_t *tile_count;            // [num_tiles] couplings of a tile | 1 << 31 once published (zeroed)
-  unsigned long long *group_count; // [groups] tiles published << 48 | couplings (zeroed)
-  unsigned long long *group_prefix;// [groups] couplings before the group | 1 << 63 once known (zeroed)
-  unsigned int *ticket;            // zeroed
-  uint64_t num_buckets, num_groups, scratch_lists;  // (bounds, debug checks only)
-  uint64_t capacity;               // entries the caller's indices/data can hold
+  unsigned long long *status;  // [num_tiles] look-back words (zeroed)
+  unsigned int *ticket;        // zeroed
+  uint64_t capacity;           // entries the caller's indices/data can hold
   int64_t *indptr;
   int32_t *indices;
   double *data;
@@ -118,25 +99,18 @@ struct FusedArgs {
   const unsigned long long *base_in;   // couplings emitted by earlier row chunks (NULL = 0)
 };
 
-__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p) {
   unsigned long long v;
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
+__device__ __forceinline__ void st_status(unsigned long long *p, unsigned long long v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
-  uint32_t v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_relaxed_u32(uint32_t *p, uint32_t v) {
-  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 
-// GF(2)-LINEAR mix of a key: hash(s ^ flip) = hash(s) ^ hash(flip), so the kernel hashes every row once
-// and every slot once instead of every candidate.
+// Two hashed bit positions of a key inside its filter word: bits 0..4 (first half-word) and bits
+// 8..12 (second half-word) of a GF(2)-LINEAR mix, so hash(s ^ flip) = hash(s) ^ hash(flip): the
+// kernel hashes every row once and every move once instead of every candidate.
 __host__ __device__ __forceinline__ uint32_t filter_hash(uint64_t key) {
   const uint32_t lo = static_cast<uint32_t>(key), hi = static_cast<uint32_t>(key >> 32);
   uint32_t y = lo ^ ((hi << 7) | (hi >> 25));
@@ -147,23 +121,111 @@ __host__ __device__ __forceinline__ uint32_t filter_hash(uint64_t key) {
   y ^= y >> 17;
   return y;
 }
-// The two presence-bit positions of a key inside its bucket's word, packed as ord | hsh << 8:
-// ord = the four key bits below the bucket bits (order-preserving inside the bucket), hsh = four hashed bits.
-// Both are linear in the key.  (The probing row adds 16 << 8: the hashed bit lives in the upper half-word.)
-__host__ __device__ __forceinline__ uint32_t index_sub(uint64_t key, int oshift) {
-  return (static_cast<uint32_t>(key >> oshift) & 15u) | ((filter_hash(key) & 15u) << 8);
-}
-__host__ __device__ __forceinline__ uint32_t index_bits(uint32_t sub) { return (1u << (sub & 15u)) | (1u << (16u + ((sub >> 8) & 15u))); }
 
-// Shared memory through 32-bit addresses.
-__device__ __forceinline__ uint32_t smem_addr(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ uint4 lds_table_v4(uint32_t addr) {  // read-only tables: free to schedule
-  uint4 v;
-  asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+// The two bits as one 64-bit word (uint2 {x, y} little endian): the index kernels set them with ONE
+// 64-bit atomic -- the index build is bound by L2 atomic throughput.
+__host__ __device__ __forceinline__ unsigned long long filter_bits(uint32_t h) {
+  return (1ull << (h & 31u)) | (1ull << (32u + ((h >> 8) & 31u)));
+}
+
+// Loads that bypass L1 allocation: filter words, table entries, keys and gathered amplitudes are
+// touched once per SM, while the warp's hit list (written, then read back) should stay in L1.
+#ifndef ASP_FX_STREAM_FILTER
+#define ASP_FX_STREAM_FILTER 0
+#endif
+#ifndef ASP_FX_STREAM_SEARCH
+#define ASP_FX_STREAM_SEARCH 0
+#endif
+#ifndef ASP_FX_STREAM_PSI
+#define ASP_FX_STREAM_PSI 0
+#endif
+__device__ __forceinline__ uint2 ldg_filter_u2(const uint2 *p) {
+#if ASP_FX_STREAM_FILTER
+  uint2 v;
+  asm("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
   return v;
+#else
+  return __ldg(p);
+#endif
+}
+__device__ __forceinline__ uint32_t ldg_stream_u32(const uint32_t *p) {
+#if ASP_FX_STREAM_SEARCH
+  uint32_t v;
+  asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
+__device__ __forceinline__ uint64_t ldg_stream_u64(const uint64_t *p) {
+#if ASP_FX_STREAM_SEARCH
+  uint64_t v;
+  asm("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
+__device__ __forceinline__ double ldg_stream_f64(const double *p) {
+#if ASP_FX_STREAM_PSI
+  double v;
+  asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
+// Shared memory through 32-bit addresses (the walk of stage B keeps running addresses).
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));  // ordered with the other volatile asm, transparent to plain loads
+  return v;
+}
+__device__ __forceinline__ uint2 lds_table_u2(uint32_t addr) {  // read-only tables: free to schedule
+  uint2 v;
+  asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(static_cast<unsigned short>(v)));
 }
 
 #include "exchange_kernels.cuh"  // index + X1 kernels (gather_index_*, gather_copy_tma_kernel, index_block_kernel)
+
+// Position of c (< 2^number_spins) in the sorted basis, or -1.
+__device__ __forceinline__ int32_t search_one(const FusedArgs &a, uint64_t c) {
+  const uint32_t *bucket = a.starts + (c >> a.tshift);
+  uint32_t lo = ldg_stream_u32(bucket), hi = ldg_stream_u32(bucket + 1);
+  if (hi - lo > 16) {  // pathological bucket: bisect down to a short scan
+    do {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      if (ldg_stream_u64(&a.spins[mid]) < c)
+        lo = mid + 1;
+      else
+        hi = mid + 1;
+    } while (hi - lo > 8);
+  }
+  for (; lo < hi; lo += 2) {  // two keys per step (independent loads)
+    const uint64_t k0 = ldg_stream_u64(&a.spins[lo]);
+    const bool second = lo + 1 < hi;
+    const uint64_t k1 = second ? ldg_stream_u64(&a.spins[lo + 1]) : 0ull;
+    if (k0 >= c) return k0 == c ? static_cast<int32_t>(lo) : -1;
+    if (second && k1 >= c) return k1 == c ? static_cast<int32_t>(lo + 1) : -1;
+  }
+  return -1;
+}
+
+// 32 x 32 bit-matrix transpose across a warp: result bit k of lane l = bit l of lane k's x.
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, uint32_t lane) {
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+    const uint32_t low = d == 16 ? 0x0000FFFFu : d == 8 ? 0x00FF00FFu : d == 4 ? 0x0F0F0F0Fu : d == 2 ? 0x33333333u : 0x55555555u;
+    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, d);
+    x = (lane & d) ? ((x & ~low) | ((y >> d) & low)) : ((x & low) | ((y << d) & ~low));
+  }
+  return x;
+}
 
 // Diagonal matrix element of one basis word: bond contributions summed in (term, bond) order.
 __device__ __forceinline__ double diagonal_element(uint64_t s, const DiagBond *s_diag, int n_diag) {
@@ -186,7 +248,7 @@ __device__ __forceinline__ double diagonal_closed_form(uint64_t s, const DiagGro
   return scalbn(static_cast<double>(acc), -scale);
 }
 
-__host__ __device__ inline FxLayout fx_layout(int n_slots_padded, int n_groups, int n_diag, uint32_t list_entries) {
+__host__ __device__ inline FxLayout fx_layout(int n_moves, int n_words, int n_groups, int n_diag, int planes_ok, int surv_slots) {
   FxLayout L;
   uint32_t off = 0;
   auto take = [&](uint32_t bytes) {
@@ -194,64 +256,72 @@ __host__ __device__ inline FxLayout fx_layout(int n_slots_padded, int n_groups, 
     off += (bytes + 15u) & ~15u;
     return at;
   };
-  const uint32_t ns = static_cast<uint32_t>(n_slots_padded);
-  L.probe = take(ns * 32u);  // {flip >> bshift, sub(flip), mask lo/hi, need_down lo/hi, need_down ^ need_up lo/hi}
-  L.side = take(ns * 16u);   // {mask, need_down}
-  L.flip = take(ns * 8u);
-  L.coef = take(ns * 16u);   // [slot * 2 + down]
+  L.cand = take(static_cast<uint32_t>(n_words) * 32u * 8u);  // {flip >> fshift, hash(flip)} per move, padded to whole words
+  L.flip = take(static_cast<uint32_t>(n_moves) * 8u);
+  L.coef = take(static_cast<uint32_t>(n_moves) * 8u);
+  L.desc = take(planes_ok ? static_cast<uint32_t>(n_words) * 128u : 0u);
+  L.mask = take(planes_ok ? 0u : static_cast<uint32_t>(n_moves) * 8u);
+  L.need = take(planes_ok ? 0u : static_cast<uint32_t>(n_moves) * 8u);
   L.groups = take(n_groups >= 0 ? static_cast<uint32_t>(n_groups) * 16u : 0u);
   L.diag = take(n_groups >= 0 ? 0u : static_cast<uint32_t>(n_diag) * static_cast<uint32_t>(sizeof(DiagBond)));
   L.tables = off;
   off = 0;
-  L.w_queue = take(kFxQueue * 16u);  // survivors {start, bits, sub, tag} | write phase: row offsets [32], down counts [32], |psi| [32]
-  L.w_key = take(32u * 8u);          // the tile's keys
-  L.w_cnt = take(64u * 4u);          // hits so far per row: up [32], down [32]
-  L.w_pend = take(36u * 4u);         // waiting tile: packed row counts [32], tile lo/hi, list length, spilled length
-  L.w_list = take(2u * list_entries * 8u);  // two hit lists {position, tag}: the tile being counted and the waiting one
-  L.list_entries = list_entries;
+  const uint32_t surv_bytes = static_cast<uint32_t>(surv_slots) * 64u;
+  L.w_surv = take(surv_bytes > 256u ? surv_bytes : 256u);                              // | planes u32[64]
+  L.w_amask = take(n_words * 128u > 384u ? static_cast<uint32_t>(n_words) * 128u : 384u);  // | abs_psi f64[32], row_off u32[32]
+  L.w_pre = take(64u * 4u);  // exclusive prefix of survivor counts [32] | owner board [32]
+  L.w_cnt = take(32u * 4u);
+  L.w_pend = take(static_cast<uint32_t>(kFxLag) * 36u * 4u);  // per waiting tile: packed row counts [32], tile lo/hi, list length
   L.per_warp = off;
   return L;
 }
 
 #ifndef ASP_FX_MIN_CTAS
-#define ASP_FX_MIN_CTAS 4
+#define ASP_FX_MIN_CTAS 6
 #endif
-template <bool kWide>  // keys wider than 32 bits
 __global__ void __launch_bounds__(kFxThreads, ASP_FX_MIN_CTAS) extract_csr_kernel(const FusedArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const FxLayout &L = a.layout;
-  uint4 *s_probe = reinterpret_cast<uint4 *>(smem_raw + L.probe);
-  ulonglong2 *s_side = reinterpret_cast<ulonglong2 *>(smem_raw + L.side);
+  uint2 *s_cand = reinterpret_cast<uint2 *>(smem_raw + L.cand);
   uint64_t *s_flip = reinterpret_cast<uint64_t *>(smem_raw + L.flip);
   double *s_coef = reinterpret_cast<double *>(smem_raw + L.coef);
+  uint32_t *s_desc = reinterpret_cast<uint32_t *>(smem_raw + L.desc);  // site i | site j << 8 | need_i << 16 | need_j << 17 | valid << 18
+  uint64_t *s_mask = reinterpret_cast<uint64_t *>(smem_raw + L.mask);
+  uint64_t *s_need = reinterpret_cast<uint64_t *>(smem_raw + L.need);
   DiagGroup *s_groups = reinterpret_cast<DiagGroup *>(smem_raw + L.groups);
   DiagBond *s_diag = reinterpret_cast<DiagBond *>(smem_raw + L.diag);
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
   unsigned char *const wbase = smem_raw + L.tables + L.per_warp * warp;
-  uint4 *const w_queue = reinterpret_cast<uint4 *>(wbase + L.w_queue);
-  uint32_t *const w_row_off = reinterpret_cast<uint32_t *>(wbase + L.w_queue);        // write phase (the queue is empty then)
-  uint32_t *const w_down = reinterpret_cast<uint32_t *>(wbase + L.w_queue + 128);
-  double *const w_abs_psi = reinterpret_cast<double *>(wbase + L.w_queue + 256);
-  uint64_t *const w_key = reinterpret_cast<uint64_t *>(wbase + L.w_key);
+  uint32_t *const w_planes = reinterpret_cast<uint32_t *>(wbase + L.w_surv);
+  uint16_t *const w_surv = reinterpret_cast<uint16_t *>(wbase + L.w_surv);
+  uint32_t *const w_amask = reinterpret_cast<uint32_t *>(wbase + L.w_amask);
+  double *const w_abs_psi = reinterpret_cast<double *>(wbase + L.w_amask);
+  uint32_t *const w_row_off = reinterpret_cast<uint32_t *>(wbase + L.w_amask + 256);
+  uint32_t *const w_pre = reinterpret_cast<uint32_t *>(wbase + L.w_pre);
   uint32_t *const w_cnt = reinterpret_cast<uint32_t *>(wbase + L.w_cnt);
   uint32_t *const w_pend = reinterpret_cast<uint32_t *>(wbase + L.w_pend);
-  uint2 *const w_lists = reinterpret_cast<uint2 *>(wbase + L.w_list);
-  const uint32_t list_cap = L.list_entries;
 
-  for (int k = threadIdx.x; k < a.n_slots_padded; k += kFxThreads) {
-    // padding slots never apply: (s & 0) ^ ~0 is neither 0 nor need_down ^ need_up = 0
-    Slot sl{0ull, 0ull, ~0ull, ~0ull, 0.0, 0.0};
-    if (k < a.n_slots) sl = a.slots[k];
-    const uint64_t dd = sl.need_down ^ sl.need_up;
-    s_probe[2 * k] = make_uint4(static_cast<uint32_t>(sl.flip >> a.bshift), index_sub(sl.flip, a.oshift), static_cast<uint32_t>(sl.mask),
-                                static_cast<uint32_t>(sl.mask >> 32));
-    s_probe[2 * k + 1] = make_uint4(static_cast<uint32_t>(sl.need_down), static_cast<uint32_t>(sl.need_down >> 32), static_cast<uint32_t>(dd),
-                                    static_cast<uint32_t>(dd >> 32));
-    s_side[k] = make_ulonglong2(sl.mask, sl.need_down);
-    s_flip[k] = sl.flip;
-    s_coef[2 * k] = sl.coef_up;
-    s_coef[2 * k + 1] = sl.coef_down;
+  for (int k = threadIdx.x; k < a.n_words * 32; k += kFxThreads) {
+    uint2 cand = make_uint2(0u, 0u);
+    uint32_t desc = 0;
+    if (k < a.n_moves) {
+      const Move mv = a.moves[k];
+      s_flip[k] = mv.flip;
+      s_coef[k] = mv.coef;
+      cand = make_uint2(static_cast<uint32_t>(mv.flip >> a.fshift), filter_hash(mv.flip));
+      if (a.planes_ok) {
+        const int i = __ffsll(static_cast<long long>(mv.mask)) - 1;
+        const int j = 63 - __clzll(static_cast<long long>(mv.mask));
+        desc = static_cast<uint32_t>(i) | (static_cast<uint32_t>(j) << 8) | (static_cast<uint32_t>((mv.need >> i) & 1) << 16) |
+               (static_cast<uint32_t>((mv.need >> j) & 1) << 17) | (1u << 18);
+      } else {
+        s_mask[k] = mv.mask;
+        s_need[k] = mv.need;
+      }
+    }
+    s_cand[k] = cand;
+    if (a.planes_ok) s_desc[k] = desc;
   }
   if (a.n_groups >= 0) {
     for (int k = threadIdx.x; k < a.n_groups; k += kFxThreads) s_groups[k] = a.groups[k];
@@ -259,18 +329,20 @@ __global__ void __launch_bounds__(kFxThreads, ASP_FX_MIN_CTAS) extract_csr_kerne
     for (int k = threadIdx.x; k < a.n_diag; k += kFxThreads) s_diag[k] = a.diag[k];
   }
   __syncthreads();  // tables loaded; from here on the warps run independently
-  FX_CHECK((static_cast<uint64_t>(blockIdx.x) * kFxWarps + warp) * 2 + 1 < a.scratch_lists, 13, blockIdx.x);
-  uint2 *const my_spill = a.scratch + (static_cast<size_t>(blockIdx.x) * kFxWarps + warp) * 2 * a.scratch_per_warp;  // one spill list per hit list
-  const uint32_t probe_base = smem_addr(s_probe);
-  const uint32_t queue_base = smem_addr(w_queue);
-  const uint32_t lane_tag = lane << 11;
+  uint2 *const my_lists = a.scratch + (static_cast<size_t>(blockIdx.x) * kFxWarps + warp) * (kFxLag + 1) * a.scratch_per_warp;  // kFxLag + 1 hit lists
+  const uint32_t slots = static_cast<uint32_t>(a.surv_slots);
+  const uint32_t cand_base = smem_addr(s_cand);
+  const uint32_t amask_base = smem_addr(w_amask) + lane * 4u;
+  const uint32_t surv_base = smem_addr(w_surv) + lane * 2u;
+  const uint32_t surv_limit = surv_base + (slots >= 8u ? slots - 4u : 0u) * 64u;  // fill level checked every 4 candidates
 
-  // Lag: a warp counts its NEXT tile before it fetches the CSR offset of the tile it counted last.
-  // The offset needs every earlier tile's count, and a warp that finished early would otherwise spin
-  // for the slowest of its predecessors (the SM's warp arbiter is not fair, so some warps ARE much
-  // slower); by the time the next tile is counted they are done.  Counts are published right after
-  // counting and never wait for anything, so the scheme cannot deadlock.  The waiting tile keeps its
-  // hit list in the other half of the warp's list memory and its row counts in w_pend.
+  // Lag: a warp runs stages A-C of its next kFxLag tiles before it fetches the CSR offset of a
+  // tile it has counted.  The offset needs every earlier tile's count, and a warp that finished
+  // early would otherwise spin for the slowest of its predecessors (the SM's warp arbiter is not
+  // fair, so some warps ARE much slower); by the time the next tiles are counted they are done.
+  // (Counts are published right after stage C and never wait for anything, so the scheme cannot
+  // deadlock.)  Waiting tiles keep their hit list in one of kFxLag + 1 scratch lists and their row
+  // counts in shared memory.
   uint32_t taken = 0, waiting = 0;  // tiles this warp has counted / of those, not yet written (warp-uniform)
   for (;;) {
     // a tile = the 32 rows of one warp; tiles are handed out in order by an atomic ticket
@@ -279,171 +351,195 @@ __global__ void __launch_bounds__(kFxThreads, ASP_FX_MIN_CTAS) extract_csr_kerne
     const uint64_t tile = __shfl_sync(0xffffffffu, ticket, 0);
     const bool have_tile = tile < a.num_tiles;
     if (!have_tile && waiting == 0) break;
-    uint2 *const my_list = w_lists + static_cast<size_t>(taken & 1u) * list_cap;
-    uint2 *const my_spill_list = my_spill + static_cast<size_t>(taken & 1u) * a.scratch_per_warp;
-    uint32_t packed_cnt = 0, list_count = 0, spilled = 0;
+    uint2 *const my_list = my_lists + static_cast<size_t>(taken % (kFxLag + 1)) * a.scratch_per_warp;
+    uint32_t packed_cnt = 0, list_count = 0;
     if (have_tile) {
-      const uint64_t r = tile * kFxTileRows + lane;
-      const bool live = r < a.num_rows;
-      const uint64_t row = a.row_begin + r;
-      uint64_t s = 0ull;
-      if (live) s = __ldg(&a.rec[row].key);
-      const uint32_t s_lo = static_cast<uint32_t>(s), s_hi = static_cast<uint32_t>(s >> 32);
-      const bool generates = live && (s & ~a.state_mask) == 0;  // keys wider than the word have no images in the basis
-      // per-row halves of the probe: bucket index and the two presence-bit positions (hashed one in the upper half-word)
-      const uint32_t s_idx = static_cast<uint32_t>(s >> a.bshift);
-      const uint32_t s_sub = index_sub(s, a.oshift) | (16u << 8);
-      w_key[lane] = s;
-      w_cnt[lane] = 0;
-      w_cnt[32 + lane] = 0;
+    const uint64_t r = tile * kFxTileRows + lane;
+    const bool live = r < a.num_rows;
+    const uint64_t row = a.row_begin + r;
+    const uint64_t s = live ? __ldg(&a.spins[row]) : 0ull;
+    const uint32_t s_lo = static_cast<uint32_t>(s), s_hi = static_cast<uint32_t>(s >> 32);
+    const bool generates = live && (s & ~a.state_mask) == 0;  // keys wider than the word have no images in the basis
+
+    // =========================== A: which moves apply to which row ===========================
+    if (a.planes_ok) {
+      const uint32_t gen_mask = __ballot_sync(0xffffffffu, generates);
+      w_planes[lane] = transpose32(s_lo, lane);
+      w_planes[32 + lane] = transpose32(s_hi, lane);
       __syncwarp();
+      for (int w = 0; w < a.n_words; ++w) {
+        const uint32_t desc = s_desc[w * 32 + lane];
+        const uint32_t pi = w_planes[desc & 63u], pj = w_planes[(desc >> 8) & 63u];
+        const uint32_t xi = ((desc >> 16) & 1u) - 1u, xj = ((desc >> 17) & 1u) - 1u;  // need 1 -> 0, need 0 -> ~0
+        uint32_t app = (pi ^ xi) & (pj ^ xj) & gen_mask;                              // rows this lane's move applies to
+        if (!(desc & (1u << 18))) app = 0;
+        w_amask[w * 32 + lane] = transpose32(app, lane);                              // moves that apply to this lane's row
+      }
+    } else {
+      for (int w = 0; w < a.n_words; ++w) {
+        uint32_t bits = 0;
+        const int m_end = min(32, a.n_moves - w * 32);
+        for (int k = 0; k < m_end; ++k)
+          if ((s & s_mask[w * 32 + k]) == s_need[w * 32 + k]) bits |= 1u << k;
+        w_amask[w * 32 + lane] = generates ? bits : 0u;
+      }
+    }
+    w_cnt[lane] = 0;
+    __syncwarp();  // planes are dead from here: their bytes become the survivor slots
 
-      uint32_t q_head = 0, q_count = 0;  // survivor queue (ring of kFxQueue entries)
+    // =========================== B + C: sieve, search, record ================================
+    uint32_t surv_addr = surv_base;   // next free survivor slot of this lane
 
-      // Verify up to 32 queued survivors against the records, rank the hits, append them to the hit list.
-      auto verify = [&](uint32_t batch) {
-        const bool valid = lane < batch;
-        const uint4 q = w_queue[(q_head + lane) & (kFxQueue - 1)];
-        const uint32_t tag = valid ? q.w : 0u;  // entries beyond the batch hold stale bytes
-        const uint32_t slot = tag & 0x7FFu, src = (tag >> 11) & 31u;
-#ifdef ASP_FX_DEBUG
-        if (valid && slot >= static_cast<uint32_t>(a.n_slots)) {
-          printf("queue garbage: block %d warp %u lane %u taken %u q_head %u q_count %u batch %u entry %08x %08x %08x %08x\n", blockIdx.x, warp, lane, taken,
-                 q_head, q_count, batch, q.x, q.y, q.z, q.w);
-          __trap();
-        }
-#endif
-        const ulonglong2 side = s_side[slot];
-        const uint64_t key = w_key[src];
-        const uint64_t c = key ^ s_flip[slot];
-        const uint32_t down = (key & side.x) == side.y ? 1u : 0u;
-        // the order bits below the candidate's own: that many keys of the bucket precede it (at least)
-        uint32_t p = q.x + __popc(q.y & ((1u << (q.z & 15u)) - 1u));
-        bool hit = false;
-        FX_CHECK(!valid || (c >> a.bshift) < a.num_buckets, 2, c);
-        if (valid && p < a.n_total) {
-          uint64_t k = __ldg(&a.rec[p].key);
-          if (k < c) {
-            // keys of the bucket share an order bit (rare), or the bucket is crowded (clustered bases):
-            // lower bound between the guess and the first position of the next bucket
-            uint32_t lo = p + 1, hi = __ldg(&a.index[(c >> a.bshift) + 1].x);
-            FX_CHECK(hi <= a.n_total, 3, hi);
-            while (lo < hi) {
-              const uint32_t mid = lo + ((hi - lo) >> 1);
-              if (__ldg(&a.rec[mid].key) < c)
-                lo = mid + 1;
-              else
-                hi = mid;
-            }
-            p = lo;
-            k = p < a.n_total ? __ldg(&a.rec[p].key) : ~c;
-          }
-          hit = k == c;
-        }
+    // C: deal the waiting survivors evenly over the lanes, search them exactly, record the hits
+    auto flush = [&]() {
+      const uint32_t h = (surv_addr - surv_base) >> 6;
+      uint32_t incl = h;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+      const uint32_t excl = incl - h;
+      w_pre[lane] = excl;
+      uint32_t carry = 0;  // lane that owns the survivor just before this batch
+      for (uint32_t base = 0; base < total; base += 32) {
+        // the lane whose survivors include number base + lane: lanes that START inside the batch
+        // leave their index at the start position, everyone looks up the nearest start at or below
+        const uint32_t start = excl - base;
+        const bool starts_here = h != 0 && start < 32u;
+        const uint32_t heads = __reduce_or_sync(0xffffffffu, starts_here ? 1u << start : 0u);
+        if (starts_here) w_pre[32 + start] = lane;  // w_pre[32..] doubles as the owner board (entries 32..63)
+        __syncwarp();
+        const uint32_t e = base + lane;
+        const bool valid = e < total;
+        const uint32_t at_or_below = heads & (0xFFFFFFFFu >> (31u - lane));
+        const uint32_t src = at_or_below ? w_pre[32 + (31 - __clz(at_or_below))] : carry;
+        carry = __shfl_sync(0xffffffffu, src, 31);
+        const uint32_t m = valid ? (static_cast<uint32_t>(w_surv[(e - w_pre[src]) * 32 + src]) - (cand_base >> 3)) & 0xFFFFu : 0u;
+        const uint64_t s_src = (static_cast<uint64_t>(__shfl_sync(0xffffffffu, s_hi, src)) << 32) | __shfl_sync(0xffffffffu, s_lo, src);
+        int32_t pos = -1;
+        if (valid) pos = search_one(a, s_src ^ s_flip[m]);
+        const bool hit = pos >= 0;
         const uint32_t hits = __ballot_sync(0xffffffffu, hit);
         if (hits) {
-          if (list_count + 32u > list_cap) {  // (warp-uniform) no room for a full batch: spill the list to the scratch list
-            FX_CHECK(spilled + list_count <= a.scratch_per_warp, 4, spilled + list_count);
-            for (uint32_t k = lane; k < list_count; k += 32) my_spill_list[spilled + k] = my_list[k];
-            spilled += list_count;
-            list_count = 0;
-            __syncwarp();
-          }
-          // hits of one row on one side arrive outward from the diagonal: the count so far is the place.
-          // Every lane takes part in the match and the barrier (a partial-mask barrier inside the divergent
-          // branch can pair up with the full-mask barriers of the lanes outside it).
-          const uint32_t who = hit ? (src | (down << 5)) : (64u + lane);
-          const uint32_t peers = __match_any_sync(0xffffffffu, who);  // same row and side in this batch (ascending slot order by lane)
-          const uint32_t before = __popc(peers & lt_mask);
-          const uint32_t sofar = hit ? w_cnt[who] : 0u;
-          __syncwarp();
+          const bool below = static_cast<int>(m) < a.n_down;
+          const uint32_t belows = __ballot_sync(0xffffffffu, hit && below);
           if (hit) {
-            if (before == 0) w_cnt[who] = sofar + __popc(peers);
-            FX_CHECK(list_count + __popc(hits & lt_mask) < list_cap, 5, list_count);
-            FX_CHECK(sofar + before < 1024u, 6, sofar + before);
-            my_list[list_count + __popc(hits & lt_mask)] = make_uint2(p, (slot * 2u + down) | (src << 11) | ((sofar + before) << 16));
+            const uint32_t peers = __match_any_sync(hits, src);  // hits of the same row in this batch (ascending move order by lane)
+            const uint32_t packed = w_cnt[src];
+            __syncwarp(hits);
+            const uint32_t before = __popc(peers & lt_mask);
+            if (before == 0) w_cnt[src] = packed + __popc(peers) + (__popc(peers & belows) << 16);
+            const uint32_t rank = (packed & 0xFFFFu) + before + (below ? 0u : 1u);  // the diagonal sits after the negative deltas
+            my_list[list_count + __popc(hits & lt_mask)] = make_uint2(static_cast<uint32_t>(pos), m | (src << 11) | (rank << 16));
           }
           list_count += __popc(hits);
         }
         __syncwarp();
-        q_head += batch;
-        q_count -= batch;
-      };
+      }
+      surv_addr = surv_base;
+    };
 
-      // The probe loop: kFxUnroll slots at a time, their index words in flight together.
-      for (int g0 = 0; g0 < a.n_slots_padded; g0 += kFxUnroll) {
-        uint2 word[kFxUnroll];
-        uint32_t sub[kFxUnroll];
-#pragma unroll
-        for (int j = 0; j < kFxUnroll; ++j) {
-          const uint32_t at = probe_base + static_cast<uint32_t>(g0 + j) * 32u;
-          const uint4 p0 = lds_table_v4(at), p1 = lds_table_v4(at + 16u);
-          // u = (s & mask) ^ need_down: 0 when the down move applies, need_down ^ need_up when the up move does
-          const uint32_t u_lo = (s_lo & p0.z) ^ p1.x;
-          const uint32_t u_hi = kWide ? (s_hi & p0.w) ^ p1.y : 0u;
-          const bool applies = (((u_lo | u_hi) == 0u) || (((u_lo ^ p1.z) | (kWide ? (u_hi ^ p1.w) : 0u)) == 0u)) && generates;
-          sub[j] = s_sub ^ p0.y;
-          word[j] = make_uint2(0u, 0u);
-          FX_CHECK(!applies || (s_idx ^ p0.x) < a.num_buckets, 7, s_idx ^ p0.x);
-          if (applies) word[j] = __ldg(&a.index[s_idx ^ p0.x]);
+    {
+      // B: every lane walks the set bits of its own mask words.  A candidate needs its filter
+      // word (index = (s >> fshift) ^ (flip >> fshift)) and its hash (= hash(s) ^ hash(flip)):
+      // one 8-byte table read and two XORs.
+      const uint32_t s_idx = static_cast<uint32_t>(s >> a.fshift), s_hash = filter_hash(s);
+      uint32_t amask_addr = amask_base, tab_addr = cand_base;
+      const uint32_t amask_last = amask_base + (a.n_words > 0 ? a.n_words - 1 : 0) * 128u;
+      uint32_t cur = a.n_words ? lds_u32(amask_addr) : 0u;
+      // first half of a step: next set bit -> table entry -> filter word on its way
+      auto fetch = [&](uint32_t &entry_addr, uint32_t &hsh, uint2 &word) {  // harmless for a lane that has run out of moves
+        if (cur == 0 && amask_addr < amask_last) {  // at most one word per step
+          amask_addr += 128;
+          tab_addr += 256;
+          cur = lds_u32(amask_addr);
         }
-#pragma unroll
-        for (int j = 0; j < kFxUnroll; ++j) {
-          // both presence bits set -> the candidate survives into the queue (a row without a candidate holds word 0)
-          const bool pass = (__funnelshift_r(word[j].y, 0u, sub[j]) & __funnelshift_r(word[j].y, 0u, sub[j] >> 8) & 1u) != 0u;
-          const uint32_t passed = __ballot_sync(0xffffffffu, pass);
-#ifdef ASP_FX_DEBUG
-          {
-            const uint32_t p_first = __shfl_sync(0xffffffffu, passed, 0), c_first = __shfl_sync(0xffffffffu, q_count, 0), h_first = __shfl_sync(0xffffffffu, q_head, 0);
-            if (p_first != passed || c_first != q_count || h_first != q_head) {
-              printf("not uniform: block %d warp %u lane %u taken %u slot %d passed %08x/%08x q_count %u/%u q_head %u/%u pass %d\n", blockIdx.x, warp, lane, taken,
-                     g0 + j, passed, p_first, q_count, c_first, q_head, h_first, static_cast<int>(pass));
-              __trap();
-            }
-          }
+        const bool act = cur != 0;
+        entry_addr = tab_addr + ((static_cast<uint32_t>(__ffs(static_cast<int>(cur)) - 1) & 31u) << 3);
+        cur &= cur - 1;
+        const uint2 entry = lds_table_u2(entry_addr);
+        hsh = s_hash ^ entry.y;
+        word = make_uint2(0u, 0u);
+        if (act) word = ldg_filter_u2(a.filter + (s_idx ^ entry.x));
+      };
+      // second half: both hashed bits set -> the candidate survives into this lane's slots
+      auto sieve = [&](uint32_t entry_addr, uint32_t hsh, uint2 word) {
+        if (__funnelshift_r(word.x, 0u, hsh) & __funnelshift_r(word.y, 0u, hsh >> 8) & 1u) {
+          sts_u16(surv_addr, entry_addr >> 3);
+          surv_addr += 64;
+        }
+      };
+      auto step = [&]() {
+        uint32_t e0, h0;
+        uint2 w0;
+        fetch(e0, h0, w0);
+        sieve(e0, h0, w0);
+      };
+      if (slots >= 8u) {
+        // four candidates per lane between two looks at the loop condition and the fill level,
+        // their four filter words in flight together
+        while (__any_sync(0xffffffffu, cur != 0 || amask_addr < amask_last)) {
+#if ASP_FX_IN_FLIGHT == 4
+          uint32_t e0, e1, e2, e3, h0, h1, h2, h3;
+          uint2 w0, w1, w2, w3;
+          fetch(e0, h0, w0);
+          fetch(e1, h1, w1);
+          fetch(e2, h2, w2);
+          fetch(e3, h3, w3);
+          sieve(e0, h0, w0);
+          sieve(e1, h1, w1);
+          sieve(e2, h2, w2);
+          sieve(e3, h3, w3);
+#else
+          uint32_t e0, e1, h0, h1;
+          uint2 w0, w1;
+          fetch(e0, h0, w0);
+          fetch(e1, h1, w1);
+          sieve(e0, h0, w0);
+          sieve(e1, h1, w1);
+          fetch(e0, h0, w0);
+          fetch(e1, h1, w1);
+          sieve(e0, h0, w0);
+          sieve(e1, h1, w1);
 #endif
-          if (passed) {
-            if (pass)
-              w_queue[(q_head + q_count + __popc(passed & lt_mask)) & (kFxQueue - 1)] =
-                  make_uint4(word[j].x, word[j].y, sub[j], static_cast<uint32_t>(g0 + j) | lane_tag);
-            q_count += __popc(passed);
-            if (q_count >= 32u) {
-              __syncwarp();
-              verify(32u);
-            }
+          if (__any_sync(0xffffffffu, surv_addr > surv_limit)) {
+            __syncwarp();
+            flush();
+          }
+        }
+      } else {  // tiny survivor lists (tests): flush after every survivor
+        while (__any_sync(0xffffffffu, cur != 0 || amask_addr < amask_last)) {
+          step();
+          if (__any_sync(0xffffffffu, surv_addr != surv_base)) {
+            __syncwarp();
+            flush();
           }
         }
       }
       __syncwarp();
-      if (q_count) verify(q_count);
-#ifdef ASP_FX_DEBUG
-      for (uint32_t k = lane; k < list_count; k += 32) {  // the list as it stands right after counting
-        const uint2 e = my_list[k];
-        const uint32_t side = (e.y & 1u) << 5 | ((e.y >> 11) & 31u);
-        FX_CHECK(e.x < a.n_total, 20, e.x);
-        FX_CHECK((e.y >> 16) < w_cnt[side] || spilled != 0, 21, (static_cast<unsigned long long>(taken) << 32) | k);
-      }
-      __syncwarp();
-#endif
-      const uint32_t up_cnt = w_cnt[lane], down_cnt = w_cnt[32 + lane];
-      packed_cnt = (up_cnt + down_cnt + (live ? 1u : 0u)) | (down_cnt << 16);  // couplings of the row (diagonal included) | those below the diagonal << 16
-      // publish the tile's count -- never waits
-      uint32_t total = packed_cnt & 0xFFFFu;
+      flush();
+    }
+    packed_cnt = w_cnt[lane] + (live ? 1u : 0u);  // couplings of the row (diagonal included) | those below the diagonal << 16
+    // publish the tile's count (tile 0: its inclusive prefix) -- never waits
+    uint32_t total = packed_cnt & 0xFFFFu;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-      FX_CHECK(tile / kFxGroupTiles < a.num_groups, 8, tile);
-      if (lane == 0) {
-        st_relaxed_u32(&a.tile_count[tile], total | 0x80000000u);
-        atomicAdd(&a.group_count[tile / kFxGroupTiles], (1ull << kGroupCountShift) | total);
-      }
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if (lane == 0) {
+      if (tile == 0)
+        st_status(&a.status[0], kFlagPrefix | ((a.base_in ? *a.base_in : 0ull) + total));
+      else
+        st_status(&a.status[tile], kFlagAggregate | total);
+    }
     }  // have_tile
 
     if (waiting == kFxLag || (!have_tile && waiting != 0)) {
-      // ======================= CSR offset of the waiting tile by two-level decoupled look-back
+      // ======================= D: CSR offset of the oldest waiting tile by decoupled look-back
       const uint32_t oldest = taken - waiting;
-      const uint32_t pend_packed = w_pend[lane], pend_count = w_pend[34], pend_spilled = w_pend[35];
-      FX_CHECK(pend_count <= list_cap && pend_spilled <= a.scratch_per_warp, 12, pend_count);
-      const uint64_t ptile = (static_cast<uint64_t>(w_pend[33]) << 32) | w_pend[32];
+      const uint32_t *const pend = w_pend + (oldest % kFxLag) * 36;
+      const uint32_t pend_packed = pend[lane], pend_count = pend[34];
+      const uint64_t ptile = (static_cast<uint64_t>(pend[33]) << 32) | pend[32];
       const uint64_t r = ptile * kFxTileRows + lane;
       const bool live = r < a.num_rows;
       const uint64_t row = a.row_begin + r;
@@ -455,85 +551,38 @@ __global__ void __launch_bounds__(kFxThreads, ASP_FX_MIN_CTAS) extract_csr_kerne
         if (lane >= o) incl += t;
       }
       const uint32_t tile_total = __shfl_sync(0xffffffffu, incl, 31);
-      const uint64_t group = ptile / kFxGroupTiles;
-      const uint32_t in_group = static_cast<uint32_t>(ptile % kFxGroupTiles);
-      // (1) the earlier tiles of this tile's group (they hold earlier tickets: counted or being counted)
-      uint32_t earlier = 0;
-      if (lane < in_group) {
-        unsigned backoff = ASP_FX_BACKOFF_NS;
-        unsigned long long t0 = 0;
-        while (((earlier = ld_relaxed_u32(&a.tile_count[group * kFxGroupTiles + lane])) >> 31) == 0u) {
-          __nanosleep(backoff);
-          if (backoff < 32 * ASP_FX_BACKOFF_NS) {
-            backoff <<= 1;
-          } else {  // a count that stays away for seconds is a bug, not a slow tile: fail, never hang the device
-            const unsigned long long now = global_timer_ns();
-            if (t0 == 0) t0 = now;
-            if (now - t0 > 4000000000ull) __trap();
+      unsigned long long exclusive = 0;
+      if (ptile == 0) {
+        if (a.base_in) exclusive = *a.base_in;
+      } else {
+        int64_t look = static_cast<int64_t>(ptile) - 1;  // window [look - 31, look]
+        for (;;) {
+          const int64_t idx = look - lane;
+          unsigned long long st = kFlagPrefix;  // virtual tiles before tile 0: prefix 0
+          if (idx >= 0) {
+            unsigned backoff = ASP_FX_BACKOFF_NS;
+            while (((st = ld_status(&a.status[idx])) >> 62) == 0) {
+              __nanosleep(backoff);
+              if (backoff < 32 * ASP_FX_BACKOFF_NS) backoff <<= 1;
+            }
           }
-        }
-        earlier &= 0x7FFFFFFFu;
-      }
+          const uint32_t has_prefix = __ballot_sync(0xffffffffu, (st >> 62) == 2);
+          const uint32_t first = has_prefix ? static_cast<uint32_t>(__ffs(has_prefix)) - 1u : 32u;  // nearest tile with a prefix
+          // counts of the tiles in front of it (each < 2^16) add up in 32 bits; the prefix itself is 64-bit
+          uint32_t counts = lane < first ? static_cast<uint32_t>(st) : 0u;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) earlier += __shfl_xor_sync(0xffffffffu, earlier, o);
-      // (2) couplings before the group: its published prefix, or the nearest published prefix plus the complete
-      // groups in between (32 groups per step; every group before this one is full)
-      unsigned long long before_group = a.base_in ? *a.base_in : 0ull;
-      if (group != 0) {
-        // ONE lane reads the word and hands it to the others: the branch below must be taken by the whole warp,
-        // and lanes that read for themselves can see the word before and after it is published
-        unsigned long long known = 0ull;
-        if (lane == 0) known = ld_relaxed_u64(&a.group_prefix[group]);
-        known = __shfl_sync(0xffffffffu, known, 0);
-        if (known & kPrefixValid) {
-          before_group = known & ~kPrefixValid;
-        } else {
-          unsigned long long acc = 0;
-          int64_t look = static_cast<int64_t>(group) - 1;  // window [look - 31, look]
-          for (;;) {
-            const int64_t g = look - lane;
-            unsigned long long prefix = 0;
-            bool has_prefix = g <= 0;  // group 0 starts at base_in
-            if (g > 0) {
-              prefix = ld_relaxed_u64(&a.group_prefix[g]);
-              has_prefix = (prefix & kPrefixValid) != 0;
-              prefix &= ~kPrefixValid;
-            } else {
-              prefix = before_group;
-            }
-            const uint32_t found = __ballot_sync(0xffffffffu, has_prefix);
-            const uint32_t first = static_cast<uint32_t>(__ffs(static_cast<int>(found))) - 1u;  // nearest group with a prefix (lane 0 = nearest); found != 0 when look < 32
-            const uint32_t upto = found ? first : 31u;
-            unsigned long long count = 0;
-            if (lane <= upto && g >= 0) {  // groups g .. look contribute their totals
-              unsigned backoff = ASP_FX_BACKOFF_NS;
-              unsigned long long t0 = 0;
-              while (((count = ld_relaxed_u64(&a.group_count[g])) >> kGroupCountShift) != static_cast<unsigned long long>(kFxGroupTiles)) {
-                __nanosleep(backoff);
-                if (backoff < 32 * ASP_FX_BACKOFF_NS) {
-                  backoff <<= 1;
-                } else {
-                  const unsigned long long now = global_timer_ns();
-                  if (t0 == 0) t0 = now;
-                  if (now - t0 > 4000000000ull) __trap();
-                }
-              }
-              count &= (1ull << kGroupCountShift) - 1ull;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
-            acc += count;
-            if (found) {
-              acc += __shfl_sync(0xffffffffu, prefix, first);
-              break;
-            }
-            look -= 32;
+          for (int o = 16; o > 0; o >>= 1) counts += __shfl_xor_sync(0xffffffffu, counts, o);
+          exclusive += counts;
+          if (has_prefix) {
+            const uint32_t p_lo = __shfl_sync(0xffffffffu, static_cast<uint32_t>(st), first);
+            const uint32_t p_hi = __shfl_sync(0xffffffffu, static_cast<uint32_t>(st >> 32), first);
+            exclusive += ((static_cast<unsigned long long>(p_hi) << 32) | p_lo) & kValueMask;
+            break;
           }
-          before_group = acc;
-          if (lane == 0) st_relaxed_u64(&a.group_prefix[group], acc | kPrefixValid);
+          look -= 32;
         }
+        if (lane == 0) st_status(&a.status[ptile], kFlagPrefix | (exclusive + tile_total));
       }
-      const unsigned long long exclusive = before_group + earlier;
       if (lane == 0 && ptile == a.num_tiles - 1) {
         a.indptr[a.num_rows] = static_cast<int64_t>(exclusive + tile_total);
         *a.nnz_out = exclusive + tile_total;
@@ -544,55 +593,44 @@ __global__ void __launch_bounds__(kFxThreads, ASP_FX_MIN_CTAS) extract_csr_kerne
       }
       const uint64_t tile_base = exclusive;
 
-      // ======================= write the waiting tile's CSR rows ============================
-      const uint2 *const list = w_lists + static_cast<size_t>(oldest & 1u) * list_cap;
-      const uint2 *const spill_list = my_spill + static_cast<size_t>(oldest & 1u) * a.scratch_per_warp;
+      // ======================= write the previous tile's CSR rows ============================
+      // (the apply masks are dead: their bytes now hold the row offsets and amplitudes)
+      const uint2 *const list = my_lists + static_cast<size_t>(oldest % (kFxLag + 1)) * a.scratch_per_warp;
       const uint32_t my_off = incl - my_cnt;  // row start relative to the tile
-      Record mine{0ull, 0.0};
-      if (live) {
-        const ulonglong2 raw = __ldg(reinterpret_cast<const ulonglong2 *>(&a.rec[row]));
-        mine.key = raw.x;
-        mine.amp = __longlong_as_double(static_cast<long long>(raw.y));
-      }
-      const double a_i = mine.amp;
+      const uint64_t s = live ? __ldg(&a.spins[row]) : 0ull;
+      const double a_i = live ? fabs(__ldg(&a.psi[row])) : 0.0;
       w_row_off[lane] = my_off;
-      w_down[lane] = down_cnt;
       w_abs_psi[lane] = a_i;
       if (live) a.indptr[r] = static_cast<int64_t>(tile_base + my_off);
       __syncwarp();
-      auto emit = [&](uint2 entry) {
-        const uint32_t pos = entry.x, code = entry.y & 0x7FFu, src = (entry.y >> 11) & 31u, k = entry.y >> 16;
-        const uint32_t dn = w_down[src];
-        FX_CHECK(pos < a.n_total, 9, (static_cast<unsigned long long>(taken) << 40) | (static_cast<unsigned long long>(waiting) << 36) | (static_cast<unsigned long long>(have_tile) << 32) | pend_count);
-        FX_CHECK(code < 2u * static_cast<uint32_t>(a.n_slots), 10, code);
-        FX_CHECK((code & 1u) ? k < dn : true, 11, k);
-        const uint64_t dest = tile_base + w_row_off[src] + ((code & 1u) ? dn - 1u - k : dn + 1u + k);
+      for (uint32_t k = lane; k < pend_count; k += 32) {
+        const uint2 entry = list[k];
+        const uint32_t pos = entry.x, m = entry.y & 0x7FFu, src = (entry.y >> 11) & 31u, rank = entry.y >> 16;
+        const uint64_t dest = tile_base + w_row_off[src] + rank;
         if (dest < a.capacity) {
           a.indices[dest] = static_cast<int32_t>(pos);
-          a.data[dest] = __dmul_rn(__dmul_rn(s_coef[code], __ldg(&a.rec[pos].amp)), w_abs_psi[src]);
+          a.data[dest] = __dmul_rn(__dmul_rn(s_coef[m], fabs(ldg_stream_f64(&a.psi[pos]))), w_abs_psi[src]);  // (c |psi_j|) |psi_i|: common.py:71-82
         }
-      };
-      for (uint32_t k = lane; k < pend_spilled; k += 32) emit(spill_list[k]);
-      for (uint32_t k = lane; k < pend_count; k += 32) emit(list[k]);
+      }
       if (live) {
-        const double d = a.n_groups >= 0 ? diagonal_closed_form(mine.key, s_groups, a.n_groups, a.diag_c0, a.diag_scale)
-                                         : diagonal_element(mine.key, s_diag, a.n_diag);
+        const double d = a.n_groups >= 0 ? diagonal_closed_form(s, s_groups, a.n_groups, a.diag_c0, a.diag_scale)
+                                         : diagonal_element(s, s_diag, a.n_diag);
         const uint64_t dest = tile_base + my_off + down_cnt;
         if (dest < a.capacity) {
           a.indices[dest] = static_cast<int32_t>(row);
           a.data[dest] = __dmul_rn(__dmul_rn(d, a_i), a_i);
         }
       }
-      __syncwarp();  // the row offsets are read by all lanes; the next tile's queue overwrites their bytes
+      __syncwarp();  // the row offsets are read by all lanes; the next tile overwrites their bytes
       --waiting;
     }
     if (have_tile) {  // the tile just counted joins the queue
-      w_pend[lane] = packed_cnt;
+      uint32_t *const pend = w_pend + (taken % kFxLag) * 36;
+      pend[lane] = packed_cnt;
       if (lane == 0) {
-        w_pend[32] = static_cast<uint32_t>(tile);
-        w_pend[33] = static_cast<uint32_t>(tile >> 32);
-        w_pend[34] = list_count;
-        w_pend[35] = spilled;
+        pend[32] = static_cast<uint32_t>(tile);
+        pend[33] = static_cast<uint32_t>(tile >> 32);
+        pend[34] = list_count;
       }
       __syncwarp();
       ++taken;
@@ -604,27 +642,25 @@ __global__ void __launch_bounds__(kFxThreads, ASP_FX_MIN_CTAS) extract_csr_kerne
 constexpr int kFxMaxChunks = kFusedMaxChunks;  // row chunks of one pipelined host call
 
 struct FusedWorkspace {
-  Record *rec;                       // [n_total] {key, |psi|}
-  uint2 *index;                      // [num_buckets + 1] {first position, presence bits}
-  uint32_t *tile_count;              // [tiles + kFxMaxChunks]: every row chunk has its own slice
-  unsigned long long *group_count;   // [groups + kFxMaxChunks]
-  unsigned long long *group_prefix;  // [groups + kFxMaxChunks]
-  unsigned int *tickets;             // [kFxMaxChunks] one per chunk, 64 B apart
-  unsigned long long *totals;        // [kFxMaxChunks] running totals
-  uint2 *scratch;                    // spill lists
-  uint64_t num_buckets;
-  int bshift, oshift;
+  uint32_t *starts;
+  uint2 *filter;
+  unsigned long long *status;  // [num_tiles + kFxMaxChunks]: every row chunk has its own slice
+  unsigned int *tickets;       // [kFxMaxChunks] one per chunk, 64 B apart
+  unsigned long long *totals;  // [kFxMaxChunks] running totals
+  uint2 *scratch;
+  uint64_t num_buckets, num_words;
+  int tshift, fshift;
   uint32_t scratch_per_warp, scratch_ctas;
   size_t bytes, zero_offset, zero_bytes;
 };
 
-static int g_list_entries_override = 0;
+static int g_surv_entries_override = 0;
 // optional CUDA-event bracket around the extraction kernel alone (bench.py's roofline figure)
 static bool g_time_kernel = false;
 constexpr int kEvRing = 64;  // the last kEvRing launches keep their event pair
 static cudaEvent_t g_ev_begin[kEvRing] = {}, g_ev_end[kEvRing] = {};
 static uint64_t g_ev_launches = 0;
-static int g_bucket_bits_delta = 0, g_diag_mode = 0;
+static int g_filter_bits_delta = 0, g_table_bits_delta = 0, g_stage_a_mode = 0;
 static int g_gather_mode = 2;  // asp_gather_index: 2 = one TMA kernel (default), 1 = one kernel with plain loads, 0 = copy engines + per-block index kernels
 
 static FusedWorkspace carve_fused(void *base, const asp_operator *op, uint64_t n_total, uint64_t num_rows) {
@@ -632,16 +668,19 @@ static FusedWorkspace carve_fused(void *base, const asp_operator *op, uint64_t n
   int lg = 0;
   while ((1ull << lg) < n_total) ++lg;
   const int key_bits = static_cast<int>(op->number_spins);
-  int bbits = lg - 2 + g_bucket_bits_delta;  // two to four keys per bucket: 8 bytes of index per ~3 keys
-  bbits = std::max(2, std::min(bbits, 27));
-  bbits = std::min(bbits, key_bits);
-  w.bshift = key_bits - bbits;
-  w.oshift = std::max(w.bshift - 4, 0);
-  w.num_buckets = 1ull << bbits;
+  int tbits = lg - 1 + g_table_bits_delta;  // about two slots per key: most buckets hold 0 or 1 keys
+  tbits = std::max(4, std::min(tbits, 26));
+  tbits = std::min(tbits, key_bits);
+  w.tshift = key_bits - tbits;
+  w.num_buckets = 1ull << tbits;
+  int fbits = lg - 1 + g_filter_bits_delta;  // 8 bytes per 2 keys: ~1 % false positives
+  fbits = std::max(4, std::min(fbits, 27));
+  fbits = std::min(fbits, key_bits);
+  w.fshift = key_bits - fbits;
+  w.num_words = 1ull << fbits;
   const uint64_t tiles = (num_rows + kFxTileRows - 1) / kFxTileRows + kFxMaxChunks;
-  const uint64_t groups = tiles / kFxGroupTiles + 1 + kFxMaxChunks;
   w.scratch_per_warp = std::max<uint32_t>(32u * static_cast<uint32_t>(op->moves.size()), 32u);
-  const size_t per_cta = static_cast<size_t>(w.scratch_per_warp) * 2 * kFxWarps * sizeof(uint2);  // two spill lists per warp
+  const size_t per_cta = static_cast<size_t>(w.scratch_per_warp) * (kFxLag + 1) * kFxWarps * sizeof(uint2);  // kFxLag + 1 hit lists per warp
   uint64_t ctas = std::min<uint64_t>(static_cast<uint64_t>(kNumSMs) * kFxMaxCtasPerSM, std::max<uint64_t>(tiles, 1));
   ctas = std::min<uint64_t>(ctas, std::max<uint64_t>(kFxScratchBudget / per_cta, kNumSMs));
   w.scratch_ctas = static_cast<uint32_t>(ctas);
@@ -651,13 +690,11 @@ static FusedWorkspace carve_fused(void *base, const asp_operator *op, uint64_t n
     off += align_up(bytes, 256);
     return p;
   };
-  w.rec = static_cast<Record *>(take((n_total + 1) * sizeof(Record)));
+  w.starts = static_cast<uint32_t *>(take((w.num_buckets + 1) * sizeof(uint32_t)));
   w.scratch = static_cast<uint2 *>(take(per_cta * ctas));
   w.zero_offset = off;
-  w.index = static_cast<uint2 *>(take((w.num_buckets + 1) * sizeof(uint2)));
-  w.tile_count = static_cast<uint32_t *>(take(tiles * sizeof(uint32_t)));
-  w.group_count = static_cast<unsigned long long *>(take(groups * sizeof(unsigned long long)));
-  w.group_prefix = static_cast<unsigned long long *>(take(groups * sizeof(unsigned long long)));
+  w.filter = static_cast<uint2 *>(take(w.num_words * sizeof(uint2)));
+  w.status = static_cast<unsigned long long *>(take(tiles * sizeof(unsigned long long)));
   w.tickets = static_cast<unsigned int *>(take(kFxMaxChunks * 64));
   w.totals = static_cast<unsigned long long *>(take(kFxMaxChunks * sizeof(unsigned long long)));
   w.zero_bytes = off - w.zero_offset;
@@ -671,16 +708,16 @@ size_t fused_workspace_bytes(const asp_operator *op, uint64_t n_total, uint64_t 
 
 int fused_check_operator(const asp_operator *op) {
   ASP_REQUIRE(op != nullptr, "operator is NULL");
-  ASP_REQUIRE(op->d_moves != nullptr && op->d_slots != nullptr, "operator has no device mirror (created without a CUDA device)");
-  if (!op->sorted_emitter() || op->slots.size() > kFxMaxSlots) {
-    set_error("fused extraction needs an unsymmetrised operator with distinct moves (at most %u move pairs); use the apply + build_matrix + canonicalise path", kFxMaxSlots);
+  ASP_REQUIRE(op->d_moves != nullptr, "operator has no device mirror (created without a CUDA device)");
+  if (!op->sorted_emitter() || op->moves.size() > kFxMaxMoves) {
+    set_error("fused extraction needs an unsymmetrised operator with distinct moves (at most %u); use the apply + build_matrix + canonicalise path", kFxMaxMoves);
     return ASP_ERR_UNSUPPORTED;
   }
   return ASP_OK;
 }
 
 // Zero the look-back state and index the sorted basis (once per call, before the chunks).
-int fused_prepare(const asp_operator *op, uint64_t n_total, const uint64_t *d_spins, const double *d_psi, uint64_t num_rows, void *d_workspace,
+int fused_prepare(const asp_operator *op, uint64_t n_total, const uint64_t *d_spins, uint64_t num_rows, void *d_workspace,
                   size_t workspace_bytes, cudaStream_t s) {
   FusedWorkspace w = carve_fused(d_workspace, op, n_total, num_rows);
   if (d_workspace == nullptr || workspace_bytes < w.bytes) {
@@ -688,10 +725,10 @@ int fused_prepare(const asp_operator *op, uint64_t n_total, const uint64_t *d_sp
     return ASP_ERR_WORKSPACE;
   }
   ASP_CUDA_CHECK(cudaMemsetAsync(static_cast<char *>(d_workspace) + w.zero_offset, 0, w.zero_bytes, s));
-  // two keys per thread: neighbours that share a bucket share one atomic (the pass is bound by L2 atomics)
-  index_block_kernel<<<static_cast<unsigned>((n_total + 511) / 512), 256, 0, s>>>(d_spins, d_psi, static_cast<uint32_t>(n_total), 0u,
-                                                                                 static_cast<uint32_t>(n_total), op->state_mask, w.bshift,
-                                                                                 w.oshift, w.num_buckets, w.index, w.rec);
+  // two keys per thread: neighbours that share a filter word share one 64-bit atomic (the pass is bound by L2 atomics)
+  index_block_kernel<<<static_cast<unsigned>((n_total + 511) / 512), 256, 0, s>>>(d_spins, static_cast<uint32_t>(n_total), 0u,
+                                                                                 static_cast<uint32_t>(n_total), op->state_mask, w.tshift,
+                                                                                 w.num_buckets, w.starts, w.fshift, w.filter);
   ASP_LAUNCH_CHECK();
   return ASP_OK;
 }
@@ -754,10 +791,10 @@ int fused_prepare_gather(const asp_operator *op, uint32_t world, uint32_t rank, 
   }
   a.state_mask = op->state_mask;
   a.num_buckets = w.num_buckets;
-  a.bshift = w.bshift;
-  a.oshift = w.oshift;
-  a.index = w.index;
-  a.rec = w.rec;
+  a.tshift = w.tshift;
+  a.fshift = w.fshift;
+  a.starts = w.starts;
+  a.filter = w.filter;
   ASP_CUDA_CHECK(cudaMemsetAsync(static_cast<char *>(d_workspace) + w.zero_offset, 0, w.zero_bytes, s));
   if (tma) {
     a.stages = kTxStages;
@@ -778,7 +815,7 @@ int fused_prepare_gather(const asp_operator *op, uint32_t world, uint32_t rank, 
 // the block is indexed as soon as its copies are done, while the next blocks travel.
 struct CopyLane {
   cudaStream_t copy = nullptr, copy2 = nullptr;  // keys on one copy engine, amplitudes on another
-  cudaEvent_t start = nullptr, flag = nullptr, done[2] = {}, block[kGxMaxRanks] = {}, block2[kGxMaxRanks] = {};
+  cudaEvent_t start = nullptr, flag = nullptr, block[kGxMaxRanks] = {}, block2[kGxMaxRanks] = {};
   int device = -1;
 };
 static CopyLane g_lane;
@@ -809,7 +846,6 @@ int fused_prepare_gather_ce(const asp_operator *op, uint32_t world, uint32_t ran
     ASP_CUDA_CHECK(cudaEventCreateWithFlags(&g_lane.flag, cudaEventDisableTiming));
     for (auto &e : g_lane.block) ASP_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto &e : g_lane.block2) ASP_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    for (auto &e : g_lane.done) ASP_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     g_lane.device = dev;
   }
   if (index) ASP_CUDA_CHECK(cudaMemsetAsync(static_cast<char *>(d_workspace) + w.zero_offset, 0, w.zero_bytes, s));
@@ -834,22 +870,20 @@ int fused_prepare_gather_ce(const asp_operator *op, uint32_t world, uint32_t ran
     ASP_CUDA_CHECK(cudaMemcpyAsync(d_psi + b0, d_shard_psi[q], len * sizeof(double), cudaMemcpyDeviceToDevice, g_lane.copy2));
     if (!index) continue;
     ASP_CUDA_CHECK(cudaEventRecord(g_lane.block[k], g_lane.copy));
-    ASP_CUDA_CHECK(cudaEventRecord(g_lane.block2[k], g_lane.copy2));
-    ASP_CUDA_CHECK(cudaStreamWaitEvent(s, g_lane.block[k], 0));  // keys and amplitudes of this block have landed: index them
-    ASP_CUDA_CHECK(cudaStreamWaitEvent(s, g_lane.block2[k], 0));
-    index_block_kernel<<<static_cast<unsigned>((len + 511) / 512), 256, 0, s>>>(d_spins, d_psi, static_cast<uint32_t>(n_total), static_cast<uint32_t>(b0),
-                                                                               static_cast<uint32_t>(b0 + len), op->state_mask, w.bshift, w.oshift,
-                                                                               w.num_buckets, w.index, w.rec);
+    ASP_CUDA_CHECK(cudaStreamWaitEvent(s, g_lane.block[k], 0));  // the keys of this block have landed: index them
+    index_block_kernel<<<static_cast<unsigned>((len + 511) / 512), 256, 0, s>>>(d_spins, static_cast<uint32_t>(n_total), static_cast<uint32_t>(b0),
+                                                                               static_cast<uint32_t>(b0 + len), op->state_mask, w.tshift,
+                                                                               w.num_buckets, w.starts, w.fshift, w.filter);
     ASP_LAUNCH_CHECK();
   }
-  // everything has landed before the caller's stream goes on
-  ASP_CUDA_CHECK(cudaEventRecord(g_lane.done[0], g_lane.copy));
-  ASP_CUDA_CHECK(cudaEventRecord(g_lane.done[1], g_lane.copy2));
-  ASP_CUDA_CHECK(cudaStreamWaitEvent(s, g_lane.done[0], 0));
-  ASP_CUDA_CHECK(cudaStreamWaitEvent(s, g_lane.done[1], 0));
+  // everything (amplitudes included) has landed before the caller's stream goes on
+  ASP_CUDA_CHECK(cudaEventRecord(g_lane.block2[0], g_lane.copy));
+  ASP_CUDA_CHECK(cudaEventRecord(g_lane.block2[1], g_lane.copy2));
+  ASP_CUDA_CHECK(cudaStreamWaitEvent(s, g_lane.block2[0], 0));
+  ASP_CUDA_CHECK(cudaStreamWaitEvent(s, g_lane.block2[1], 0));
   if (index) {
-    index_seam_kernel<<<1, 32, 0, s>>>(d_spins, static_cast<uint32_t>(n_total), seams, static_cast<int>(world), op->state_mask, w.bshift,
-                                       w.num_buckets, w.index);
+    index_seam_kernel<<<1, 32, 0, s>>>(d_spins, static_cast<uint32_t>(n_total), seams, static_cast<int>(world), op->state_mask, w.tshift,
+                                       w.num_buckets, w.starts);
     ASP_LAUNCH_CHECK();
   }
   return ASP_OK;
@@ -867,36 +901,37 @@ int fused_launch(const asp_operator *op, uint64_t n_total, const uint64_t *d_spi
   ASP_REQUIRE(chunk_begin % kFxTileRows == 0, "row chunks start at tile boundaries");
   FusedWorkspace w = carve_fused(d_workspace, op, n_total, num_rows);
   FusedArgs a{};
-  (void)d_spins;
-  (void)d_psi;  // the kernel reads the {key, |psi|} records the index pass made of them
-  a.rec = w.rec;
-  a.index = w.index;
-  a.bshift = w.bshift;
-  a.oshift = w.oshift;
+  a.spins = d_spins;
+  a.psi = d_psi;
+  a.starts = w.starts;
+  a.tshift = w.tshift;
+  a.filter = w.filter;
+  a.fshift = w.fshift;
   a.state_mask = op->state_mask;
   a.n_total = static_cast<uint32_t>(n_total);
   a.row_begin = row_begin + chunk_begin;
   a.num_rows = chunk_rows;
   a.num_tiles = (chunk_rows + kFxTileRows - 1) / kFxTileRows;
-  a.slots = op->d_slots;
-  a.n_slots = static_cast<int>(op->slots.size());
-  a.n_slots_padded = (a.n_slots + kFxUnroll - 1) / kFxUnroll * kFxUnroll;
+  a.moves = op->d_moves;
+  a.n_moves = static_cast<int>(op->moves.size());
+  a.n_down = static_cast<int>(op->n_down);
+  a.n_words = (a.n_moves + 31) / 32;
   a.diag = op->d_diag;
   a.n_diag = static_cast<int>(op->diag.size());
-  const bool closed_form = op->diag_scale >= 0 && g_diag_mode != 1;
+  const bool closed_form = op->diag_scale >= 0 && g_stage_a_mode != 1;
   a.groups = op->d_diag_groups;
   a.n_groups = closed_form ? static_cast<int>(op->diag_groups.size()) : -1;
   a.diag_scale = op->diag_scale;
   a.diag_c0 = op->diag_c0;
+  int slots = kFxSurvSlotsDefault;
+  if (g_surv_entries_override > 0) slots = std::max(1, g_surv_entries_override / 32);
+  a.surv_slots = slots;
+  bool two_bit = true;
+  for (const Move &mv : op->moves) two_bit = two_bit && __builtin_popcountll(mv.mask) == 2;
+  a.planes_ok = (two_bit && g_stage_a_mode != 1) ? 1 : 0;
   a.scratch = w.scratch;
   a.scratch_per_warp = w.scratch_per_warp;
-  a.scratch_lists = static_cast<uint64_t>(w.scratch_ctas) * kFxWarps * 2;
-  a.num_buckets = w.num_buckets;
-  a.num_groups = (chunk_rows + kFxTileRows - 1) / kFxTileRows / kFxGroupTiles + 1;
-  const uint64_t first_tile = chunk_begin / kFxTileRows;
-  a.tile_count = w.tile_count + first_tile + chunk;
-  a.group_count = w.group_count + first_tile / kFxGroupTiles + chunk;
-  a.group_prefix = w.group_prefix + first_tile / kFxGroupTiles + chunk;
+  a.status = w.status + chunk_begin / kFxTileRows + chunk;
   a.ticket = w.tickets + 16 * chunk;
   a.capacity = capacity;
   a.indptr = d_indptr + chunk_begin;
@@ -905,31 +940,13 @@ int fused_launch(const asp_operator *op, uint64_t n_total, const uint64_t *d_spi
   a.nnz_out = w.totals + chunk;
   a.nnz_mirror = nnz_mirror;
   a.base_in = chunk == 0 ? nullptr : w.totals + (chunk - 1);
-  const bool wide = op->number_spins > 32;
-  auto kernel = wide ? extract_csr_kernel<true> : extract_csr_kernel<false>;
-  // Hit lists: as long as the shared memory of an SM allows with kFxTargetCtas resident CTAs (a tile of the
-  // headline workload holds ~120 hits; a longer list only matters for dense bases, which spill).
-  int device = 0, smem_sm = 0, smem_cta = 0;
-  ASP_CUDA_CHECK(cudaGetDevice(&device));
-  ASP_CUDA_CHECK(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
-  ASP_CUDA_CHECK(cudaDeviceGetAttribute(&smem_cta, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-  const FxLayout fixed = fx_layout(a.n_slots_padded, a.n_groups, a.n_diag, 0);
-  const size_t fixed_bytes = fixed.tables + static_cast<size_t>(fixed.per_warp) * kFxWarps;
-  uint32_t list_entries = 0;
-  for (int ctas = ASP_FX_MIN_CTAS; ctas >= 1 && list_entries < 96; --ctas) {  // prefer more resident CTAs; never a list below 96 entries if fewer CTAs allow one
-    const size_t budget = std::min<size_t>(static_cast<size_t>(smem_cta), (static_cast<size_t>(smem_sm) - 32 * 1024) / ctas - 1024);  // 32 KB stay L1
-    if (budget <= fixed_bytes) continue;
-    list_entries = static_cast<uint32_t>(std::min<size_t>((budget - fixed_bytes) / (kFxWarps * 2 * sizeof(uint2)), 512)) / 32 * 32;
-  }
-  if (g_list_entries_override > 0) list_entries = std::max(32, g_list_entries_override / 32 * 32);
-  ASP_REQUIRE(list_entries >= 32, "operator too large for the fused kernel's shared-memory tables");
-  const FxLayout layout = fx_layout(a.n_slots_padded, a.n_groups, a.n_diag, list_entries);
+  const FxLayout layout = fx_layout(a.n_moves, a.n_words, a.n_groups, a.n_diag, a.planes_ok, slots);
   a.layout = layout;
   const size_t smem = layout.tables + static_cast<size_t>(layout.per_warp) * kFxWarps;
-  ASP_REQUIRE(smem <= static_cast<size_t>(smem_cta), "operator too large for the fused kernel's shared-memory tables");
-  ASP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  ASP_REQUIRE(smem <= 200 * 1024, "operator too large for the fused kernel's shared-memory tables");
+  ASP_CUDA_CHECK(cudaFuncSetAttribute(extract_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int per_sm = 0;
-  ASP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kFxThreads, smem));
+  ASP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, extract_csr_kernel, kFxThreads, smem));
   ASP_REQUIRE(per_sm >= 1, "fused extraction kernel does not fit on an SM");
   const uint64_t resident = static_cast<uint64_t>(kNumSMs) * std::min(per_sm, kFxMaxCtasPerSM);
   const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(std::min<uint64_t>(a.num_tiles, resident), w.scratch_ctas));
@@ -941,7 +958,7 @@ int fused_launch(const asp_operator *op, uint64_t n_total, const uint64_t *d_spi
     }
     ASP_CUDA_CHECK(cudaEventRecord(g_ev_begin[ev_slot], s));
   }
-  kernel<<<grid, kFxThreads, smem, s>>>(a);
+  extract_csr_kernel<<<grid, kFxThreads, smem, s>>>(a);
   ASP_LAUNCH_CHECK();
   if (g_time_kernel) {
     ASP_CUDA_CHECK(cudaEventRecord(g_ev_end[ev_slot], s));
@@ -960,12 +977,12 @@ using namespace asp;
 
 extern "C" {
 
-void asp_debug_set_hit_list_capacity(int entries_per_warp) { g_list_entries_override = entries_per_warp; }
+void asp_debug_set_hit_list_capacity(int entries_per_warp) { g_surv_entries_override = entries_per_warp; }
 
-void asp_debug_set_extract_tuning(int bucket_bits_delta, int reserved, int diag_mode) {
-  (void)reserved;
-  g_bucket_bits_delta = bucket_bits_delta;
-  g_diag_mode = diag_mode;
+void asp_debug_set_extract_tuning(int filter_bits_delta, int table_bits_delta, int stage_a_mode) {
+  g_filter_bits_delta = filter_bits_delta;
+  g_table_bits_delta = table_bits_delta;
+  g_stage_a_mode = stage_a_mode;
 }
 
 void asp_debug_time_extract_kernel(int enable) { g_time_kernel = enable != 0; }
@@ -1009,7 +1026,7 @@ static int extract_csr_impl(asp_operator const *op, uint64_t n_total, uint64_t c
   if (indexed) {  // the workspace was zeroed and indexed for this very (n_total, num_rows) by asp_gather_index
     ASP_REQUIRE(d_workspace != nullptr && workspace_bytes >= fused_workspace_bytes(op, n_total, num_rows), "workspace too small");
   } else {
-    rc = fused_prepare(op, n_total, d_spins, d_psi, num_rows, d_workspace, workspace_bytes, s);
+    rc = fused_prepare(op, n_total, d_spins, num_rows, d_workspace, workspace_bytes, s);
     if (rc != ASP_OK) return rc;
   }
   rc = fused_launch(op, n_total, d_spins, d_psi, row_begin, num_rows, 0, 0, num_rows, d_workspace, capacity, d_indptr, d_indices,

@@ -10,8 +10,8 @@ constexpr int kFusedMaxChunks = 32;
 
 size_t fused_workspace_bytes(const asp_operator *op, uint64_t n_total, uint64_t num_rows);
 int fused_check_operator(const asp_operator *op);
-int fused_prepare(const asp_operator *op, uint64_t n_total, const uint64_t *d_spins, const double *d_psi, uint64_t num_rows,
-                  void *d_workspace, size_t workspace_bytes, cudaStream_t s);
+int fused_prepare(const asp_operator *op, uint64_t n_total, const uint64_t *d_spins, uint64_t num_rows, void *d_workspace,
+                  size_t workspace_bytes, cudaStream_t s);
 int fused_prepare_gather(const asp_operator *op, uint32_t world, uint32_t rank, const uint64_t *shard_begin,
                          const uint64_t *const *d_shard_spins, const double *const *d_shard_psi, const uint64_t *d_ready,
                          uint64_t epoch, uint64_t *d_spins, double *d_psi, uint64_t num_rows, void *d_workspace,

@@ -241,11 +241,11 @@ static int extract_host_impl(asp_operator const *op, uint64_t n, uint64_t const 
     HOST_CUDA(cudaEventRecord(A.ev_spins, A.copy_in));
     HOST_CUDA(cudaMemcpyAsync(d_psi, h_psi, n * sizeof(double), cudaMemcpyHostToDevice, A.copy_in));
     HOST_CUDA(cudaEventRecord(A.ev_psi, A.copy_in));
-    // the index pass interleaves keys and amplitudes into records: it needs both
+    // the index only needs the basis words: it is built while the amplitudes are still in flight
     HOST_CUDA(cudaStreamWaitEvent(A.compute, A.ev_spins, 0));
-    HOST_CUDA(cudaStreamWaitEvent(A.compute, A.ev_psi, 0));
-    rc = asp::fused_prepare(op, n, d_spins, d_psi, num_rows, A.workspace.p, A.workspace.cap, A.compute);
+    rc = asp::fused_prepare(op, n, d_spins, num_rows, A.workspace.p, A.workspace.cap, A.compute);
     if (rc != ASP_OK) goto out;
+    HOST_CUDA(cudaStreamWaitEvent(A.compute, A.ev_psi, 0));
     rc = extract_chunks_to_host(A, op, n, d_spins, d_psi, row_begin, num_rows, chunk_rows, chunks, A.workspace.p, dev_capacity, capacity,
                                 d_indptr, d_indices, d_data, d_totals, h_indptr, narrow, h_indices, h_data, h_nnz);
   }

@@ -176,50 +176,6 @@ static void build_diag_groups(asp_operator *op) {
   op->diag_scale = scale;
 }
 
-// Slots of the single-pass kernel (operator.cuh: Slot): moves grouped by (flip, |delta|), one per
-// direction, sorted by |delta|.  The moves arrive delta-sorted; delta is recomputed from flip/need.
-static void build_slots(asp_operator *op) {
-  struct Keyed {
-    Slot s;
-    unsigned __int128 abs_delta;
-    size_t seq;
-  };
-  std::vector<Keyed> keyed;
-  for (const Move &m : op->moves) {
-    __int128 delta = 0;
-    for (int b = 0; b < 64; ++b) {
-      const uint64_t bit = 1ull << b;
-      if (m.flip & bit) delta += (m.need & bit) ? -static_cast<__int128>(bit) : static_cast<__int128>(bit);
-    }
-    const bool down = delta < 0;
-    const unsigned __int128 ad = static_cast<unsigned __int128>(down ? -delta : delta);
-    bool placed = false;
-    for (Keyed &k : keyed) {
-      if (k.s.flip != m.flip || k.abs_delta != ad || k.s.mask != m.mask) continue;
-      uint64_t &need = down ? k.s.need_down : k.s.need_up;
-      if (need != ~0ull) continue;  // that direction is taken: a second move of the same kind opens its own slot
-      need = m.need;
-      (down ? k.s.coef_down : k.s.coef_up) = m.coef;
-      placed = true;
-      break;
-    }
-    if (placed) continue;
-    Keyed k;
-    k.s.flip = m.flip;
-    k.s.mask = m.mask;
-    k.s.need_down = down ? m.need : ~0ull;
-    k.s.need_up = down ? ~0ull : m.need;
-    k.s.coef_down = down ? m.coef : 0.0;
-    k.s.coef_up = down ? 0.0 : m.coef;
-    k.abs_delta = ad;
-    k.seq = keyed.size();
-    keyed.push_back(k);
-  }
-  std::stable_sort(keyed.begin(), keyed.end(), [](const Keyed &x, const Keyed &y) { return x.abs_delta < y.abs_delta; });
-  op->slots.clear();
-  for (const Keyed &k : keyed) op->slots.push_back(k.s);
-}
-
 }  // namespace asp
 
 using asp::DiagBond;
@@ -324,7 +280,6 @@ int asp_operator_create(asp_operator **out, uint32_t number_spins, int32_t hammi
       }
     }
   asp::build_diag_groups(op);
-  asp::build_slots(op);
   for (uint32_t g = 0; g < num_perms; ++g) {
     asp::BitPerm net;
     if (!asp::make_bit_perm(perms + static_cast<size_t>(g) * number_spins, number_spins, net)) {
@@ -346,7 +301,6 @@ int asp_operator_create(asp_operator **out, uint32_t number_spins, int32_t hammi
       return ASP_OK;
     };
     int rc = upload(op->d_moves, op->moves);
-    if (rc == ASP_OK) rc = upload(op->d_slots, op->slots);
     if (rc == ASP_OK) rc = upload(op->d_diag, op->diag);
     if (rc == ASP_OK) rc = upload(op->d_diag_groups, op->diag_groups);
     if (rc == ASP_OK) rc = upload(op->d_perms, op->perms);
@@ -363,7 +317,6 @@ int asp_operator_create(asp_operator **out, uint32_t number_spins, int32_t hammi
 void asp_operator_destroy(asp_operator *op) {
   if (!op) return;
   if (op->d_moves) cudaFree(op->d_moves);
-  if (op->d_slots) cudaFree(op->d_slots);
   if (op->d_diag) cudaFree(op->d_diag);
   if (op->d_diag_groups) cudaFree(op->d_diag_groups);
   if (op->d_perms) cudaFree(op->d_perms);
@@ -372,22 +325,6 @@ void asp_operator_destroy(asp_operator *op) {
 }
 
 uint32_t asp_operator_max_candidates(asp_operator const *op) { return op ? op->max_candidates() : 0; }
-
-uint32_t asp_debug_operator_slots(asp_operator const *op, uint32_t capacity, uint64_t *flip, uint64_t *mask, uint64_t *need_down,
-                                  uint64_t *need_up, double *coef_down, double *coef_up) {
-  if (!op) return 0;
-  const uint32_t n = static_cast<uint32_t>(op->slots.size());
-  for (uint32_t k = 0; k < n && k < capacity; ++k) {
-    const asp::Slot &sl = op->slots[k];
-    if (flip) flip[k] = sl.flip;
-    if (mask) mask[k] = sl.mask;
-    if (need_down) need_down[k] = sl.need_down;
-    if (need_up) need_up[k] = sl.need_up;
-    if (coef_down) coef_down[k] = sl.coef_down;
-    if (coef_up) coef_up[k] = sl.coef_up;
-  }
-  return n;
-}
 int asp_operator_is_sorted_emitter(asp_operator const *op) { return op && op->sorted_emitter() ? 1 : 0; }
 
 }  // extern "C"

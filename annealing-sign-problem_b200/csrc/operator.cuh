@@ -34,17 +34,6 @@ struct DiagGroup {
   uint32_t shift;
 };
 
-// Moves grouped for the single-pass extraction kernel (extract_fused.cu).  A slot holds the (at most
-// two) moves that share one flip mask AND one |delta|: the "down" move (image < word) and the "up"
-// move (image > word).  They never apply to the same word, so a slot yields at most one candidate
-// s ^ flip per row.  Slots are sorted by |delta| ascending: walking them in order meets the down
-// images of ANY row in descending and its up images in ascending key order.
-struct Slot {
-  uint64_t flip, mask;
-  uint64_t need_down, need_up;  // ~0: the slot has no move in that direction
-  double coef_down, coef_up;
-};
-
 // A permutation of <= 64 bits as a Benes network of delta swaps:
 // x = delta_swap(x, mask[k], shift[k]) for k = 0..stages-1.
 struct BitPerm {
@@ -65,13 +54,11 @@ struct asp_operator {
   int64_t diag_c0 = 0;
   int32_t diag_scale = -1;
   bool distinct_flips = true;
-  std::vector<asp::Slot> slots;  // |delta|-sorted (flip, |delta|) groups of the moves
   // symmetry group (non-identity permutations), real characters
   std::vector<asp::BitPerm> perms;
   std::vector<double> characters;
   // device mirrors (device current at creation)
   asp::Move *d_moves = nullptr;
-  asp::Slot *d_slots = nullptr;
   asp::DiagBond *d_diag = nullptr;
   asp::DiagGroup *d_diag_groups = nullptr;
   asp::BitPerm *d_perms = nullptr;

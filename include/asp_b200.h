@@ -153,18 +153,12 @@ int asp_extract_csr(asp_operator const *op, uint64_t n_total, uint64_t const *d_
                     double const *d_psi, uint64_t row_begin, uint64_t num_rows, void *d_workspace,
                     size_t workspace_bytes, uint64_t capacity, int64_t *d_indptr,
                     int32_t *d_indices, double *d_data, uint64_t *h_nnz, void *stream);
-/* Test hooks.  Entries of one shared-memory hit list of a warp of the single-pass kernel
- * (0 = automatic): small values force the spill path.  Tuning: bucket_bits_delta changes the
- * log2 number of index buckets relative to the automatic choice (coarse buckets send most
- * candidates to the exact search and make it bisect), diag_mode 1 = sum the diagonal bond by
- * bond instead of in closed form. */
+/* Test hooks.  Survivor-list entries per warp of the single-pass kernel (0 = automatic, 512):
+ * small values force many exact-search rounds per tile.  Tuning: change the log2 size of the
+ * Bloom filter / first-position table relative to the automatic choice, stage_a_mode 1 = test
+ * move applicability lane by lane instead of on bit planes. */
 void asp_debug_set_hit_list_capacity(int entries_per_warp);
-/* The operator's slots as the single-pass kernel walks them (|delta| ascending; a slot = the down
- * and the up move that share one flip mask; need = ~0: no move in that direction).  Returns the
- * number of slots; fills at most `capacity` entries of every non-NULL array. */
-uint32_t asp_debug_operator_slots(asp_operator const *op, uint32_t capacity, uint64_t *flip, uint64_t *mask,
-                                  uint64_t *need_down, uint64_t *need_up, double *coef_down, double *coef_up);
-void asp_debug_set_extract_tuning(int bucket_bits_delta, int reserved, int diag_mode);
+void asp_debug_set_extract_tuning(int filter_bits_delta, int table_bits_delta, int stage_a_mode);
 /* Measurement hook: when enabled, every launch of the single-pass extraction kernel is bracketed by
  * CUDA events on its own stream; the second call returns the device time of the LAST such launch
  * (milliseconds; synchronises on it; -1 if none). */
