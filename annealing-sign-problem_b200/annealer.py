@@ -57,6 +57,10 @@ class Hamiltonian:
             csr = scipy.sparse.csr_matrix(self.exchange)
             csr.sum_duplicates()
             csr.sort_indices()
+            # the annealer and the greedy solver take dE from row p alone and colour the graph by row adjacency: both
+            # are only right for a symmetric exchange matrix (E = s^T J s with J = J^T, as make_ising_model builds it)
+            if csr.shape[0] != csr.shape[1] or (csr != csr.T).nnz != 0:
+                raise ValueError("'exchange' must be a symmetric matrix")
             fld = torch.from_numpy(self.field).to(dev) if self.field.any() else None
             self._dev = (
                 torch.from_numpy(csr.indptr.astype(np.int64)).to(dev),

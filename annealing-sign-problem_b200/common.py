@@ -321,11 +321,19 @@ def make_ising_model(
     tock = time.time()
     logger.debug("extraction took {:.4f} seconds", tock - tick)
 
-    h_indptr = indptr.cpu().numpy()
-    h_indices = indices.cpu().numpy()
-    h_data = data.cpu().numpy()
-    matrix = scipy.sparse.csr_matrix((h_data, h_indices, h_indptr.astype(np.int32) if h_data.shape[0] < 2 ** 31 else h_indptr),
-                                     shape=(n, n)).tocoo()
+    # COO as the reference returns it (common.py:195-196: csr -> sort_indices -> tocoo): the row of every entry is made
+    # on the device and the three arrays cross PCIe once, into pinned host memory (no CSR -> COO pass on the CPU)
+    index_dtype = torch.int32 if max(n, int(indices.shape[0])) < 2 ** 31 else torch.int64
+    rows = torch.repeat_interleave(torch.arange(n, dtype=index_dtype, device=dev), indptr[1:] - indptr[:-1])
+    h_rows = torch.empty(rows.shape, dtype=rows.dtype, pin_memory=True)
+    h_cols = torch.empty(indices.shape, dtype=index_dtype, pin_memory=True)
+    h_data = torch.empty(data.shape, dtype=data.dtype, pin_memory=True)
+    h_rows.copy_(rows, non_blocking=True)
+    h_cols.copy_(indices if index_dtype == torch.int32 else indices.to(index_dtype), non_blocking=True)
+    h_data.copy_(data, non_blocking=True)
+    del rows
+    torch.cuda.synchronize()
+    matrix = scipy.sparse.coo_matrix((h_data.numpy(), (h_rows.numpy(), h_cols.numpy())), shape=(n, n), copy=False)
     field = np.zeros(n, dtype=np.float64)
     ising_hamiltonian = sa.Hamiltonian(matrix, field, _device_csr=(indptr, indices, data, None))
     x0 = sa.signs_to_bits_device(psi).cpu().numpy().view(np.uint64)

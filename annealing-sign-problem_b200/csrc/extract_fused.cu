@@ -26,6 +26,9 @@
 // Every lane enumerates its moves in ascending key-delta order, so hits get ascending columns;
 // positions are exact indices into the sorted basis (bit-exact CSR) and values are
 // (coef * |psi_j|) * |psi_i|, the association of the reference's live path (common.py:71-82), as in extract.cu.
+#include <mutex>
+#include <unordered_set>
+
 #include "fused.cuh"
 
 namespace asp {
@@ -702,6 +705,20 @@ static FusedWorkspace carve_fused(void *base, const asp_operator *op, uint64_t n
   return w;
 }
 
+// The index asp_gather_index leaves in a workspace is single-use: the extraction consumes the tickets and the
+// look-back words.  The library remembers which workspaces hold a fresh index so that a second extraction
+// without a new asp_gather_index is refused instead of silently writing nothing.
+static std::mutex g_indexed_mu;
+static std::unordered_set<const void *> g_indexed;
+void fused_mark_indexed(const void *workspace) {
+  std::lock_guard<std::mutex> lock(g_indexed_mu);
+  g_indexed.insert(workspace);
+}
+bool fused_consume_indexed(const void *workspace) {
+  std::lock_guard<std::mutex> lock(g_indexed_mu);
+  return g_indexed.erase(workspace) > 0;
+}
+
 size_t fused_workspace_bytes(const asp_operator *op, uint64_t n_total, uint64_t num_rows) {
   return carve_fused(nullptr, op, n_total, num_rows).bytes;
 }
@@ -1025,6 +1042,8 @@ static int extract_csr_impl(asp_operator const *op, uint64_t n_total, uint64_t c
   ASP_REQUIRE(d_spins && d_psi, "NULL input buffer");
   if (indexed) {  // the workspace was zeroed and indexed for this very (n_total, num_rows) by asp_gather_index
     ASP_REQUIRE(d_workspace != nullptr && workspace_bytes >= fused_workspace_bytes(op, n_total, num_rows), "workspace too small");
+    ASP_REQUIRE(fused_consume_indexed(d_workspace),
+                "the workspace holds no fresh index: call asp_gather_index before every indexed extraction (the index is single-use)");
   } else {
     rc = fused_prepare(op, n_total, d_spins, num_rows, d_workspace, workspace_bytes, s);
     if (rc != ASP_OK) return rc;
@@ -1065,10 +1084,13 @@ int asp_gather_index(asp_operator const *op, uint32_t world, uint32_t rank, uint
   ASP_REQUIRE(shard_begin[world] > 0 && shard_begin[world] < (1ull << 31), "the gathered basis needs 0 < n_total < 2^31");
   ASP_REQUIRE(d_spins && d_psi, "NULL output buffer");
   if (g_gather_mode != 0)
-    return fused_prepare_gather(op, world, rank, shard_begin, d_shard_spins, d_shard_psi, d_ready, epoch, d_spins, d_psi, num_rows,
-                                d_workspace, workspace_bytes, static_cast<cudaStream_t>(stream), g_gather_mode == 2);
-  return fused_prepare_gather_ce(op, world, rank, shard_begin, d_shard_spins, d_shard_psi, d_ready, epoch, d_spins, d_psi, num_rows,
+    rc = fused_prepare_gather(op, world, rank, shard_begin, d_shard_spins, d_shard_psi, d_ready, epoch, d_spins, d_psi, num_rows,
+                              d_workspace, workspace_bytes, static_cast<cudaStream_t>(stream), g_gather_mode == 2);
+  else
+    rc = fused_prepare_gather_ce(op, world, rank, shard_begin, d_shard_spins, d_shard_psi, d_ready, epoch, d_spins, d_psi, num_rows,
                                  d_workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+  if (rc == ASP_OK) fused_mark_indexed(d_workspace);
+  return rc;
 }
 
 int asp_gather_blocks(uint32_t world, uint32_t rank, uint64_t const *shard_begin, uint64_t const *const *d_shard_spins,

@@ -286,6 +286,8 @@ static int extract_indexed_to_host_impl(asp_operator const *op, uint64_t n, uint
   }
   ASP_REQUIRE(d_spins && d_psi && d_workspace, "NULL device buffer");
   ASP_REQUIRE(workspace_bytes >= asp::fused_workspace_bytes(op, n, num_rows), "workspace too small");
+  ASP_REQUIRE(asp::fused_consume_indexed(d_workspace),
+              "the workspace holds no fresh index: call asp_gather_index before every indexed extraction (the index is single-use)");
   Arena &A = g_arena;
   rc = acquire(A);
   if (rc != ASP_OK) return rc;

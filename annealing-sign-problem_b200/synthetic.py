@@ -80,6 +80,34 @@ def cluster_closed_states(operator, n: int, seed: int, device="cuda", interior_f
     return pool.contiguous()
 
 
+def representative_cluster_states(operator, n: int, seed: int, device="cuda") -> torch.Tensor:
+    """Cluster-closed subset of a SYMMETRISED basis: only images of batched_apply are kept (they are orbit
+    representatives by construction, random words of the sector are not): first shell of random seeds, then a
+    random part of the second shell up to n states.  Needs CUDA."""
+    basis = operator.basis
+    d = max(2.0, operator.max_candidates / 4.0)
+    m = max(8, int(n / (d * d)) + 1)
+    seeds = random_sector_states(basis.number_spins, basis.hamming_weight, m, seed, device)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed + 1)
+    pool = _sorted_unique_unsigned(operator.batched_apply_device(seeds)[0])
+    while pool.shape[0] < n:
+        grown = torch.zeros(0, dtype=torch.int64, device=device)
+        for start in range(0, pool.shape[0], 1 << 18):  # bounded candidate buffers (a group orbit per candidate)
+            shell, _, _ = operator.batched_apply_device(pool[start:start + (1 << 18)])
+            grown = _sorted_unique_unsigned(torch.cat([grown, shell]))
+            if pool.shape[0] + grown.shape[0] > 4 * n:
+                break
+        new = _setdiff_sorted(grown, pool)
+        if new.shape[0] == 0:
+            break
+        need = n - pool.shape[0]
+        if new.shape[0] > need:
+            new = new[torch.sort(torch.randperm(new.shape[0], generator=gen, device=device)[:need]).values]
+        pool = _sorted_unique_unsigned(torch.cat([pool, new]))
+    return pool.contiguous()
+
+
 def synthetic_amplitudes(n: int, seed: int, sigma: float = 2.0, device="cpu") -> torch.Tensor:
     """psi_i = +-exp(sigma z_i), z ~ N(0,1), uniform sign, L2-normalised (common.py:181)."""
     gen = torch.Generator(device=device)

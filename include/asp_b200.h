@@ -228,6 +228,10 @@ int asp_accuracy_overlap(uint64_t n, uint32_t num_replicas, uint64_t const *d_pr
  *    relabelled CSR on the device.  A sweep visits positions 0..n_padded-1 in order; spins
  *    of one class do not interact, so the kernel updates a class in parallel and the
  *    result equals the sequential sweep (DESIGN.md "SA chain definition").
+ *    The CSR must be SYMMETRIC (J = J^T; dE is taken from row p alone and the colouring looks
+ *    at row adjacency only) -- the caller's job, like the reference's preconditions; the Python
+ *    mirror checks it.  The plan BORROWS d_indptr / d_indices / d_data / d_field (the greedy
+ *    solver and the energy pass read the original model): they must outlive the plan.
  * ---------------------------------------------------------------------------------- */
 int asp_sa_plan_create(asp_sa_plan **out, uint64_t n, int64_t const *d_indptr,
                        int32_t const *d_indices, double const *d_data, double const *d_field,
@@ -342,7 +346,9 @@ int asp_extract_indexed_to_host_i32(asp_operator const *op, uint64_t n_total, ui
  * it has landed. */
 void asp_set_gather_mode(int mode);
 /* asp_extract_csr without its zero + index pass: the workspace was prepared by asp_gather_index
- * for the same (op, n_total, num_rows) on the same stream. */
+ * for the same (op, n_total, num_rows) on the same stream.  The index is SINGLE-USE (the extraction
+ * consumes its tickets and look-back words): a second indexed extraction on the same workspace without
+ * a new asp_gather_index returns ASP_ERR_ARG. */
 int asp_extract_csr_indexed(asp_operator const *op, uint64_t n_total, uint64_t const *d_spins,
                             double const *d_psi, uint64_t row_begin, uint64_t num_rows,
                             void *d_workspace, size_t workspace_bytes, uint64_t capacity,

@@ -15,7 +15,7 @@ if not torch.cuda.is_available():
 
 import annealing_sign_problem_b200 as asp  # noqa: E402
 from annealing_sign_problem_b200 import common, synthetic  # noqa: E402
-from annealing_sign_problem_b200._lib import ffi, lib  # noqa: E402
+from annealing_sign_problem_b200._lib import AspError, ffi, lib  # noqa: E402
 from oracle import live_path  # noqa: E402
 from oracle.operator_np import OperatorNP  # noqa: E402
 
@@ -292,6 +292,9 @@ def test_gather_index_kernel_over_emulated_shards_equals_the_unsharded_build():
             lo, hi = int(ref[0][row_begin]), int(ref[0][row_begin + num_rows])
             assert torch.equal(indptr, ref[0][row_begin:row_begin + num_rows + 1] - lo)
             assert torch.equal(indices, ref[1][lo:hi]) and torch.equal(data, ref[2][lo:hi])
+            if mode == 2:  # the index is single-use: a second extraction without a new asp_gather_index is refused
+                with pytest.raises(AspError, match="single-use"):
+                    common.extract_csr_indexed_device(op, full_s, full_p, row_begin, num_rows, workspace, capacity=int(ref[1].numel()))
             if mode == 2 and world == 4:  # the sharded host-buffer path: gather again, CSR straight into pinned host memory
                 common.check(lib().asp_gather_index(
                     op.handle, world, rank, ffi.new("uint64_t[]", bounds),
