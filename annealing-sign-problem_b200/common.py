@@ -275,14 +275,17 @@ def make_ising_model(
     d_spins, first, counts = _sort_unique_device(d_spins_in)
     if bool((counts != 1).any()):
         logger.warning("'spins' were not unique, are you sure this is what you want?")
+    h_sorted = torch.empty(d_spins.shape, dtype=torch.int64, pin_memory=True)
+    h_sorted.copy_(d_spins, non_blocking=True)
     if log_psi is not None:
-        log_psi = np.asarray(log_psi)[first.cpu().numpy()]  # first occurrence, sorted order (common.py:149-151)
-    spins = d_spins.cpu().numpy().view(np.uint64)
+        # first occurrence, sorted order (common.py:149-151) -- gathered on the device
+        d_log_psi = torch.from_numpy(np.ascontiguousarray(log_psi, dtype=np.complex128)).to(dev)[first]
+    torch.cuda.synchronize()
+    spins = h_sorted.numpy().view(np.uint64)
     if log_psi is None:
-        log_psi = log_psi_fn(spins)
+        d_log_psi = torch.from_numpy(np.ascontiguousarray(log_psi_fn(spins), dtype=np.complex128)).to(dev)
     n = spins.shape[0]
 
-    d_log_psi = torch.from_numpy(np.ascontiguousarray(log_psi, dtype=np.complex128)).to(dev)
     psi = torch.exp(d_log_psi)
     if not bool(torch.all(psi.imag.abs() <= 1e-6)):
         raise ValueError("expected all wavefunction coefficients to be real")

@@ -11,6 +11,8 @@
 // Device buffers, streams and events live in a process-wide arena that only grows, so repeated
 // calls pay no cudaMalloc/cudaFree (each costs a device synchronisation).
 #include <mutex>
+#include <string>
+#include <thread>
 
 #include "fused.cuh"
 
@@ -78,16 +80,34 @@ struct Arena {
   }
 };
 
-Arena g_arena;
+// Two arenas: two host extractions can be in flight, so that the upload of call k+1 rides under the download of
+// call k on the full-duplex host link (asp_extract_host_i32_submit / asp_extract_host_join).
+constexpr int kArenas = 2;
+Arena g_arenas[kArenas];
+std::mutex g_arenas_mu;
 
-int acquire(Arena &A) {
-  std::lock_guard<std::mutex> lock(A.mu);
-  ASP_REQUIRE(!A.busy, "another host extraction is in flight (one job at a time per process)");
+int acquire(Arena *&out) {
+  std::lock_guard<std::mutex> pick(g_arenas_mu);
   int device = 0;
   ASP_CUDA_CHECK(cudaGetDevice(&device));
-  int rc = A.init(device);
+  Arena *chosen = nullptr;
+  for (Arena &A : g_arenas)  // prefer an arena that already holds buffers for this device
+    if (!A.busy && A.device == device) {
+      chosen = &A;
+      break;
+    }
+  if (!chosen)
+    for (Arena &A : g_arenas)
+      if (!A.busy) {
+        chosen = &A;
+        break;
+      }
+  ASP_REQUIRE(chosen != nullptr, "two host extractions are already in flight (at most two jobs per process)");
+  std::lock_guard<std::mutex> lock(chosen->mu);
+  int rc = chosen->init(device);
   if (rc != ASP_OK) return rc;
-  A.busy = true;
+  chosen->busy = true;
+  out = chosen;
   return ASP_OK;
 }
 
@@ -183,13 +203,20 @@ out:
 
 struct asp_host_job {
   uint64_t num_rows = 0, nnz = 0;
+  Arena *arena = nullptr;  // begin / finish: the arena the job holds
+  std::thread worker;      // submit / join: the thread that runs the blocking call
+  int rc = ASP_OK;
+  std::string error;
 };
 
 extern "C" {
 
 void asp_host_release(void) {
-  std::lock_guard<std::mutex> lock(g_arena.mu);
-  if (!g_arena.busy) g_arena.release();
+  std::lock_guard<std::mutex> pick(g_arenas_mu);
+  for (Arena &A : g_arenas) {
+    std::lock_guard<std::mutex> lock(A.mu);
+    if (!A.busy) A.release();
+  }
 }
 
 static int extract_host_impl(asp_operator const *op, uint64_t n, uint64_t const *h_spins, double const *h_psi, uint64_t row_begin,
@@ -210,9 +237,10 @@ static int extract_host_impl(asp_operator const *op, uint64_t n, uint64_t const 
       static_cast<int64_t *>(h_indptr)[0] = 0;
     return ASP_OK;
   }
-  Arena &A = g_arena;
-  rc = acquire(A);
+  Arena *arena = nullptr;
+  rc = acquire(arena);
   if (rc != ASP_OK) return rc;
+  Arena &A = *arena;
   {
     // row chunks: multiples of the tile, at most kFusedMaxChunks, about 2^20 rows each
     uint64_t chunk_rows = (num_rows + 7) / 8;
@@ -288,9 +316,10 @@ static int extract_indexed_to_host_impl(asp_operator const *op, uint64_t n, uint
   ASP_REQUIRE(workspace_bytes >= asp::fused_workspace_bytes(op, n, num_rows), "workspace too small");
   ASP_REQUIRE(asp::fused_consume_indexed(d_workspace),
               "the workspace holds no fresh index: call asp_gather_index before every indexed extraction (the index is single-use)");
-  Arena &A = g_arena;
-  rc = acquire(A);
+  Arena *arena = nullptr;
+  rc = acquire(arena);
   if (rc != ASP_OK) return rc;
+  Arena &A = *arena;
   {
     uint64_t chunk_rows = (num_rows + 7) / 8;
     if (chunk_rows < (1u << 17)) chunk_rows = 1u << 17;
@@ -344,11 +373,13 @@ int asp_extract_host_begin(asp_operator const *op, uint64_t n, uint64_t const *h
   ASP_REQUIRE(n == 0 || (h_spins && h_psi), "NULL input buffer");
   ASP_REQUIRE(n < (1ull << 31), "int32 column indices need n_total < 2^31 (scipy picks int32 the same way)");
   ASP_REQUIRE(row_begin + num_rows <= n, "row block exceeds the basis");
-  Arena &A = g_arena;
-  rc = acquire(A);
+  Arena *arena = nullptr;
+  rc = acquire(arena);
   if (rc != ASP_OK) return rc;
+  Arena &A = *arena;
   auto *job = new asp_host_job();
   job->num_rows = num_rows;
+  job->arena = arena;
   {
     const size_t ws_bytes = asp::fused_workspace_bytes(op, n, num_rows);
     const uint64_t worst = num_rows * op->max_candidates();
@@ -391,7 +422,8 @@ out:
 
 int asp_extract_host_finish(asp_host_job *job, int64_t *h_indptr, int32_t *h_indices, double *h_data) {
   ASP_REQUIRE(job != nullptr, "job is NULL");
-  Arena &A = g_arena;
+  ASP_REQUIRE(job->arena != nullptr, "the job was not started by asp_extract_host_begin");
+  Arena &A = *job->arena;
   int rc = ASP_OK;
   if (!h_indptr || (job->nnz != 0 && (!h_indices || !h_data))) {
     asp::set_error("asp_extract_host_finish: NULL output buffer");
@@ -412,6 +444,42 @@ int asp_extract_host_finish(asp_host_job *job, int64_t *h_indptr, int32_t *h_ind
 out:
   delete job;
   release_busy(A);
+  return rc;
+}
+
+// Asynchronous form of asp_extract_host_i32: the blocking call runs on a worker thread with its own arena (device
+// buffers, streams), so a second submit can upload its basis while this job's CSR is still travelling back.
+int asp_extract_host_i32_submit(asp_operator const *op, uint64_t n, uint64_t const *h_spins, double const *h_psi, uint64_t row_begin,
+                                uint64_t num_rows, uint64_t capacity, int32_t *h_indptr, int32_t *h_indices, double *h_data,
+                                asp_host_job **out_job) {
+  ASP_REQUIRE(out_job != nullptr, "out_job is NULL");
+  int device = 0;
+  ASP_CUDA_CHECK(cudaGetDevice(&device));
+  auto *job = new asp_host_job();
+  job->num_rows = num_rows;
+  job->worker = std::thread([=]() {
+    if (cudaSetDevice(device) != cudaSuccess) {
+      job->rc = ASP_ERR_CUDA;
+      job->error = "cudaSetDevice failed on the worker thread";
+      return;
+    }
+    uint64_t nnz = 0;
+    job->rc = extract_host_impl(op, n, h_spins, h_psi, row_begin, num_rows, capacity, h_indptr, true, h_indices, h_data, &nnz);
+    job->nnz = nnz;
+    if (job->rc != ASP_OK) job->error = asp_last_error();  // the error text is per thread: carry it to the joiner
+  });
+  *out_job = job;
+  return ASP_OK;
+}
+
+int asp_extract_host_join(asp_host_job *job, uint64_t *h_nnz) {
+  ASP_REQUIRE(job != nullptr, "job is NULL");
+  ASP_REQUIRE(job->worker.joinable(), "the job was not started by asp_extract_host_i32_submit");
+  job->worker.join();
+  const int rc = job->rc;
+  if (h_nnz) *h_nnz = job->nnz;
+  if (rc != ASP_OK) asp::set_error("%s", job->error.c_str());
+  delete job;
   return rc;
 }
 

@@ -205,8 +205,18 @@ int asp_extract_host_begin(asp_operator const *op, uint64_t n_total, uint64_t co
                            double const *h_psi, uint64_t row_begin, uint64_t num_rows,
                            uint64_t *h_nnz, asp_host_job **job);
 int asp_extract_host_finish(asp_host_job *job, int64_t *h_indptr, int32_t *h_indices, double *h_data);
-/* The host entry points keep their device buffers in a process-wide arena that only grows
- * (one job in flight at a time); this frees it. */
+/* asp_extract_host_i32 without blocking the caller: the call runs on a worker thread with its own
+ * device buffers and streams; asp_extract_host_join waits for it, returns its code (the error text
+ * moves to the joining thread) and frees the job.  Two jobs may be in flight: submitting call k+1
+ * before joining call k lets its upload and extraction ride under call k's download (the host link
+ * is full duplex).  The caller's buffers must stay untouched until the join. */
+int asp_extract_host_i32_submit(asp_operator const *op, uint64_t n_total, uint64_t const *h_spins,
+                                double const *h_psi, uint64_t row_begin, uint64_t num_rows,
+                                uint64_t capacity, int32_t *h_indptr, int32_t *h_indices,
+                                double *h_data, asp_host_job **job);
+int asp_extract_host_join(asp_host_job *job, uint64_t *h_nnz);
+/* The host entry points keep their device buffers in two process-wide arenas that only grow
+ * (at most two jobs in flight); this frees the idle ones. */
 void asp_host_release(void);
 
 /* ------------------------------------------------------------------------------------

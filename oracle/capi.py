@@ -1,6 +1,6 @@
 """ctypes bindings of the CPU oracle libraries (TEST INFRASTRUCTURE ONLY).
 
-* ``oracle/_lib/liboracle.so``          -- extract_port.c + anneal_port.c + greedy_port.c (our restatements)
+* ``oracle/_lib/liboracle.so``          -- extract_port.c + anneal_port.c + greedy_port.c + colour_port.c (our restatements)
 * ``oracle/_ref/libref_build_matrix.so`` -- the reference's cbits/build_matrix.c, compiled
   where it lies by ``oracle/Makefile``; exports the two symbols of cbits/build_matrix.h:7-14.
 """
@@ -62,6 +62,12 @@ def port():
         lib.oracle_greedy.argtypes = [_u64, _p, _p, _p, _p, _p]
         lib.oracle_anneal.restype = None
         lib.oracle_anneal.argtypes = [_u64, _p, _p, _p, _p, _u32, _u32, _p, _u64, _p, _f64, _p, _p, _p, _u32]
+        lib.oracle_colour.restype = _u32
+        lib.oracle_colour.argtypes = [_u64, _p, _p, _p]
+        lib.oracle_positions.restype = _u64
+        lib.oracle_positions.argtypes = [_u64, _u32, _p, _p, _p, _p]
+        lib.oracle_relabel.restype = _u64
+        lib.oracle_relabel.argtypes = [_u64, _u64] + [_p] * 10
         _port = lib
     return _port
 
@@ -205,3 +211,28 @@ def anneal(indptr, indices, data, field, repetitions, betas, seed, x0=None, esca
                          _ptr(betas), int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(x0), float(escale),
                          _ptr(best), _ptr(best_rel), _ptr(final_rel), int(threads))
     return best, best_rel, final_rel
+
+
+def plan(indptr, indices, data, field):
+    """oracle/colour_port.c: the annealing plan of a CSR model (greedy colouring in (hash, index) priority, classes
+    padded to multiples of 4, relabelled CSR without the diagonal) -> dict like AnnealPlan.export()."""
+    indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+    indices = np.ascontiguousarray(indices, dtype=np.int32)
+    data = np.ascontiguousarray(data, dtype=np.float64)
+    field = None if field is None else np.ascontiguousarray(field, dtype=np.float64)
+    n = indptr.shape[0] - 1
+    colour = np.empty(n, dtype=np.int32)
+    classes = int(port().oracle_colour(n, _ptr(indptr), _ptr(indices), _ptr(colour)))
+    class_ptr = np.empty(classes + 1, dtype=np.int64)
+    n_padded = int(port().oracle_positions(n, classes, _ptr(colour), _ptr(class_ptr), None, None))
+    order = np.empty(n_padded, dtype=np.int32)
+    position = np.empty(n, dtype=np.int32)
+    port().oracle_positions(n, classes, _ptr(colour), _ptr(class_ptr), _ptr(order), _ptr(position))
+    out_indptr = np.empty(n_padded + 1, dtype=np.int64)
+    out_cols = np.empty(max(indices.shape[0], 1), dtype=np.int32)
+    out_vals = np.empty(max(indices.shape[0], 1), dtype=np.float64)
+    out_field = np.empty(n_padded, dtype=np.float64)
+    nnz = int(port().oracle_relabel(n, n_padded, _ptr(indptr), _ptr(indices), _ptr(data), _ptr(field), _ptr(order), _ptr(position),
+                                    _ptr(out_indptr), _ptr(out_cols), _ptr(out_vals), _ptr(out_field)))
+    return dict(order=order, position=position, class_ptr=class_ptr, indptr=out_indptr, indices=out_cols[:nnz], data=out_vals[:nnz],
+                field=out_field, colour=colour)

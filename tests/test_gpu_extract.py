@@ -435,6 +435,41 @@ def test_properties_at_scale(system, states):
         assert np.array_equal(h_data[h_indptr[r]:h_indptr[r + 1]], vals[order])  # same association: bitwise
 
 
+def test_full_matrix_equals_the_reference_c_at_a_million_states(oracle_capi):
+    """EVERY row of a 10^6-state extraction (kagome_36-shaped, 4.6e6 couplings) against the reference's own compiled C
+    (oracle/_ref = cbits/build_matrix.c, 512-bit keys), fed row chunk by row chunk with the oracle's neighbour lists:
+    row starts and columns bit for bit, values to 1e-12 (the C path multiplies in another order)."""
+    if not oracle_capi.have_ref():
+        pytest.skip("oracle/_ref was not built (no /root/reference at build time)")
+    from oracle.capi import pad512
+
+    cfg = asp.ls.load_config(asp.ls.system_path("heisenberg_kagome_36"))
+    cfg["basis"]["symmetries"], cfg["basis"]["spin_inversion"] = [], None
+    op = asp.ls.Operator.load_from_yaml(cfg["hamiltonian"], asp.ls.SpinBasis.load_from_yaml(cfg["basis"]))
+    op_np = OperatorNP.from_config(cfg)
+    spins = synthetic.cluster_closed_states(op, 1_000_000, 31, DEV)
+    n = spins.shape[0]
+    psi = synthetic.synthetic_amplitudes(n, 31, device=DEV)
+    indptr, indices, data = (t.cpu().numpy() for t in common.extract_csr_device(op, spins, psi))
+    h_spins, h_psi = spins.cpu().numpy().view(np.uint64), psi.cpu().numpy()
+    s512 = pad512(h_spins)
+    counts = np.ones(n, dtype=np.int64)
+    step = 125_000
+    for lo in range(0, n, step):
+        hi = min(lo + step, n)
+        other, coeffs, k = op_np.apply_u64(h_spins[lo:hi])
+        pos = np.clip(np.searchsorted(h_spins, other), 0, n - 1)
+        other_psi = np.where(h_spins[pos] == other, h_psi[pos], 0.0)
+        other_counts = np.zeros(n, dtype=np.int64)
+        other_counts[lo:hi] = k
+        rows, cols, vals, _ = oracle_capi.build_matrix(s512, counts, h_psi, pad512(other), coeffs, other_counts, other_psi, impl="ref")
+        order = np.lexsort((cols, rows))
+        rows, cols, vals = rows[order], cols[order], vals[order]
+        assert np.array_equal(np.bincount(rows.astype(np.int64) - lo, minlength=hi - lo), np.diff(indptr[lo:hi + 1]))
+        assert np.array_equal(cols.astype(np.int32), indices[indptr[lo]:indptr[hi]])
+        np.testing.assert_allclose(data[indptr[lo]:indptr[hi]], vals, rtol=1e-12, atol=0)
+
+
 def test_host_buffer_entry_points_match_device_path():
     op = asp.load_hamiltonian(asp.ls.system_path("j1j2_square_4x4"))
     spins = synthetic.cluster_closed_states(op, 5000, 2, DEV)
@@ -456,6 +491,36 @@ def test_host_buffer_entry_points_match_device_path():
     assert rc == 0
     assert np.array_equal(hp, indptr.cpu().numpy()) and np.array_equal(hi, indices.cpu().numpy())
     assert np.array_equal(hd, data.cpu().numpy())
+
+
+def test_two_host_extractions_in_flight_match_the_device_path():
+    """asp_extract_host_i32_submit / asp_extract_host_join: two jobs on different bases run concurrently (two arenas),
+    each equals the device path."""
+    op = asp.load_hamiltonian(asp.ls.system_path("j1j2_square_4x4"))
+    cases = []
+    for seed, n in [(3, 4000), (4, 9000)]:
+        spins = synthetic.cluster_closed_states(op, n, seed, DEV)
+        psi = synthetic.synthetic_amplitudes(spins.shape[0], seed, device=DEV)
+        ref = common.extract_csr_device(op, spins, psi)
+        m = int(ref[1].numel())
+        h = dict(spins=spins.cpu().pin_memory(), psi=psi.cpu().pin_memory(), indptr=torch.zeros(spins.shape[0] + 1, dtype=torch.int32).pin_memory(),
+                 indices=torch.zeros(m + 7, dtype=torch.int32).pin_memory(), data=torch.zeros(m + 7, dtype=torch.float64).pin_memory())
+        cases.append((ref, m, h))
+    jobs = []
+    for ref, m, h in cases:
+        job = ffi.new("asp_host_job **")
+        n = h["spins"].shape[0]
+        common.check(lib().asp_extract_host_i32_submit(op.handle, n, ffi.cast("uint64_t *", h["spins"].data_ptr()), ffi.cast("double *", h["psi"].data_ptr()),
+                                                       0, n, m + 7, ffi.cast("int32_t *", h["indptr"].data_ptr()),
+                                                       ffi.cast("int32_t *", h["indices"].data_ptr()), ffi.cast("double *", h["data"].data_ptr()), job))
+        jobs.append(job[0])
+    for job, (ref, m, h) in zip(jobs, cases):
+        nnz = ffi.new("uint64_t *")
+        common.check(lib().asp_extract_host_join(job, nnz))
+        assert int(nnz[0]) == m
+        assert torch.equal(h["indptr"].to(torch.int64), ref[0].cpu())
+        assert torch.equal(h["indices"][:m], ref[1].cpu()) and torch.equal(h["data"][:m], ref[2].cpu())
+    assert lib().asp_extract_host_join(ffi.NULL, ffi.NULL) == lib().ASP_ERR_ARG
 
 
 def _u1_operator(system):
