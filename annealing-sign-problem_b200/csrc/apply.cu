@@ -4,6 +4,8 @@
 // chi(g) * norm(rep)/norm(s), norm(x)^2 = sum_g chi(g)[g x == x] / |G|.
 // Plus the canonicalisation kernel (stable per-row column sort + duplicate merge) that
 // turns generation-order rows into the canonical CSR of common.py:193-195.
+#include <algorithm>
+
 #include "operator.cuh"
 
 namespace asp {
@@ -239,6 +241,144 @@ __global__ void __launch_bounds__(kApplyThreads) apply_fill_positive_kernel(cons
   }
 }
 
+// Fill pass, one WARP per row: the lanes share the group (element e = lane + 32 k).  g(s ^ flip) = g(s) ^ g(flip) and
+// g(flip) is two bits looked up in the element's site table, so the Benes networks run ONCE per row (for g(s)) and a
+// candidate costs two byte loads, two shifts and two XORs per group element instead of eleven delta swaps; the orbit
+// minimum and the stabiliser count are warp reductions.  Same representatives, same coefficient arithmetic as
+// apply_fill_positive_kernel (bitwise equal outputs).
+constexpr int kOrbitK = 10;  // group elements per lane: up to 320 non-identity elements
+constexpr int kOrbitThreads = 256;
+
+__device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
+  const uint32_t hi = static_cast<uint32_t>(v >> 32), lo = static_cast<uint32_t>(v);
+  const uint32_t hi_min = __reduce_min_sync(0xffffffffu, hi);
+  const uint32_t lo_min = __reduce_min_sync(0xffffffffu, hi == hi_min ? lo : 0xFFFFFFFFu);
+  return (static_cast<uint64_t>(hi_min) << 32) | lo_min;
+}
+
+__global__ void __launch_bounds__(kOrbitThreads) apply_fill_orbit_kernel(const ApplyArgs a, const uint8_t *__restrict__ perm_dst, int number_spins) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Move *s_moves = reinterpret_cast<Move *>(smem_raw);
+  DiagBond *s_diag = reinterpret_cast<DiagBond *>(s_moves + a.n_moves);
+  BitPerm *s_perms = reinterpret_cast<BitPerm *>(s_diag + a.n_diag);
+  uint2 *s_image = reinterpret_cast<uint2 *>(s_perms + a.sym.num_perms);  // [bit][element]: g(1 << bit) as {low word, high word}
+  for (int k = threadIdx.x; k < a.n_moves; k += blockDim.x) s_moves[k] = a.moves[k];
+  for (int k = threadIdx.x; k < a.n_diag; k += blockDim.x) s_diag[k] = a.diag[k];
+  for (int k = threadIdx.x; k < a.sym.num_perms; k += blockDim.x) s_perms[k] = a.sym.perms[k];
+  // image of every single bit under every group element, laid out [bit][element]: the lanes of a warp (consecutive
+  // elements) read consecutive 8-byte words
+  const int stride = (a.sym.num_perms + 31) & ~31;
+  for (int k = threadIdx.x; k < number_spins * stride; k += blockDim.x) {
+    const int bit = k / stride, e = k % stride;
+    const uint64_t image = e < a.sym.num_perms ? 1ull << perm_dst[e * 64 + bit] : 0ull;
+    s_image[k] = make_uint2(static_cast<uint32_t>(image), static_cast<uint32_t>(image >> 32));
+  }
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31;
+  const int rounds = (a.sym.num_perms + 31) / 32;  // group elements per lane actually present (<= kOrbitK)
+  const uint64_t warps = static_cast<uint64_t>(gridDim.x) * (kOrbitThreads / 32);
+  const bool inversion = a.sym.spin_inversion != 0;
+  const uint64_t top = 1ull << (number_spins - 1);
+  // under spin inversion x and ~x are one state: the member of the pair without the top bit is the smaller one
+  auto fold = [&](uint64_t x) { return (inversion && (x & top)) ? ~x & a.sym.state_mask : x; };
+  for (uint64_t r = static_cast<uint64_t>(blockIdx.x) * (kOrbitThreads / 32) + (threadIdx.x >> 5); r < a.num_rows; r += warps) {
+    const uint64_t s = a.spins[r];
+    uint64_t gs[kOrbitK];
+#pragma unroll
+    for (int k = 0; k < kOrbitK; ++k) {
+      const int e = static_cast<int>(lane) + 32 * k;
+      gs[k] = 0;
+      if (k < rounds && e < a.sym.num_perms) {
+        const BitPerm &p = s_perms[e];
+        uint64_t x = s;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) x = delta_swap(x, p.mask[q], 32 >> q);
+#pragma unroll
+        for (int q = 6; q < 11; ++q) x = delta_swap(x, p.mask[q], 2 << (q - 6));
+        gs[k] = x;
+      }
+    }
+    // orbit of the candidate s ^ flip (flip = bits b0, b1; 255 = none): representative and stabiliser size.
+    // min(y, ~y) = fold(y), and [y == c] + [~y == c] = [fold(y) == fold(c)] (y and ~y differ in the top bit).
+    auto orbit = [&](uint64_t c, uint32_t b0, uint32_t b1, uint64_t &rep, uint32_t &stab) {
+      const uint64_t c_folded = fold(c);
+      uint64_t best = ~0ull;
+      uint32_t fixed = 0;
+      if (lane == 0) {  // the identity
+        best = c_folded;
+        fixed = 1;
+      }
+      const uint2 *const image0 = s_image + (b0 == 255u ? 0u : b0) * stride + lane, *const image1 = s_image + (b1 == 255u ? 0u : b1) * stride + lane;
+#pragma unroll
+      for (int k = 0; k < kOrbitK; ++k) {
+        if (k >= rounds) break;  // (uniform) no group elements beyond
+        const int e = static_cast<int>(lane) + 32 * k;
+        if (e < a.sym.num_perms) {
+          uint32_t lo = static_cast<uint32_t>(gs[k]), hi = static_cast<uint32_t>(gs[k] >> 32);
+          if (b0 != 255u) {
+            const uint2 f = image0[32 * k];
+            lo ^= f.x;
+            hi ^= f.y;
+          }
+          if (b1 != 255u) {
+            const uint2 f = image1[32 * k];
+            lo ^= f.x;
+            hi ^= f.y;
+          }
+          const uint64_t y = fold((static_cast<uint64_t>(hi) << 32) | lo);
+          fixed += y == c_folded;
+          best = min(best, y);
+        }
+      }
+      rep = warp_min_u64(best);
+      stab = __reduce_add_sync(0xffffffffu, fixed);
+    };
+    uint64_t rep_s;
+    uint32_t stab_s;
+    orbit(s, 255u, 255u, rep_s, stab_s);
+    const double norm_s = sqrt(fmax(static_cast<double>(stab_s), 0.0) / a.sym.group_order);
+    int64_t out = a.offsets[r];
+    auto emit = [&](uint64_t c, double coef, uint32_t b0, uint32_t b1) {
+      uint64_t rep;
+      uint32_t stab_c;
+      orbit(c, b0, b1, rep, stab_c);
+      if (lane == 0) {
+        const double norm_c = sqrt(fmax(static_cast<double>(stab_c), 0.0) / a.sym.group_order);
+        a.other_spins[out] = rep;
+        a.other_coeffs[out] = coef * ((1.0 * norm_c) / norm_s);
+      }
+      ++out;
+    };
+    auto flip_bits = [](uint64_t flip, uint32_t &b0, uint32_t &b1) {
+      b0 = static_cast<uint32_t>(__ffsll(static_cast<long long>(flip))) - 1u;
+      const uint64_t rest = flip & (flip - 1);
+      b1 = rest ? static_cast<uint32_t>(__ffsll(static_cast<long long>(rest))) - 1u : 255u;
+    };
+    for (int m = 0; m < a.n_down; ++m) {
+      const Move mv = s_moves[m];
+      if ((s & mv.mask) != mv.need) continue;  // the same row on every lane: a uniform branch
+      uint32_t b0, b1;
+      flip_bits(mv.flip, b0, b1);
+      emit(s ^ mv.flip, mv.coef, b0, b1);
+    }
+    {
+      double d = 0.0;
+      for (int k = 0; k < a.n_diag; ++k) {
+        const DiagBond db = s_diag[k];
+        d += db.d[((s >> db.i) & 1) * 2 + ((s >> db.j) & 1)];
+      }
+      emit(s, d, 255u, 255u);
+    }
+    for (int m = a.n_down; m < a.n_moves; ++m) {
+      const Move mv = s_moves[m];
+      if ((s & mv.mask) != mv.need) continue;
+      uint32_t b0, b1;
+      flip_bits(mv.flip, b0, b1);
+      emit(s ^ mv.flip, mv.coef, b0, b1);
+    }
+  }
+}
+
 // ---- canonicalisation: one warp per row, bitonic sort of (col, seq) keys in smem --------
 constexpr int kCanonThreads = 128;
 constexpr int kCanonMaxRow = 1024;
@@ -333,7 +473,7 @@ __global__ void __launch_bounds__(256) compact_rows_kernel(uint64_t num_rows, co
 
 using namespace asp;
 
-static int g_apply_mode = 0;  // test hook: 1 = always the general kernels
+static int g_apply_mode = 0;  // test hook: 1 = always the general kernels, 2 = the lane-per-row fast kernel instead of the warp-per-row one
 
 extern "C" {
 
@@ -399,7 +539,19 @@ int asp_operator_apply_dev(asp_operator const *op, uint64_t num_rows, uint64_t c
   a.offsets = d_offsets;
   a.other_spins = d_other_spins;
   a.other_coeffs = d_other_coeffs;
-  if (positive) {
+  // moves that flip one or two bits (every two-site term) and a group of at most 32 * kOrbitK elements: one warp per row
+  bool warp_per_row = positive && g_apply_mode != 2 && op->d_perm_dst != nullptr && op->perms.size() <= 32u * kOrbitK;
+  for (const Move &mv : op->moves) warp_per_row = warp_per_row && __builtin_popcountll(mv.flip) <= 2;
+  if (warp_per_row) {
+    const size_t osmem = smem + ((op->perms.size() + 31) / 32 * 32) * static_cast<size_t>(op->number_spins) * sizeof(uint2);
+    ASP_REQUIRE(osmem <= 200 * 1024, "operator too large for shared memory");
+    ASP_CUDA_CHECK(cudaFuncSetAttribute(apply_fill_orbit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(osmem)));
+    int per_sm = 0;
+    ASP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, apply_fill_orbit_kernel, kOrbitThreads, osmem));
+    const uint64_t want = (num_rows + kOrbitThreads / 32 - 1) / (kOrbitThreads / 32);
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(want, static_cast<uint64_t>(kNumSMs) * std::max(per_sm, 1)));
+    apply_fill_orbit_kernel<<<grid, kOrbitThreads, osmem, s>>>(a, op->d_perm_dst, static_cast<int>(op->number_spins));
+  } else if (positive) {
     ASP_CUDA_CHECK(cudaFuncSetAttribute(apply_fill_positive_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     apply_fill_positive_kernel<<<blocks, kApplyThreads, smem, s>>>(a);
   } else {

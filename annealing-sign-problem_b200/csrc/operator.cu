@@ -289,6 +289,11 @@ int asp_operator_create(asp_operator **out, uint32_t number_spins, int32_t hammi
     }
     op->perms.push_back(net);
     op->characters.push_back(characters ? characters[g] : 1.0);
+    // out bit k = in bit perm[k]: the element sends bit perm[k] to bit k (bits beyond number_spins stay)
+    const size_t base = op->perm_dst.size();
+    op->perm_dst.resize(base + 64);
+    for (uint32_t k = 0; k < 64; ++k) op->perm_dst[base + k] = static_cast<uint8_t>(k);
+    for (uint32_t k = 0; k < number_spins; ++k) op->perm_dst[base + perms[static_cast<size_t>(g) * number_spins + k]] = static_cast<uint8_t>(k);
   }
 
   if (asp_device_count() > 0) {
@@ -305,6 +310,7 @@ int asp_operator_create(asp_operator **out, uint32_t number_spins, int32_t hammi
     if (rc == ASP_OK) rc = upload(op->d_diag_groups, op->diag_groups);
     if (rc == ASP_OK) rc = upload(op->d_perms, op->perms);
     if (rc == ASP_OK) rc = upload(op->d_characters, op->characters);
+    if (rc == ASP_OK) rc = upload(op->d_perm_dst, op->perm_dst);
     if (rc != ASP_OK) {
       asp_operator_destroy(op);
       return rc;
@@ -321,6 +327,7 @@ void asp_operator_destroy(asp_operator *op) {
   if (op->d_diag_groups) cudaFree(op->d_diag_groups);
   if (op->d_perms) cudaFree(op->d_perms);
   if (op->d_characters) cudaFree(op->d_characters);
+  if (op->d_perm_dst) cudaFree(op->d_perm_dst);
   delete op;
 }
 

@@ -57,12 +57,14 @@ struct asp_operator {
   // symmetry group (non-identity permutations), real characters
   std::vector<asp::BitPerm> perms;
   std::vector<double> characters;
+  std::vector<uint8_t> perm_dst;  // [perms.size()][64]: group element g sends bit i to bit perm_dst[g * 64 + i]
   // device mirrors (device current at creation)
   asp::Move *d_moves = nullptr;
   asp::DiagBond *d_diag = nullptr;
   asp::DiagGroup *d_diag_groups = nullptr;
   asp::BitPerm *d_perms = nullptr;
   double *d_characters = nullptr;
+  uint8_t *d_perm_dst = nullptr;
   int device = -1;
 
   bool symmetrised() const { return spin_inversion != 0 || !perms.empty(); }

@@ -349,8 +349,8 @@ def test_batched_apply_device_matches_oracle_including_symmetry_groups():
 
 
 def test_symmetrised_apply_fast_kernels_equal_the_general_ones_bitwise():
-    """All characters +1: counts without visiting orbits + the converged orbit walk
-    (apply_fill_positive_kernel) against the general move-by-move kernels."""
+    """All characters +1: counts without visiting orbits + the warp-per-row orbit kernel (apply_fill_orbit_kernel)
+    against the lane-per-row walk (apply_fill_positive_kernel) and the general move-by-move kernels."""
     for system, m in [("heisenberg_kagome_36", 20000), ("heisenberg_pyrochlore_2x2x2", 5000), ("heisenberg_kagome_18", 24310)]:
         op = asp.load_hamiltonian(asp.ls.system_path(system))
         rows = op.basis.states if system == "heisenberg_kagome_18" else None
@@ -358,14 +358,15 @@ def test_symmetrised_apply_fast_kernels_equal_the_general_ones_bitwise():
             rows = synthetic.cluster_closed_states(op, m, 9, DEV)
         else:
             rows = torch.from_numpy(np.ascontiguousarray(rows).view(np.int64)).to(DEV)
-        fast = op.batched_apply_device(rows)
-        lib().asp_debug_set_apply_mode(1)
-        try:
-            general = op.batched_apply_device(rows)
-        finally:
-            lib().asp_debug_set_apply_mode(0)
-        for a, b in zip(fast, general):
-            assert torch.equal(a, b), system
+        fast = op.batched_apply_device(rows)  # warp per row: g(s ^ flip) = g(s) ^ g(flip), orbit minimum by warp reduction
+        for mode in (1, 2):  # 1 = general move-by-move kernels, 2 = lane per row (apply_fill_positive_kernel)
+            lib().asp_debug_set_apply_mode(mode)
+            try:
+                other = op.batched_apply_device(rows)
+            finally:
+                lib().asp_debug_set_apply_mode(0)
+            for a, b in zip(fast, other):
+                assert torch.equal(a, b), (system, mode)
 
 
 def test_symmetrised_kagome_36_extraction_vs_oracle():
