@@ -830,12 +830,14 @@ int fused_prepare_gather(const asp_operator *op, uint32_t world, uint32_t rank, 
 // X1 with the copy engines: per block (own block first, then ring order) [wait for its ready flag ->
 // cudaMemcpyAsync keys + amplitudes into the private full copy] on a copy stream; on the caller's stream
 // the block is indexed as soon as its copies are done, while the next blocks travel.
+constexpr int kCopyStreamsMax = 8;
 struct CopyLane {
-  cudaStream_t copy = nullptr, copy2 = nullptr;  // keys on one copy engine, amplitudes on another
-  cudaEvent_t start = nullptr, flag = nullptr, block[kGxMaxRanks] = {}, block2[kGxMaxRanks] = {};
+  cudaStream_t copy[kCopyStreamsMax] = {};  // one copy engine each; the blocks of a gather are dealt over them
+  cudaEvent_t start = nullptr, done[kCopyStreamsMax] = {}, block[kGxMaxRanks] = {};
   int device = -1;
 };
 static CopyLane g_lane;
+static int g_copy_streams = 4;  // copy streams a gather uses (asp_set_copy_streams): blocks in flight at a time
 
 int fused_prepare_gather_ce(const asp_operator *op, uint32_t world, uint32_t rank, const uint64_t *shard_begin,
                             const uint64_t *const *d_shard_spins, const double *const *d_shard_psi, const uint64_t *d_ready,
@@ -857,18 +859,16 @@ int fused_prepare_gather_ce(const asp_operator *op, uint32_t world, uint32_t ran
   ASP_CUDA_CHECK(cudaGetDevice(&dev));
   if (g_lane.device != dev) {
     ASP_REQUIRE(g_lane.device < 0, "one device per process");
-    ASP_CUDA_CHECK(cudaStreamCreateWithFlags(&g_lane.copy, cudaStreamNonBlocking));
-    ASP_CUDA_CHECK(cudaStreamCreateWithFlags(&g_lane.copy2, cudaStreamNonBlocking));
+    for (auto &c : g_lane.copy) ASP_CUDA_CHECK(cudaStreamCreateWithFlags(&c, cudaStreamNonBlocking));
     ASP_CUDA_CHECK(cudaEventCreateWithFlags(&g_lane.start, cudaEventDisableTiming));
-    ASP_CUDA_CHECK(cudaEventCreateWithFlags(&g_lane.flag, cudaEventDisableTiming));
+    for (auto &e : g_lane.done) ASP_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto &e : g_lane.block) ASP_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    for (auto &e : g_lane.block2) ASP_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     g_lane.device = dev;
   }
+  const int streams = std::max(1, std::min(g_copy_streams, kCopyStreamsMax));
   if (index) ASP_CUDA_CHECK(cudaMemsetAsync(static_cast<char *>(d_workspace) + w.zero_offset, 0, w.zero_bytes, s));
   ASP_CUDA_CHECK(cudaEventRecord(g_lane.start, s));  // the copies may overwrite the full copy only after the caller's earlier work
-  ASP_CUDA_CHECK(cudaStreamWaitEvent(g_lane.copy, g_lane.start, 0));
-  ASP_CUDA_CHECK(cudaStreamWaitEvent(g_lane.copy2, g_lane.start, 0));
+  for (int c = 0; c < streams; ++c) ASP_CUDA_CHECK(cudaStreamWaitEvent(g_lane.copy[c], g_lane.start, 0));
   SeamArgs seams{};
   for (uint32_t k = 0; k < world; ++k) {
     const uint32_t q = (rank + k) % world;  // own block first (no flag to wait for), then ring order
@@ -877,27 +877,29 @@ int fused_prepare_gather_ce(const asp_operator *op, uint32_t world, uint32_t ran
     seams.first[q] = len > 0 ? static_cast<uint32_t>(b0) : static_cast<uint32_t>(n_total);
     if (len == 0) continue;
     ASP_REQUIRE(d_shard_spins[q] && d_shard_psi[q], "NULL shard pointer");
+    // a block travels on ONE stream (keys, then amplitudes); the blocks are dealt over the streams, so several peers
+    // are pulled at a time, each by its own copy engine
+    cudaStream_t lane = g_lane.copy[k % streams];
     if (d_ready != nullptr && q != rank) {
-      wait_one_flag_kernel<<<1, 1, 0, g_lane.copy>>>(reinterpret_cast<const unsigned long long *>(d_ready) + q, epoch);
+      wait_one_flag_kernel<<<1, 1, 0, lane>>>(reinterpret_cast<const unsigned long long *>(d_ready) + q, epoch);
       ASP_LAUNCH_CHECK();
-      ASP_CUDA_CHECK(cudaEventRecord(g_lane.flag, g_lane.copy));  // the second engine starts on the same flag
-      ASP_CUDA_CHECK(cudaStreamWaitEvent(g_lane.copy2, g_lane.flag, 0));
     }
-    ASP_CUDA_CHECK(cudaMemcpyAsync(d_spins + b0, d_shard_spins[q], len * sizeof(uint64_t), cudaMemcpyDeviceToDevice, g_lane.copy));
-    ASP_CUDA_CHECK(cudaMemcpyAsync(d_psi + b0, d_shard_psi[q], len * sizeof(double), cudaMemcpyDeviceToDevice, g_lane.copy2));
-    if (!index) continue;
-    ASP_CUDA_CHECK(cudaEventRecord(g_lane.block[k], g_lane.copy));
-    ASP_CUDA_CHECK(cudaStreamWaitEvent(s, g_lane.block[k], 0));  // the keys of this block have landed: index them
-    index_block_kernel<<<static_cast<unsigned>((len + 511) / 512), 256, 0, s>>>(d_spins, static_cast<uint32_t>(n_total), static_cast<uint32_t>(b0),
-                                                                               static_cast<uint32_t>(b0 + len), op->state_mask, w.tshift,
-                                                                               w.num_buckets, w.starts, w.fshift, w.filter);
-    ASP_LAUNCH_CHECK();
+    ASP_CUDA_CHECK(cudaMemcpyAsync(d_spins + b0, d_shard_spins[q], len * sizeof(uint64_t), cudaMemcpyDeviceToDevice, lane));
+    if (index) {  // the keys of this block have landed: index them while its amplitudes and the other blocks travel
+      ASP_CUDA_CHECK(cudaEventRecord(g_lane.block[k], lane));
+      ASP_CUDA_CHECK(cudaStreamWaitEvent(s, g_lane.block[k], 0));
+      index_block_kernel<<<static_cast<unsigned>((len + 511) / 512), 256, 0, s>>>(d_spins, static_cast<uint32_t>(n_total), static_cast<uint32_t>(b0),
+                                                                                 static_cast<uint32_t>(b0 + len), op->state_mask, w.tshift,
+                                                                                 w.num_buckets, w.starts, w.fshift, w.filter);
+      ASP_LAUNCH_CHECK();
+    }
+    ASP_CUDA_CHECK(cudaMemcpyAsync(d_psi + b0, d_shard_psi[q], len * sizeof(double), cudaMemcpyDeviceToDevice, lane));
   }
   // everything (amplitudes included) has landed before the caller's stream goes on
-  ASP_CUDA_CHECK(cudaEventRecord(g_lane.block2[0], g_lane.copy));
-  ASP_CUDA_CHECK(cudaEventRecord(g_lane.block2[1], g_lane.copy2));
-  ASP_CUDA_CHECK(cudaStreamWaitEvent(s, g_lane.block2[0], 0));
-  ASP_CUDA_CHECK(cudaStreamWaitEvent(s, g_lane.block2[1], 0));
+  for (int c = 0; c < streams; ++c) {
+    ASP_CUDA_CHECK(cudaEventRecord(g_lane.done[c], g_lane.copy[c]));
+    ASP_CUDA_CHECK(cudaStreamWaitEvent(s, g_lane.done[c], 0));
+  }
   if (index) {
     index_seam_kernel<<<1, 32, 0, s>>>(d_spins, static_cast<uint32_t>(n_total), seams, static_cast<int>(world), op->state_mask, w.tshift,
                                        w.num_buckets, w.starts);
@@ -1107,6 +1109,8 @@ int asp_gather_blocks(uint32_t world, uint32_t rank, uint64_t const *shard_begin
 }
 
 void asp_set_gather_mode(int mode) { g_gather_mode = (mode == 0 || mode == 1) ? mode : 2; }
+
+void asp_set_copy_streams(int streams) { g_copy_streams = streams < 1 ? 1 : (streams > kCopyStreamsMax ? kCopyStreamsMax : streams); }
 
 int asp_extract_csr_indexed(asp_operator const *op, uint64_t n_total, uint64_t const *d_spins, double const *d_psi,
                             uint64_t row_begin, uint64_t num_rows, void *d_workspace, size_t workspace_bytes,

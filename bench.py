@@ -80,6 +80,7 @@ def parse_args():
                         "(asp_gather_index)")
     p.add_argument("--pipeline-slots", type=int, default=2, choices=[2, 3],
                    help="private copies of the basis in the pipelined exchange: the exchange runs up to slots - 1 steps ahead")
+    p.add_argument("--copy-streams", type=int, default=4, help="copy engines the pipelined exchange pulls with (blocks in flight at a time)")
     p.add_argument("--skip-anneal", action="store_true")
     p.add_argument("--skip-cpu", action="store_true")
     p.add_argument("--skip-e2e", action="store_true")
@@ -285,6 +286,7 @@ def run_ours(args):
     dev = torch.device("cuda", torch.cuda.current_device())
     peak, peak_src = hbm_peak()
     op, cfg = u1_operator(asp)
+    lib().asp_set_copy_streams(args.copy_streams)
 
     def measure_extraction(states_per_rank, with_e2e):
         """One full measurement of the extraction step on a basis of `states_per_rank` sampled states per rank:
