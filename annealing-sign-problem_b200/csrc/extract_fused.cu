@@ -837,7 +837,7 @@ struct CopyLane {
   int device = -1;
 };
 static CopyLane g_lane;
-static int g_copy_streams = 4;  // copy streams a gather uses (asp_set_copy_streams): blocks in flight at a time
+static int g_copy_streams = 2;  // copy streams a gather uses (asp_set_copy_streams): blocks in flight at a time (8 GPUs: 2 -> 3.05 ms per step, 4 -> 3.60, 7 -> 3.42)
 
 int fused_prepare_gather_ce(const asp_operator *op, uint32_t world, uint32_t rank, const uint64_t *shard_begin,
                             const uint64_t *const *d_shard_spins, const double *const *d_shard_psi, const uint64_t *d_ready,

@@ -80,7 +80,7 @@ def parse_args():
                         "(asp_gather_index)")
     p.add_argument("--pipeline-slots", type=int, default=2, choices=[2, 3],
                    help="private copies of the basis in the pipelined exchange: the exchange runs up to slots - 1 steps ahead")
-    p.add_argument("--copy-streams", type=int, default=4, help="copy engines the pipelined exchange pulls with (blocks in flight at a time)")
+    p.add_argument("--copy-streams", type=int, default=2, help="copy engines the pipelined exchange pulls with (blocks in flight at a time)")
     p.add_argument("--skip-anneal", action="store_true")
     p.add_argument("--skip-cpu", action="store_true")
     p.add_argument("--skip-e2e", action="store_true")
@@ -236,9 +236,43 @@ def cpu_live_path_once(inputs):
     return int(model.exchange.nnz), dt
 
 
+def cpu_extract_threaded(capi, inputs, impl, threads):
+    """The reference's C (re-entrant, no globals: cbits/build_matrix.c:22-53) on `threads` host threads: every thread gets
+    a contiguous block of rows -- its own candidate slice and counts that are zero outside the block -- and its own
+    output arrays, exactly what a caller with a thread pool around the reference's function would do (ctypes releases
+    the GIL for the call).  -> (couplings, seconds of the slowest-to-finish pool)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle.capi import pad512
+
+    spins, psi, other_spins, other_coeffs, other_counts, other_psi = inputs
+    n = spins.shape[0]
+    s512 = pad512(spins)
+    counts = np.ones(n, dtype=np.int64)
+    offsets = np.concatenate([[0], np.cumsum(other_counts)])
+    bounds = np.linspace(0, n, threads + 1).astype(np.int64)
+    jobs = []
+    for t in range(threads):
+        lo, hi = int(bounds[t]), int(bounds[t + 1])
+        block_counts = np.zeros(n, dtype=np.int64)
+        block_counts[lo:hi] = other_counts[lo:hi]
+        sl = slice(int(offsets[lo]), int(offsets[hi]))
+        jobs.append((pad512(other_spins[sl]), np.ascontiguousarray(other_coeffs[sl]), block_counts, np.ascontiguousarray(other_psi[sl])))
+
+    def work(job):
+        o512, coeffs, block_counts, o_psi = job
+        return capi.build_matrix(s512, counts, psi, o512, coeffs, block_counts, o_psi, impl=impl)[0].shape[0]
+
+    with ThreadPoolExecutor(max_workers=threads) as pool:
+        t0 = time.perf_counter()
+        nnz = sum(pool.map(work, jobs))
+        dt = time.perf_counter() - t0
+    return nnz, dt
+
+
 def run_reference(args):
-    """`--impl reference`: the reference's own CPU implementation of the path (cbits/build_matrix.c
-    compiled where it lies, oracle/_ref) on a bounded sample of the same workload."""
+    """`--impl reference`: the reference's own CPU implementation of the path (cbits/build_matrix.c compiled where it
+    lies, oracle/_ref) on a bounded sample of the same workload, on all host cores (one row block per thread)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -246,23 +280,27 @@ def run_reference(args):
 
     capi.build()
     impl = "ref" if capi.have_ref() else "port"
+    cores = max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     inputs = cpu_sample_inputs(args.cpu_sample)
     nnz, times = 0, []
     for step in range(args.warmup + args.steps):
-        nnz, dt = cpu_extract_once(capi, inputs, impl)
+        nnz, dt = cpu_extract_threaded(capi, inputs, impl, cores)
         if step >= args.warmup:
             times.append(dt)
     total = sum(times)
     value = nnz * args.steps / total
-    sample = "%d-state kagome_36-shaped cluster-closed subset, %d candidates, time of the C call only (neighbour lists precomputed)" % (
-        inputs[0].shape[0], inputs[2].shape[0])
+    nnz_1, dt_1 = cpu_extract_once(capi, inputs, impl)
+    sample = ("%d-state kagome_36-shaped cluster-closed subset, %d candidates; the reference's C function (serial, re-entrant) called on %d "
+              "threads, one contiguous row block each; time of the calls only (neighbour lists precomputed: the reference takes them from "
+              "lattice_symmetries, absent here)" % (inputs[0].shape[0], inputs[2].shape[0], cores))
     line = {
         "impl": "reference", "metric": "ising_couplings_built_per_sec", "value": value, "unit": "couplings/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "heisenberg_kagome_36-shaped U(1) basis, Ising extraction (bounded CPU sample)", "states": int(inputs[0].shape[0]),
                    "candidates": int(inputs[2].shape[0]), "couplings": int(nnz)},
-        "cpu_baseline": {"value": value, "unit": "couplings/s", "cores": 1, "kind": "reference" if impl == "ref" else "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "couplings/s", "cores": cores, "kind": "reference" if impl == "ref" else "port", "sample": sample,
+                         "one_thread": {"value": nnz_1 / dt_1, "unit": "couplings/s"}},
         "e2e": {"value": value, "unit": "couplings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "candidates_per_sec": inputs[2].shape[0] * args.steps / total,
     }
@@ -852,11 +890,15 @@ def run_ours(args):
         capi.build()
         impl = "ref" if capi.have_ref() else "port"
         inputs = cpu_sample_inputs(args.cpu_sample)
-        nnz_s, dt = cpu_extract_once(capi, inputs, impl)
+        host_cores = max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+        nnz_1, dt_1 = cpu_extract_once(capi, inputs, impl)
+        nnz_s, dt = cpu_extract_threaded(capi, inputs, impl, host_cores)
         flips_s, cores, reps = cpu_anneal_once(capi, inputs, 4)
-        cpu = {"value": nnz_s / dt, "unit": "couplings/s", "cores": 1, "kind": "reference" if impl == "ref" else "port",
-               "sample": "%d-state subset of the same shape, %d candidates; cbits/build_matrix.c call only (serial C, 512-bit keys), "
-                         "neighbour lists precomputed" % (inputs[0].shape[0], inputs[2].shape[0]),
+        cpu = {"value": nnz_s / dt, "unit": "couplings/s", "cores": host_cores, "kind": "reference" if impl == "ref" else "port",
+               "sample": "%d-state subset of the same shape, %d candidates; cbits/build_matrix.c (serial, re-entrant C, 512-bit keys) called on "
+                         "%d threads, one contiguous row block each; calls only, neighbour lists precomputed" % (
+                             inputs[0].shape[0], inputs[2].shape[0], host_cores),
+               "one_thread": {"value": nnz_1 / dt_1, "unit": "couplings/s"},
                "candidates_per_sec": inputs[2].shape[0] / dt,
                "anneal": {"value": flips_s, "unit": "proposals/s", "cores": cores, "kind": "port",
                           "sample": "oracle/anneal_port.c, %d replicas x 4 sweeps on the %d-spin sample model" % (reps, inputs[0].shape[0])}}

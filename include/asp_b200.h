@@ -355,8 +355,8 @@ int asp_extract_indexed_to_host_i32(asp_operator const *op, uint64_t n_total, ui
  * blocks (cudaMemcpyAsync on an internal stream) and every block is indexed on the SMs as soon as
  * it has landed. */
 void asp_set_gather_mode(int mode);
-/* Copy streams (= copy engines, 1..8, default 4) the copy-engine gather (mode 0, asp_gather_blocks) deals the row
- * blocks over: that many peers are pulled at a time. */
+/* Copy streams (= copy engines, 1..8, default 2) the copy-engine gather (mode 0, asp_gather_blocks) deals the row
+  * blocks over: that many peers are pulled at a time (default 2: measured best on 8 GPUs). */
 void asp_set_copy_streams(int streams);
 /* asp_extract_csr without its zero + index pass: the workspace was prepared by asp_gather_index
  * for the same (op, n_total, num_rows) on the same stream.  The index is SINGLE-USE (the extraction
