@@ -64,8 +64,6 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIBRARY
     cmd = ["nvcc"] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-o", LIBRARY]
-    if os.environ.get("ASP_FX_DEBUG"):  # device-side bounds checks in the extraction kernel (debug builds only)
-        cmd.insert(1, "-DASP_FX_DEBUG=1")
     cmd += [os.path.join(CSRC, f) for f in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
