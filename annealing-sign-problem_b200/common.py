@@ -249,6 +249,43 @@ def symmetrize_csr_device(n: int, indptr, indices, data) -> None:
                        "a non-Hermitian operator is outside the hot path".format(int(missing[0])))
 
 
+_STAGING = {}
+
+
+def _upload(array: np.ndarray, dev) -> torch.Tensor:
+    """Host array -> device through a cached pinned staging buffer: a pageable numpy array goes up at ~8 GB/s through the
+    driver's own bounce buffers; a memcpy into pinned memory (~20 GB/s on one core) plus a DMA at link speed is quicker for
+    the 240 MB a 10^7-state call uploads."""
+    src = torch.from_numpy(array)
+    if array.nbytes < (1 << 22):
+        return src.to(dev)
+    key = src.dtype
+    buf = _STAGING.get(key)
+    if buf is None or buf.numel() < src.numel():
+        buf = torch.empty(src.numel(), dtype=src.dtype, pin_memory=True)
+        _STAGING[key] = buf
+    view = buf[: src.numel()].view(src.shape)
+    view.copy_(src)
+    out = torch.empty(src.shape, dtype=src.dtype, device=dev)
+    out.copy_(view, non_blocking=True)
+    torch.cuda.current_stream().synchronize()  # the staging buffer is reused by the next upload
+    return out
+
+
+def _coo_from_valid_arrays(n: int, rows: np.ndarray, cols: np.ndarray, data: np.ndarray) -> scipy.sparse.coo_matrix:
+    """A real scipy COO matrix around arrays that are valid by construction (row-sorted, columns ascending inside a row,
+    no duplicates: the kernel's output).  The checked constructor would walk both index arrays four times for their
+    minima and maxima -- 36 ms on 4.5e7 entries, half of what make_ising_model takes."""
+    matrix = scipy.sparse.coo_matrix((n, n), dtype=np.float64)
+    matrix.data = data
+    try:
+        matrix.coords = (rows, cols)
+    except AttributeError:  # scipy < 1.13 keeps .row / .col
+        matrix.row, matrix.col = rows, cols
+    matrix.has_canonical_format = True
+    return matrix
+
+
 # ---------------------------------------------------------------------------------------
 # make_ising_model -- common.py:131-208
 # ---------------------------------------------------------------------------------------
@@ -271,7 +308,7 @@ def make_ising_model(
     dev = require_cuda()
 
     spins = _normalize_spins_1d(spins)
-    d_spins_in = torch.from_numpy(spins.view(np.int64)).to(dev)
+    d_spins_in = _upload(spins.view(np.int64), dev)
     d_spins, first, counts = _sort_unique_device(d_spins_in)
     if bool((counts != 1).any()):
         logger.warning("'spins' were not unique, are you sure this is what you want?")
@@ -279,7 +316,7 @@ def make_ising_model(
     h_sorted.copy_(d_spins, non_blocking=True)
     if log_psi is not None:
         # first occurrence, sorted order (common.py:149-151) -- gathered on the device
-        d_log_psi = torch.from_numpy(np.ascontiguousarray(log_psi, dtype=np.complex128)).to(dev)[first]
+        d_log_psi = _upload(np.ascontiguousarray(log_psi, dtype=np.complex128), dev)[first]
     torch.cuda.synchronize()
     spins = h_sorted.numpy().view(np.uint64)
     if log_psi is None:
@@ -336,7 +373,7 @@ def make_ising_model(
     h_data.copy_(data, non_blocking=True)
     del rows
     torch.cuda.synchronize()
-    matrix = scipy.sparse.coo_matrix((h_data.numpy(), (h_rows.numpy(), h_cols.numpy())), shape=(n, n), copy=False)
+    matrix = _coo_from_valid_arrays(n, h_rows.numpy(), h_cols.numpy(), h_data.numpy())
     field = np.zeros(n, dtype=np.float64)
     ising_hamiltonian = sa.Hamiltonian(matrix, field, _device_csr=(indptr, indices, data, None))
     x0 = sa.signs_to_bits_device(psi).cpu().numpy().view(np.uint64)
