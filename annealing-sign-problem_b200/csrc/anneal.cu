@@ -124,6 +124,20 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   return c;
 }
 
+// the same function with the ten round keys precomputed on the host (kernel arguments: constant-bank operands)
+struct PhiloxKeys {
+  uint32_t x[10], y[10];
+};
+__device__ __forceinline__ uint4 philox4x32_10_scheduled(uint4 c, const PhiloxKeys &k) {
+#pragma unroll
+  for (int round = 0; round < 10; ++round) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x[round], lo1, hi0 ^ c.w ^ k.y[round], lo0);
+  }
+  return c;
+}
+
 // exp(-x), 0 < x < 23, binary32, the operation sequence of oracle/anneal_port.c:exp_neg_f32
 // (explicit _rn intrinsics: nothing is contracted or reassociated).
 __device__ __forceinline__ float exp_neg_f32(float x) {
@@ -208,6 +222,9 @@ struct SaArgs {
   long long *rel;        // [groups*32] running fixed-point energy (zeroed by the host)
   long long *best_rel;   // [groups*32] out
   unsigned long long *barriers;  // [num_teams] zeroed by the host
+  const int4 *bounds;    // [n_padded / 4] row boundaries of each warp-task, relative to its first entry
+  uint32_t has_field;    // 0: every field is zero (the usual case for Ising models made from a wavefunction)
+  PhiloxKeys round_keys; // key schedule of `seed`
 };
 
 constexpr int kSaThreads = 256;
@@ -297,17 +314,48 @@ __device__ __forceinline__ void accumulate_rows(const TaskRows &rows, int64_t e_
   }
 }
 
+// Row boundaries of a warp-task relative to its first entry (b[0] = 0 is implied): one 16-byte word,
+// read by all lanes at once, replaces five 64-bit row pointers and their shuffles.
+__global__ void __launch_bounds__(256) task_bounds_kernel(uint64_t tasks, const int64_t *__restrict__ indptr, int4 *__restrict__ bounds) {
+  const uint64_t q = static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (q >= tasks) return;
+  const int64_t b0 = indptr[q * 4];
+  bounds[q] = make_int4(static_cast<int>(indptr[q * 4 + 1] - b0), static_cast<int>(indptr[q * 4 + 2] - b0), static_cast<int>(indptr[q * 4 + 3] - b0),
+                        static_cast<int>(indptr[q * 4 + 4] - b0));
+}
+
+__global__ void __launch_bounds__(256) any_field_kernel(uint64_t n_padded, const double *__restrict__ field, uint32_t *__restrict__ out) {
+  const uint64_t p = static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (p < n_padded && field[p] != 0.0) *out = 1u;
+}
+
+// sum of one staged row [lo, hi) for this lane's replica, stored order, two entries per trip
+__device__ __forceinline__ double staged_row_sum(const StagedEntry *stage, int32_t lo, int32_t hi, uint32_t up) {
+  double acc = 0.0;
+#pragma unroll 1
+  for (int32_t k = lo; k < hi; k += 2) {
+    // one 16-byte load per entry (x, y: value; z: spin word); stage has a 33rd slot
+    const uint4 x0 = reinterpret_cast<const uint4 *>(stage)[k], x1 = reinterpret_cast<const uint4 *>(stage)[k + 1];
+    acc = __dadd_rn(acc, __hiloint2double(static_cast<int>(x0.y ^ (~(x0.z << up) & 0x80000000u)), static_cast<int>(x0.x)));
+    if (k + 1 < hi) acc = __dadd_rn(acc, __hiloint2double(static_cast<int>(x1.y ^ (~(x1.z << up) & 0x80000000u)), static_cast<int>(x1.x)));
+  }
+  return acc;
+}
+
 __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm) sa_sweep_kernel(const SaArgs a) {
   __shared__ StagedEntry s_stage[kSaWarps][33];
-  const uint32_t lane = threadIdx.x & 31, warp_in_cta = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  // broadcast from lane 0: tells the compiler that the warp index -- and with it every task loop below -- is warp-uniform
+  const uint32_t warp_in_cta = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const uint32_t team = blockIdx.x / a.team_size;
   if (team >= a.num_teams) return;
   const uint32_t member = blockIdx.x % a.team_size;
   const uint32_t team_warps = a.team_size * kSaWarps;
   const uint32_t my_warp = member * kSaWarps + warp_in_cta;
+  const uint32_t up = 31u - lane, lane_bit = 1u << lane;
   TeamBarrier bar{a.barriers + team, 0ull, a.team_size};
   StagedEntry *stage = s_stage[warp_in_cta];
-  const uint2 key = make_uint2(static_cast<uint32_t>(a.seed), static_cast<uint32_t>(a.seed >> 32));
+  const bool has_field = a.has_field != 0;
 
   for (uint32_t g = team; g < a.groups; g += a.num_teams) {
     uint32_t *words = a.words + static_cast<uint64_t>(g) * a.n_padded;
@@ -319,88 +367,107 @@ __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm) sa_sweep_kernel(cons
       const double beta = a.betas[t];
       long long rel_delta = 0;
       for (uint32_t c = 0; c < a.num_classes; ++c) {
-        const uint64_t q_begin = static_cast<uint64_t>(a.class_ptr[c]) >> 2, q_end = static_cast<uint64_t>(a.class_ptr[c + 1]) >> 2;
-        uint64_t q = q_begin + my_warp;
-        // software pipeline over this warp's tasks of the class: row pointers two tasks ahead,
-        // first-chunk (value, column) one task ahead (the CSR is read-only, so prefetching is safe;
-        // spin words are only read after the class barrier)
-        int64_t ip0 = 0, ip1 = 0;
+        // positions < 2^31, so tasks (and tasks + 2 strides) fit 32 bits
+        const uint32_t q_begin = static_cast<uint32_t>(a.class_ptr[c] >> 2), q_end = static_cast<uint32_t>(a.class_ptr[c + 1] >> 2);
+        uint32_t q = q_begin + my_warp;
+        // software pipeline over this warp's tasks of the class: task words (first entry, row
+        // boundaries) two tasks ahead, first-chunk (value, column) one task ahead (the CSR is
+        // read-only, so prefetching is safe; spin words are only read after the class barrier).
+        // Every lane reads the same task word: one transaction, no shuffles.
+        int64_t eb0 = 0, eb1 = 0;
+        int4 bd0 = make_int4(0, 0, 0, 0), bd1 = bd0;
         double pv = 0.0;
         int32_t pi = 0;
-        if (q < q_end && lane < 5) ip0 = __ldg(&a.indptr[q * 4 + lane]);
-        if (q + team_warps < q_end && lane < 5) ip1 = __ldg(&a.indptr[(q + team_warps) * 4 + lane]);
         if (q < q_end) {
-          const int64_t eb = __shfl_sync(0xffffffffu, ip0, 0), ee = __shfl_sync(0xffffffffu, ip0, 4);
-          if (eb + lane < ee) {
-            pv = __ldg(&a.data[eb + lane]);
-            pi = __ldg(&a.indices[eb + lane]);
+          eb0 = __ldg(&a.indptr[static_cast<uint64_t>(q) * 4]);
+          bd0 = __ldg(&a.bounds[q]);
+          if (static_cast<int32_t>(lane) < bd0.w) {
+            pv = __ldg(&a.data[eb0 + lane]);
+            pi = __ldg(&a.indices[eb0 + lane]);
           }
         }
+        if (q + team_warps < q_end) {
+          eb1 = __ldg(&a.indptr[static_cast<uint64_t>(q + team_warps) * 4]);
+          bd1 = __ldg(&a.bounds[q + team_warps]);
+        }
         for (; q < q_end; q += team_warps) {
-          const uint64_t p0 = q * 4;
-          const int64_t e_begin = __shfl_sync(0xffffffffu, ip0, 0);
-          const int32_t rel_ip = static_cast<int32_t>(ip0 - e_begin);
-          TaskRows rows;
-          rows.b[0] = 0;
-#pragma unroll
-          for (int j = 1; j < 5; ++j) rows.b[j] = __shfl_sync(0xffffffffu, rel_ip, j);
+          const uint32_t p0 = q * 4;
+          const int4 rows = bd0;
+          const int64_t e_begin = eb0;
           // this task's spin words (after the barrier: always fresh from L2)
           uint32_t wv = 0u;
-          if (static_cast<int32_t>(lane) < rows.b[4]) wv = __ldcg(&words[pi]);
+          if (static_cast<int32_t>(lane) < rows.w) wv = __ldcg(&words[pi]);
           const uint4 cur = __ldcg(reinterpret_cast<const uint4 *>(words + p0));
-          const double my_field = lane < 4 ? __ldg(&a.field[p0 + lane]) : 0.0;
+          double field2 = 0.0;  // 2 h of position p0 + lane
+          if (has_field && lane < 4) field2 = __dmul_rn(2.0, __ldg(&a.field[p0 + lane]));
           const double cur_pv = pv;
           // prefetch for the following tasks
-          int64_t ip2 = 0;
-          if (q + 2ull * team_warps < q_end && lane < 5) ip2 = __ldg(&a.indptr[(q + 2ull * team_warps) * 4 + lane]);
+          int64_t eb2 = 0;
+          int4 bd2 = make_int4(0, 0, 0, 0);
+          if (q + 2u * team_warps < q_end) {
+            eb2 = __ldg(&a.indptr[static_cast<uint64_t>(q + 2u * team_warps) * 4]);
+            bd2 = __ldg(&a.bounds[q + 2u * team_warps]);
+          }
           pv = 0.0;
           pi = 0;
-          if (q + team_warps < q_end) {
-            const int64_t eb = __shfl_sync(0xffffffffu, ip1, 0), ee = __shfl_sync(0xffffffffu, ip1, 4);
-            if (eb + lane < ee) {
-              pv = __ldg(&a.data[eb + lane]);
-              pi = __ldg(&a.indices[eb + lane]);
-            }
+          if (static_cast<int32_t>(lane) < bd1.w) {  // bd1 is zero past the end of the class
+            pv = __ldg(&a.data[eb1 + lane]);
+            pi = __ldg(&a.indices[eb1 + lane]);
           }
-          ip0 = ip1;
-          ip1 = ip2;
+          eb0 = eb1;
+          bd0 = bd1;
+          eb1 = eb2;
+          bd1 = bd2;
 
           double acc[4];
-          accumulate_rows(rows, e_begin, cur_pv, wv, a.indices, a.data, words, stage, lane, acc);
+          if (rows.w <= 32) {  // the usual case: the four rows are one staged chunk
+            __syncwarp();
+            StagedEntry se;
+            se.val = cur_pv;
+            se.word = wv;
+            se.pad = 0;
+            stage[lane] = se;
+            __syncwarp();
+            acc[0] = staged_row_sum(stage, 0, rows.x, up);
+            acc[1] = staged_row_sum(stage, rows.x, rows.y, up);
+            acc[2] = staged_row_sum(stage, rows.y, rows.z, up);
+            acc[3] = staged_row_sum(stage, rows.z, rows.w, up);
+          } else {
+            TaskRows tr;
+            tr.b[0] = 0;
+            tr.b[1] = rows.x;
+            tr.b[2] = rows.y;
+            tr.b[3] = rows.z;
+            tr.b[4] = rows.w;
+            accumulate_rows(tr, e_begin, cur_pv, wv, a.indices, a.data, words, stage, lane, acc);
+          }
           const uint32_t cur_w[4] = {cur.x, cur.y, cur.z, cur.w};
-          double dE[4];
-          bool need_rng = false;
+          // dE = -s (4 sum + 2 h): 4 acc is exact, so one fma rounds like the oracle's mul, mul, add;
+          // uphill lanes (dE > 0, beta dE < 23) need a variate
+          double dE[4], x[4];
+          uint32_t uphill[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const double fj = __shfl_sync(0xffffffffu, my_field, j);
-            const double gsum = __dadd_rn(__dmul_rn(4.0, acc[j]), __dmul_rn(2.0, fj));
-            dE[j] = ((cur_w[j] >> lane) & 1) ? -gsum : gsum;
-            need_rng |= dE[j] > 0.0 && __dmul_rn(beta, dE[j]) < kRejectAbove;
+            const double f2 = has_field ? __shfl_sync(0xffffffffu, field2, j) : 0.0;
+            const double gsum = __fma_rn(4.0, acc[j], f2);
+            const uint32_t neg = (cur_w[j] << up) & 0x80000000u;  // spin up: dE = -gsum
+            dE[j] = __hiloint2double(__double2hiint(gsum) ^ static_cast<int>(neg), __double2loint(gsum));
+            x[j] = __dmul_rn(beta, dE[j]);
+            uphill[j] = __ballot_sync(0xffffffffu, dE[j] > 0.0 && x[j] < kRejectAbove);
           }
-          uint32_t rnd[4] = {0, 0, 0, 0};
-          if (__any_sync(0xffffffffu, need_rng)) {
-            const uint4 r4 = philox4x32_10(make_uint4(static_cast<uint32_t>(q), t, stream_id, static_cast<uint32_t>(p0 >> 34)), key);
-            rnd[0] = r4.x;
-            rnd[1] = r4.y;
-            rnd[2] = r4.z;
-            rnd[3] = r4.w;
-          }
+          uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
+          if (uphill[0] | uphill[1] | uphill[2] | uphill[3])
+            rnd = philox4x32_10_scheduled(make_uint4(q, t, stream_id, 0u), a.round_keys);
+          const uint32_t rnd_w[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
           uint32_t new_w[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            bool accept;
-            if (dE[j] <= 0.0) {
-              accept = true;
-            } else {
-              const double x = __dmul_rn(beta, dE[j]);
-              if (x >= kRejectAbove) {
-                accept = false;
-              } else {
-                accept = accept_uphill(x, rnd[j]);
-              }
-            }
-            if (accept) rel_delta += round_to_ll(__dmul_rn(dE[j], a.escale));
-            new_w[j] = cur_w[j] ^ __ballot_sync(0xffffffffu, accept);
+            uint32_t accepted = __ballot_sync(0xffffffffu, !(dE[j] > 0.0));
+            if (uphill[j])  // warp-uniform; the test is garbage but harmless on the lanes that are not uphill
+              accepted |= __ballot_sync(0xffffffffu, accept_uphill(x[j], rnd_w[j])) & uphill[j];
+            const long long inc = round_to_ll(__dmul_rn(dE[j], a.escale));
+            if (accepted & lane_bit) rel_delta += inc;
+            new_w[j] = cur_w[j] ^ accepted;
           }
           if (lane == 0) __stcg(reinterpret_cast<uint4 *>(words + p0), make_uint4(new_w[0], new_w[1], new_w[2], new_w[3]));
         }
@@ -577,7 +644,7 @@ void asp_sa_plan_destroy(asp_sa_plan *plan) {
   if (!plan) return;
   for (void *p : {static_cast<void *>(plan->d_order), static_cast<void *>(plan->d_position), static_cast<void *>(plan->d_indptr),
                   static_cast<void *>(plan->d_indices), static_cast<void *>(plan->d_data), static_cast<void *>(plan->d_field),
-                  static_cast<void *>(plan->d_class_ptr)})
+                  static_cast<void *>(plan->d_class_ptr), static_cast<void *>(plan->d_bounds)})
     if (p) cudaFree(p);
   delete plan;
 }
@@ -696,6 +763,19 @@ int asp_sa_plan_create(asp_sa_plan **out, uint64_t n, int64_t const *d_indptr, i
     ASP_LAUNCH_CHECK();
     ASP_CUDA_CHECK(cudaMemcpyAsync(&plan->max_de, d_part, sizeof(double), cudaMemcpyDeviceToHost, s));
     ASP_CUDA_CHECK(cudaStreamSynchronize(s));
+    // the sweep kernel's task words; whether any field is non-zero
+    uint32_t any_field = 0;
+    ASP_CUDA_CHECK(cudaMemsetAsync(d_part, 0, sizeof(double), s));
+    if (d_field) {
+      any_field_kernel<<<pblocks, 256, 0, s>>>(np, plan->d_field, reinterpret_cast<uint32_t *>(d_part));
+      ASP_LAUNCH_CHECK();
+    }
+    ASP_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&plan->d_bounds), (np / 4) * sizeof(int4)));
+    task_bounds_kernel<<<static_cast<unsigned>((np / 4 + 255) / 256), 256, 0, s>>>(np / 4, plan->d_indptr, plan->d_bounds);
+    ASP_LAUNCH_CHECK();
+    ASP_CUDA_CHECK(cudaMemcpyAsync(&any_field, d_part, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    ASP_CUDA_CHECK(cudaStreamSynchronize(s));
+    plan->has_field = any_field != 0;
     cudaFree(d_part);
   }
   ASP_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -756,6 +836,8 @@ int asp_sa_anneal(asp_sa_plan *plan, uint32_t num_replicas, uint32_t replica_off
   a.data = plan->d_data;
   a.field = plan->d_field;
   a.class_ptr = plan->d_class_ptr;
+  a.bounds = plan->d_bounds;
+  a.has_field = plan->has_field ? 1u : 0u;
   a.num_classes = plan->num_classes;
   a.groups = groups;
   if (groups >= max_ctas) {
@@ -775,6 +857,10 @@ int asp_sa_anneal(asp_sa_plan *plan, uint32_t num_replicas, uint32_t replica_off
   a.num_sweeps = num_sweeps;
   a.replica_offset = replica_offset;
   a.seed = seed;
+  for (int r = 0; r < 10; ++r) {
+    a.round_keys.x[r] = static_cast<uint32_t>(seed) + static_cast<uint32_t>(r) * 0x9E3779B9u;
+    a.round_keys.y[r] = static_cast<uint32_t>(seed >> 32) + static_cast<uint32_t>(r) * 0xBB67AE85u;
+  }
   a.escale = energy_scale;
 
   double *d_betas = nullptr;
