@@ -329,21 +329,28 @@ __global__ void __launch_bounds__(256) any_field_kernel(uint64_t n_padded, const
   if (p < n_padded && field[p] != 0.0) *out = 1u;
 }
 
-// sum of one staged row [lo, hi) for this lane's replica, stored order, two entries per trip
+// sum of one staged row [lo, hi) for this lane's replica, stored order, two entries per trip (one 16-byte shared
+// load per entry -- x, y: value; z: spin word of the column); pointers instead of indices: 12 instructions per trip
+__device__ __forceinline__ double staged_entry(const uint4 e, uint32_t up) {
+  return __hiloint2double(static_cast<int>(e.y ^ (~(e.z << up) & 0x80000000u)), static_cast<int>(e.x));
+}
+
 __device__ __forceinline__ double staged_row_sum(const StagedEntry *stage, int32_t lo, int32_t hi, uint32_t up) {
   double acc = 0.0;
+  const uint4 *p = reinterpret_cast<const uint4 *>(stage) + lo, *const last = reinterpret_cast<const uint4 *>(stage) + (hi - 1);
 #pragma unroll 1
-  for (int32_t k = lo; k < hi; k += 2) {
-    // one 16-byte load per entry (x, y: value; z: spin word); stage has a 33rd slot
-    const uint4 x0 = reinterpret_cast<const uint4 *>(stage)[k], x1 = reinterpret_cast<const uint4 *>(stage)[k + 1];
-    acc = __dadd_rn(acc, __hiloint2double(static_cast<int>(x0.y ^ (~(x0.z << up) & 0x80000000u)), static_cast<int>(x0.x)));
-    if (k + 1 < hi) acc = __dadd_rn(acc, __hiloint2double(static_cast<int>(x1.y ^ (~(x1.z << up) & 0x80000000u)), static_cast<int>(x1.x)));
+  for (; p <= last; p += 2) {
+    const uint4 x0 = p[0], x1 = p[1];  // the stage has a 33rd slot
+    acc = __dadd_rn(acc, staged_entry(x0, up));
+    if (p < last) acc = __dadd_rn(acc, staged_entry(x1, up));
   }
   return acc;
 }
 
+constexpr int kStageSlots = 33;  // 32 staged entries + one: the row loop reads two entries per trip
+
 __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm) sa_sweep_kernel(const SaArgs a) {
-  __shared__ StagedEntry s_stage[kSaWarps][33];
+  __shared__ StagedEntry s_stage[kSaWarps][kStageSlots];
   const uint32_t lane = threadIdx.x & 31;
   // broadcast from lane 0: tells the compiler that the warp index -- and with it every task loop below -- is warp-uniform
   const uint32_t warp_in_cta = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -367,57 +374,68 @@ __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm) sa_sweep_kernel(cons
       const double beta = a.betas[t];
       long long rel_delta = 0;
       for (uint32_t c = 0; c < a.num_classes; ++c) {
-        // positions < 2^31, so tasks (and tasks + 2 strides) fit 32 bits
+        // positions < 2^31, so tasks (and tasks + 3 strides) fit 32 bits
         const uint32_t q_begin = static_cast<uint32_t>(a.class_ptr[c] >> 2), q_end = static_cast<uint32_t>(a.class_ptr[c + 1] >> 2);
         uint32_t q = q_begin + my_warp;
-        // software pipeline over this warp's tasks of the class: task words (first entry, row
-        // boundaries) two tasks ahead, first-chunk (value, column) one task ahead (the CSR is
-        // read-only, so prefetching is safe; spin words are only read after the class barrier).
-        // Every lane reads the same task word: one transaction, no shuffles.
-        int64_t eb0 = 0, eb1 = 0;
-        int4 bd0 = make_int4(0, 0, 0, 0), bd1 = bd0;
-        double pv = 0.0;
-        int32_t pi = 0;
+        // software pipeline over this warp's tasks of the class, three stages deep: task words (first
+        // entry, row boundaries) three tasks ahead, first-chunk (value, column) two tasks ahead, the
+        // gathered spin words one task ahead.  The CSR is read-only, and the neighbours of a class
+        // lie in OTHER classes, whose words do not change before the next barrier -- so all of it is
+        // safe to prefetch once the class has begun.  Every lane reads the same task word: one
+        // transaction, no shuffles.
+        //   stage A: (ebA, bdA) of task q + 2T;  stage B: (pvB, piB, bdB) of q + T;  stage C: (pvC, wvC, bdC) of q
+        const int4 zero4 = make_int4(0, 0, 0, 0);
+        int64_t ebA = 0;
+        int4 bdA = zero4, bdB = zero4, bdC = zero4;
+        double pvB = 0.0, pvC = 0.0;
+        int32_t piB = 0;
+        uint32_t wvC = 0u;
         if (q < q_end) {
-          eb0 = __ldg(&a.indptr[static_cast<uint64_t>(q) * 4]);
-          bd0 = __ldg(&a.bounds[q]);
-          if (static_cast<int32_t>(lane) < bd0.w) {
-            pv = __ldg(&a.data[eb0 + lane]);
-            pi = __ldg(&a.indices[eb0 + lane]);
+          const int64_t eb = __ldg(&a.indptr[static_cast<uint64_t>(q) * 4]);
+          bdC = __ldg(&a.bounds[q]);
+          if (static_cast<int32_t>(lane) < bdC.w) {
+            pvC = __ldg(&a.data[eb + lane]);
+            wvC = __ldcg(&words[__ldg(&a.indices[eb + lane])]);
           }
         }
         if (q + team_warps < q_end) {
-          eb1 = __ldg(&a.indptr[static_cast<uint64_t>(q + team_warps) * 4]);
-          bd1 = __ldg(&a.bounds[q + team_warps]);
+          const int64_t eb = __ldg(&a.indptr[static_cast<uint64_t>(q + team_warps) * 4]);
+          bdB = __ldg(&a.bounds[q + team_warps]);
+          if (static_cast<int32_t>(lane) < bdB.w) {
+            pvB = __ldg(&a.data[eb + lane]);
+            piB = __ldg(&a.indices[eb + lane]);
+          }
+        }
+        if (q + 2u * team_warps < q_end) {
+          ebA = __ldg(&a.indptr[static_cast<uint64_t>(q + 2u * team_warps) * 4]);
+          bdA = __ldg(&a.bounds[q + 2u * team_warps]);
         }
         for (; q < q_end; q += team_warps) {
           const uint32_t p0 = q * 4;
-          const int4 rows = bd0;
-          const int64_t e_begin = eb0;
-          // this task's spin words (after the barrier: always fresh from L2)
-          uint32_t wv = 0u;
-          if (static_cast<int32_t>(lane) < rows.w) wv = __ldcg(&words[pi]);
+          const int4 rows = bdC;
+          const uint32_t wv = wvC;
+          const double cur_pv = pvC;
           const uint4 cur = __ldcg(reinterpret_cast<const uint4 *>(words + p0));
           double field2 = 0.0;  // 2 h of position p0 + lane
           if (has_field && lane < 4) field2 = __dmul_rn(2.0, __ldg(&a.field[p0 + lane]));
-          const double cur_pv = pv;
-          // prefetch for the following tasks
-          int64_t eb2 = 0;
-          int4 bd2 = make_int4(0, 0, 0, 0);
-          if (q + 2u * team_warps < q_end) {
-            eb2 = __ldg(&a.indptr[static_cast<uint64_t>(q + 2u * team_warps) * 4]);
-            bd2 = __ldg(&a.bounds[q + 2u * team_warps]);
+          // advance the pipeline (bounds are zero past the end of the class, which switches the loads off)
+          wvC = 0u;
+          if (static_cast<int32_t>(lane) < bdB.w) wvC = __ldcg(&words[piB]);
+          pvC = pvB;
+          bdC = bdB;
+          pvB = 0.0;
+          piB = 0;
+          if (static_cast<int32_t>(lane) < bdA.w) {
+            pvB = __ldg(&a.data[ebA + lane]);
+            piB = __ldg(&a.indices[ebA + lane]);
           }
-          pv = 0.0;
-          pi = 0;
-          if (static_cast<int32_t>(lane) < bd1.w) {  // bd1 is zero past the end of the class
-            pv = __ldg(&a.data[eb1 + lane]);
-            pi = __ldg(&a.indices[eb1 + lane]);
+          bdB = bdA;
+          ebA = 0;
+          bdA = zero4;
+          if (q + 3u * team_warps < q_end) {
+            ebA = __ldg(&a.indptr[static_cast<uint64_t>(q + 3u * team_warps) * 4]);
+            bdA = __ldg(&a.bounds[q + 3u * team_warps]);
           }
-          eb0 = eb1;
-          bd0 = bd1;
-          eb1 = eb2;
-          bd1 = bd2;
 
           double acc[4];
           if (rows.w <= 32) {  // the usual case: the four rows are one staged chunk
@@ -439,7 +457,7 @@ __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm) sa_sweep_kernel(cons
             tr.b[2] = rows.y;
             tr.b[3] = rows.z;
             tr.b[4] = rows.w;
-            accumulate_rows(tr, e_begin, cur_pv, wv, a.indices, a.data, words, stage, lane, acc);
+            accumulate_rows(tr, __ldg(&a.indptr[static_cast<uint64_t>(q) * 4]), cur_pv, wv, a.indices, a.data, words, stage, lane, acc);
           }
           const uint32_t cur_w[4] = {cur.x, cur.y, cur.z, cur.w};
           // dE = -s (4 sum + 2 h): 4 acc is exact, so one fma rounds like the oracle's mul, mul, add;
@@ -455,19 +473,23 @@ __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm) sa_sweep_kernel(cons
             x[j] = __dmul_rn(beta, dE[j]);
             uphill[j] = __ballot_sync(0xffffffffu, dE[j] > 0.0 && x[j] < kRejectAbove);
           }
-          uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
-          if (uphill[0] | uphill[1] | uphill[2] | uphill[3])
-            rnd = philox4x32_10_scheduled(make_uint4(q, t, stream_id, 0u), a.round_keys);
-          const uint32_t rnd_w[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+          // the variates and the four Metropolis tests in ONE warp-uniform block, so that the four
+          // exponentials interleave; the test is garbage but harmless on the lanes that are not uphill
+          uint32_t accepted[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) accepted[j] = __ballot_sync(0xffffffffu, !(dE[j] > 0.0));
+          if (uphill[0] | uphill[1] | uphill[2] | uphill[3]) {
+            const uint4 rnd = philox4x32_10_scheduled(make_uint4(q, t, stream_id, 0u), a.round_keys);
+            const uint32_t rnd_w[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) accepted[j] |= __ballot_sync(0xffffffffu, accept_uphill(x[j], rnd_w[j])) & uphill[j];
+          }
           uint32_t new_w[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            uint32_t accepted = __ballot_sync(0xffffffffu, !(dE[j] > 0.0));
-            if (uphill[j])  // warp-uniform; the test is garbage but harmless on the lanes that are not uphill
-              accepted |= __ballot_sync(0xffffffffu, accept_uphill(x[j], rnd_w[j])) & uphill[j];
             const long long inc = round_to_ll(__dmul_rn(dE[j], a.escale));
-            if (accepted & lane_bit) rel_delta += inc;
-            new_w[j] = cur_w[j] ^ accepted;
+            if (accepted[j] & lane_bit) rel_delta += inc;
+            new_w[j] = cur_w[j] ^ accepted[j];
           }
           if (lane == 0) __stcg(reinterpret_cast<uint4 *>(words + p0), make_uint4(new_w[0], new_w[1], new_w[2], new_w[3]));
         }
