@@ -223,8 +223,8 @@ struct SaArgs {
   long long *best_rel;   // [groups*32] out
   unsigned long long *barriers;  // [num_teams] zeroed by the host
   const int4 *bounds;    // [n_padded / 4] row boundaries of each warp-task, relative to its first entry
-  uint32_t has_field;    // 0: every field is zero (the usual case for Ising models made from a wavefunction)
   PhiloxKeys round_keys; // key schedule of `seed`
+  unsigned int *tickets; // [num_teams][num_classes] chunk tickets, zeroed by the host
 };
 
 constexpr int kSaThreads = 256;
@@ -232,6 +232,10 @@ constexpr int kSaWarps = kSaThreads / 32;
 #ifndef ASP_SA_CTAS_PER_SM
 #define ASP_SA_CTAS_PER_SM 3
 #endif
+#ifndef ASP_SA_CHUNK
+#define ASP_SA_CHUNK 8
+#endif
+constexpr uint32_t kSaChunk = ASP_SA_CHUNK;  // consecutive tasks per ticket
 constexpr int kSaCtasPerSm = ASP_SA_CTAS_PER_SM;  // 24 warps/SM: hides the indptr -> entries -> spin-word load chain
 
 struct TeamBarrier {
@@ -349,6 +353,7 @@ __device__ __forceinline__ double staged_row_sum(const StagedEntry *stage, int32
 
 constexpr int kStageSlots = 33;  // 32 staged entries + one: the row loop reads two entries per trip
 
+template <bool kField>  // kField = false: every field is zero, nothing of it is read
 __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm) sa_sweep_kernel(const SaArgs a) {
   __shared__ StagedEntry s_stage[kSaWarps][kStageSlots];
   const uint32_t lane = threadIdx.x & 31;
@@ -362,7 +367,6 @@ __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm) sa_sweep_kernel(cons
   const uint32_t up = 31u - lane, lane_bit = 1u << lane;
   TeamBarrier bar{a.barriers + team, 0ull, a.team_size};
   StagedEntry *stage = s_stage[warp_in_cta];
-  const bool has_field = a.has_field != 0;
 
   for (uint32_t g = team; g < a.groups; g += a.num_teams) {
     uint32_t *words = a.words + static_cast<uint64_t>(g) * a.n_padded;
@@ -376,65 +380,97 @@ __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm) sa_sweep_kernel(cons
       for (uint32_t c = 0; c < a.num_classes; ++c) {
         // positions < 2^31, so tasks (and tasks + 3 strides) fit 32 bits
         const uint32_t q_begin = static_cast<uint32_t>(a.class_ptr[c] >> 2), q_end = static_cast<uint32_t>(a.class_ptr[c + 1] >> 2);
-        uint32_t q = q_begin + my_warp;
+        // Tasks are handed out in chunks of kSaChunk consecutive tasks: the first chunk of a warp is its own
+        // index, later ones come from the team's ticket counter of the class (reset after the class barrier), so
+        // no warp waits at the barrier for a slower one with a fixed share.  Which warp runs a task does not
+        // matter: the tasks of a class are independent and the variates are keyed by (task, sweep, replica).
+        // The ticket for the NEXT chunk is drawn when a chunk begins (lane 0; read by shuffle when needed).
+        unsigned int *const ticket_counter = a.tickets + static_cast<uint64_t>(team) * a.num_classes + c;
+        uint32_t it_q = 0xFFFFFFFFu, it_end = 0xFFFFFFFFu, pending = 0u;
+        bool it_done = true;
+        {
+          const uint64_t start = static_cast<uint64_t>(q_begin) + static_cast<uint64_t>(my_warp) * kSaChunk;
+          if (start < q_end) {
+            it_done = false;
+            it_q = static_cast<uint32_t>(start);
+            it_end = static_cast<uint32_t>(min(start + kSaChunk, static_cast<uint64_t>(q_end)));
+            if (lane == 0) pending = atomicAdd(ticket_counter, 1u);
+          }
+        }
+        auto next_task = [&]() -> uint32_t {  // warp-uniform; 0xFFFFFFFF when the class is used up
+          if (it_q == it_end) {
+            if (it_done) return 0xFFFFFFFFu;
+            const uint32_t ticket = __shfl_sync(0xffffffffu, pending, 0);
+            const uint64_t start = static_cast<uint64_t>(q_begin) + (static_cast<uint64_t>(ticket) + team_warps) * kSaChunk;
+            if (start >= q_end) {
+              it_done = true;
+              it_q = it_end = 0xFFFFFFFFu;
+              return 0xFFFFFFFFu;
+            }
+            it_q = static_cast<uint32_t>(start);
+            it_end = static_cast<uint32_t>(min(start + kSaChunk, static_cast<uint64_t>(q_end)));
+            if (lane == 0) pending = atomicAdd(ticket_counter, 1u);
+          }
+          return it_q++;
+        };
         // software pipeline over this warp's tasks of the class, three stages deep: task words (first
         // entry, row boundaries) three tasks ahead, first-chunk (value, column) two tasks ahead, the
         // gathered spin words one task ahead.  The CSR is read-only, and the neighbours of a class
         // lie in OTHER classes, whose words do not change before the next barrier -- so all of it is
         // safe to prefetch once the class has begun.  Every lane reads the same task word: one
         // transaction, no shuffles.
-        //   stage A: (ebA, bdA) of task q + 2T;  stage B: (pvB, piB, bdB) of q + T;  stage C: (pvC, wvC, bdC) of q
-        const int4 zero4 = make_int4(0, 0, 0, 0);
+        //   stage A: (ebA, spanA) of task qA;  stage B: (pvB, piB) of qB;  stage C: (pvC, wvC) of q.
+        // Little state rides along (a column of -1 marks a lane past the span; the row boundaries are read
+        // again, from L1, when the task is summed), so rotating the pipeline is a handful of moves.
+        uint32_t q = next_task(), qB = next_task(), qA = next_task();
         int64_t ebA = 0;
-        int4 bdA = zero4, bdB = zero4, bdC = zero4;
+        int32_t spanA = 0;
         double pvB = 0.0, pvC = 0.0;
-        int32_t piB = 0;
+        int32_t piB = -1;
         uint32_t wvC = 0u;
-        if (q < q_end) {
+        if (q != 0xFFFFFFFFu) {
           const int64_t eb = __ldg(&a.indptr[static_cast<uint64_t>(q) * 4]);
-          bdC = __ldg(&a.bounds[q]);
-          if (static_cast<int32_t>(lane) < bdC.w) {
+          if (static_cast<int32_t>(lane) < __ldg(&a.bounds[q].w)) {
             pvC = __ldg(&a.data[eb + lane]);
             wvC = __ldcg(&words[__ldg(&a.indices[eb + lane])]);
           }
         }
-        if (q + team_warps < q_end) {
-          const int64_t eb = __ldg(&a.indptr[static_cast<uint64_t>(q + team_warps) * 4]);
-          bdB = __ldg(&a.bounds[q + team_warps]);
-          if (static_cast<int32_t>(lane) < bdB.w) {
+        if (qB != 0xFFFFFFFFu) {
+          const int64_t eb = __ldg(&a.indptr[static_cast<uint64_t>(qB) * 4]);
+          if (static_cast<int32_t>(lane) < __ldg(&a.bounds[qB].w)) {
             pvB = __ldg(&a.data[eb + lane]);
             piB = __ldg(&a.indices[eb + lane]);
           }
         }
-        if (q + 2u * team_warps < q_end) {
-          ebA = __ldg(&a.indptr[static_cast<uint64_t>(q + 2u * team_warps) * 4]);
-          bdA = __ldg(&a.bounds[q + 2u * team_warps]);
+        if (qA != 0xFFFFFFFFu) {
+          ebA = __ldg(&a.indptr[static_cast<uint64_t>(qA) * 4]);
+          spanA = __ldg(&a.bounds[qA].w);
         }
-        for (; q < q_end; q += team_warps) {
-          const uint32_t p0 = q * 4;
-          const int4 rows = bdC;
+        while (q != 0xFFFFFFFFu) {
+          const uint32_t p0 = q * 4, q_now = q;
+          const int4 rows = __ldg(&a.bounds[q]);
           const uint32_t wv = wvC;
           const double cur_pv = pvC;
           const uint4 cur = __ldcg(reinterpret_cast<const uint4 *>(words + p0));
           double field2 = 0.0;  // 2 h of position p0 + lane
-          if (has_field && lane < 4) field2 = __dmul_rn(2.0, __ldg(&a.field[p0 + lane]));
-          // advance the pipeline (bounds are zero past the end of the class, which switches the loads off)
+          if (kField && lane < 4) field2 = __dmul_rn(2.0, __ldg(&a.field[p0 + lane]));
+          // advance the pipeline
           wvC = 0u;
-          if (static_cast<int32_t>(lane) < bdB.w) wvC = __ldcg(&words[piB]);
+          if (piB >= 0) wvC = __ldcg(&words[piB]);
           pvC = pvB;
-          bdC = bdB;
           pvB = 0.0;
-          piB = 0;
-          if (static_cast<int32_t>(lane) < bdA.w) {
+          piB = -1;
+          if (static_cast<int32_t>(lane) < spanA) {
             pvB = __ldg(&a.data[ebA + lane]);
             piB = __ldg(&a.indices[ebA + lane]);
           }
-          bdB = bdA;
-          ebA = 0;
-          bdA = zero4;
-          if (q + 3u * team_warps < q_end) {
-            ebA = __ldg(&a.indptr[static_cast<uint64_t>(q + 3u * team_warps) * 4]);
-            bdA = __ldg(&a.bounds[q + 3u * team_warps]);
+          q = qB;
+          qB = qA;
+          qA = next_task();
+          spanA = 0;
+          if (qA != 0xFFFFFFFFu) {
+            ebA = __ldg(&a.indptr[static_cast<uint64_t>(qA) * 4]);
+            spanA = __ldg(&a.bounds[qA].w);
           }
 
           double acc[4];
@@ -457,7 +493,7 @@ __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm) sa_sweep_kernel(cons
             tr.b[2] = rows.y;
             tr.b[3] = rows.z;
             tr.b[4] = rows.w;
-            accumulate_rows(tr, __ldg(&a.indptr[static_cast<uint64_t>(q) * 4]), cur_pv, wv, a.indices, a.data, words, stage, lane, acc);
+            accumulate_rows(tr, __ldg(&a.indptr[static_cast<uint64_t>(q_now) * 4]), cur_pv, wv, a.indices, a.data, words, stage, lane, acc);
           }
           const uint32_t cur_w[4] = {cur.x, cur.y, cur.z, cur.w};
           // dE = -s (4 sum + 2 h): 4 acc is exact, so one fma rounds like the oracle's mul, mul, add;
@@ -466,7 +502,7 @@ __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm) sa_sweep_kernel(cons
           uint32_t uphill[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const double f2 = has_field ? __shfl_sync(0xffffffffu, field2, j) : 0.0;
+            const double f2 = kField ? __shfl_sync(0xffffffffu, field2, j) : 0.0;
             const double gsum = __fma_rn(4.0, acc[j], f2);
             const uint32_t neg = (cur_w[j] << up) & 0x80000000u;  // spin up: dE = -gsum
             dE[j] = __hiloint2double(__double2hiint(gsum) ^ static_cast<int>(neg), __double2loint(gsum));
@@ -479,7 +515,7 @@ __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm) sa_sweep_kernel(cons
 #pragma unroll
           for (int j = 0; j < 4; ++j) accepted[j] = __ballot_sync(0xffffffffu, !(dE[j] > 0.0));
           if (uphill[0] | uphill[1] | uphill[2] | uphill[3]) {
-            const uint4 rnd = philox4x32_10_scheduled(make_uint4(q, t, stream_id, 0u), a.round_keys);
+            const uint4 rnd = philox4x32_10_scheduled(make_uint4(q_now, t, stream_id, 0u), a.round_keys);
             const uint32_t rnd_w[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) accepted[j] |= __ballot_sync(0xffffffffu, accept_uphill(x[j], rnd_w[j])) & uphill[j];
@@ -494,6 +530,8 @@ __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm) sa_sweep_kernel(cons
           if (lane == 0) __stcg(reinterpret_cast<uint4 *>(words + p0), make_uint4(new_w[0], new_w[1], new_w[2], new_w[3]));
         }
         bar.sync();
+        // every warp of the team has drawn its last ticket of this class; the counter is next used one sweep (>= 1 barrier) later
+        if (member == 0 && threadIdx.x == 0) *ticket_counter = 0u;
       }
       // end of sweep: publish running energies, snapshot improved replicas
       if (rel_delta != 0) atomicAdd(reinterpret_cast<unsigned long long *>(&a.rel[replica]), static_cast<unsigned long long>(rel_delta));
@@ -847,7 +885,8 @@ int asp_sa_anneal(asp_sa_plan *plan, uint32_t num_replicas, uint32_t replica_off
   ASP_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   ASP_CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
   ASP_REQUIRE(coop != 0, "device does not support cooperative launches");
-  ASP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sa_sweep_kernel, kSaThreads, 0));
+  void *const sweep = plan->has_field ? reinterpret_cast<void *>(sa_sweep_kernel<true>) : reinterpret_cast<void *>(sa_sweep_kernel<false>);
+  ASP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<void (*)(SaArgs)>(sweep), kSaThreads, 0));
   ASP_REQUIRE(per_sm >= 1, "sweep kernel does not fit on an SM");
   const uint32_t max_ctas = static_cast<uint32_t>(sms * per_sm);
 
@@ -859,7 +898,6 @@ int asp_sa_anneal(asp_sa_plan *plan, uint32_t num_replicas, uint32_t replica_off
   a.field = plan->d_field;
   a.class_ptr = plan->d_class_ptr;
   a.bounds = plan->d_bounds;
-  a.has_field = plan->has_field ? 1u : 0u;
   a.num_classes = plan->num_classes;
   a.groups = groups;
   if (groups >= max_ctas) {
@@ -898,6 +936,9 @@ int asp_sa_anneal(asp_sa_plan *plan, uint32_t num_replicas, uint32_t replica_off
   ASP_CUDA_CHECK(cudaMemsetAsync(a.rel, 0, groups * 32 * sizeof(long long), s));
   ASP_CUDA_CHECK(cudaMemsetAsync(a.best_rel, 0, groups * 32 * sizeof(long long), s));
   ASP_CUDA_CHECK(cudaMemsetAsync(a.barriers, 0, a.num_teams * sizeof(unsigned long long), s));
+  const size_t ticket_bytes = static_cast<size_t>(a.num_teams) * plan->num_classes * sizeof(unsigned int);
+  ASP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&a.tickets), ticket_bytes, s));
+  ASP_CUDA_CHECK(cudaMemsetAsync(a.tickets, 0, ticket_bytes, s));
 
   {
     const uint64_t warps = (np / 4) * groups;
@@ -909,7 +950,7 @@ int asp_sa_anneal(asp_sa_plan *plan, uint32_t num_replicas, uint32_t replica_off
   if (num_sweeps > 0) {
     void *params[] = {&a};
     const unsigned grid = a.num_teams * a.team_size;
-    ASP_CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(sa_sweep_kernel), dim3(grid), dim3(kSaThreads), params, 0, s));
+    ASP_CUDA_CHECK(cudaLaunchCooperativeKernel(sweep, dim3(grid), dim3(kSaThreads), params, 0, s));
     g_launches.fetch_add(1, std::memory_order_relaxed);
   }
   {
@@ -937,6 +978,7 @@ int asp_sa_anneal(asp_sa_plan *plan, uint32_t num_replicas, uint32_t replica_off
   ASP_CUDA_CHECK(cudaFreeAsync(a.rel, s));
   ASP_CUDA_CHECK(cudaFreeAsync(a.best_rel, s));
   ASP_CUDA_CHECK(cudaFreeAsync(a.barriers, s));
+  ASP_CUDA_CHECK(cudaFreeAsync(a.tickets, s));
   return rc;
 }
 

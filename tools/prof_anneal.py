@@ -40,6 +40,9 @@ def main():
 
     ham = asp.sa.Hamiltonian(_Shape(), np.zeros(n), _device_csr=(indptr, indices, data, None))
     plan = asp.sa.AnnealPlan(ham)
+    if os.environ.get("ASP_PRINT_CLASSES"):
+        ex = plan.export()
+        print("class sizes:", np.diff(ex["class_ptr"]).tolist(), "row length histogram:", np.bincount(np.diff(ex["indptr"]))[:16].tolist(), flush=True)
     betas = np.ascontiguousarray(asp.sa.default_betas(ham, args.sweeps * 8)[3::8])
     escale = asp.sa.energy_scale(ham)
     for k in range(args.calls):
