@@ -380,36 +380,43 @@ __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm) sa_sweep_kernel(cons
       for (uint32_t c = 0; c < a.num_classes; ++c) {
         // positions < 2^31, so tasks (and tasks + 3 strides) fit 32 bits
         const uint32_t q_begin = static_cast<uint32_t>(a.class_ptr[c] >> 2), q_end = static_cast<uint32_t>(a.class_ptr[c + 1] >> 2);
-        // Tasks are handed out in chunks of kSaChunk consecutive tasks: the first chunk of a warp is its own
-        // index, later ones come from the team's ticket counter of the class (reset after the class barrier), so
-        // no warp waits at the barrier for a slower one with a fixed share.  Which warp runs a task does not
-        // matter: the tasks of a class are independent and the variates are keyed by (task, sweep, replica).
-        // The ticket for the NEXT chunk is drawn when a chunk begins (lane 0; read by shuffle when needed).
+        // Big classes hand their tasks out in chunks of kSaChunk consecutive tasks: the first chunk of a warp is
+        // its own index, later ones come from the team's ticket counter of the class (reset after the class
+        // barrier), so no warp waits at the barrier for a slower one with a fixed share.  Which warp runs a task
+        // does not matter: the tasks of a class are independent and the variates are keyed by (task, sweep,
+        // replica).  The ticket for the NEXT chunk is drawn when a chunk begins (lane 0; read by shuffle when
+        // needed).  Small classes (fewer than four chunks per warp) are dealt out task by task with a fixed
+        // stride instead -- every warp gets work, and no atomic sits on the path between two barriers.
         unsigned int *const ticket_counter = a.tickets + static_cast<uint64_t>(team) * a.num_classes + c;
-        uint32_t it_q = 0xFFFFFFFFu, it_end = 0xFFFFFFFFu, pending = 0u;
+        const bool dealt = (q_end - q_begin) < 4u * kSaChunk * team_warps;
+        const uint32_t chunk = dealt ? 1u : kSaChunk;
+        uint32_t it_q = 0xFFFFFFFFu, it_end = 0xFFFFFFFFu, pending = my_warp;
         bool it_done = true;
         {
-          const uint64_t start = static_cast<uint64_t>(q_begin) + static_cast<uint64_t>(my_warp) * kSaChunk;
+          const uint64_t start = static_cast<uint64_t>(q_begin) + static_cast<uint64_t>(my_warp) * chunk;
           if (start < q_end) {
             it_done = false;
             it_q = static_cast<uint32_t>(start);
-            it_end = static_cast<uint32_t>(min(start + kSaChunk, static_cast<uint64_t>(q_end)));
-            if (lane == 0) pending = atomicAdd(ticket_counter, 1u);
+            it_end = static_cast<uint32_t>(min(start + chunk, static_cast<uint64_t>(q_end)));
+            if (!dealt && lane == 0) pending = atomicAdd(ticket_counter, 1u);
           }
         }
         auto next_task = [&]() -> uint32_t {  // warp-uniform; 0xFFFFFFFF when the class is used up
           if (it_q == it_end) {
             if (it_done) return 0xFFFFFFFFu;
             const uint32_t ticket = __shfl_sync(0xffffffffu, pending, 0);
-            const uint64_t start = static_cast<uint64_t>(q_begin) + (static_cast<uint64_t>(ticket) + team_warps) * kSaChunk;
+            const uint64_t start = static_cast<uint64_t>(q_begin) + (static_cast<uint64_t>(ticket) + team_warps) * chunk;
             if (start >= q_end) {
               it_done = true;
               it_q = it_end = 0xFFFFFFFFu;
               return 0xFFFFFFFFu;
             }
             it_q = static_cast<uint32_t>(start);
-            it_end = static_cast<uint32_t>(min(start + kSaChunk, static_cast<uint64_t>(q_end)));
-            if (lane == 0) pending = atomicAdd(ticket_counter, 1u);
+            it_end = static_cast<uint32_t>(min(start + chunk, static_cast<uint64_t>(q_end)));
+            if (dealt)
+              pending += team_warps;
+            else if (lane == 0)
+              pending = atomicAdd(ticket_counter, 1u);
           }
           return it_q++;
         };
@@ -531,7 +538,7 @@ __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm) sa_sweep_kernel(cons
         }
         bar.sync();
         // every warp of the team has drawn its last ticket of this class; the counter is next used one sweep (>= 1 barrier) later
-        if (member == 0 && threadIdx.x == 0) *ticket_counter = 0u;
+        if (!dealt && member == 0 && threadIdx.x == 0) *ticket_counter = 0u;
       }
       // end of sweep: publish running energies, snapshot improved replicas
       if (rel_delta != 0) atomicAdd(reinterpret_cast<unsigned long long *>(&a.rel[replica]), static_cast<unsigned long long>(rel_delta));
