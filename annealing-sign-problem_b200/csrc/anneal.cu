@@ -427,17 +427,19 @@ __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm) sa_sweep_kernel(cons
         // safe to prefetch once the class has begun.  Every lane reads the same task word: one
         // transaction, no shuffles.
         //   stage A: (ebA, spanA) of task qA;  stage B: (pvB, piB) of qB;  stage C: (pvC, wvC) of q.
-        // Little state rides along (a column of -1 marks a lane past the span; the row boundaries are read
-        // again, from L1, when the task is summed), so rotating the pipeline is a handful of moves.
+        // Little state rides along (a column of -1 marks a lane past the span; the full row boundaries are read
+        // again one task ahead, when the sector is in L2), so rotating the pipeline is a handful of moves.
         uint32_t q = next_task(), qB = next_task(), qA = next_task();
         int64_t ebA = 0;
         int32_t spanA = 0;
         double pvB = 0.0, pvC = 0.0;
         int32_t piB = -1;
         uint32_t wvC = 0u;
+        int4 rowsC = make_int4(0, 0, 0, 0);
         if (q != 0xFFFFFFFFu) {
           const int64_t eb = __ldg(&a.indptr[static_cast<uint64_t>(q) * 4]);
-          if (static_cast<int32_t>(lane) < __ldg(&a.bounds[q].w)) {
+          rowsC = __ldg(&a.bounds[q]);
+          if (static_cast<int32_t>(lane) < rowsC.w) {
             pvC = __ldg(&a.data[eb + lane]);
             wvC = __ldcg(&words[__ldg(&a.indices[eb + lane])]);
           }
@@ -455,7 +457,8 @@ __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm) sa_sweep_kernel(cons
         }
         while (q != 0xFFFFFFFFu) {
           const uint32_t p0 = q * 4, q_now = q;
-          const int4 rows = __ldg(&a.bounds[q]);
+          const int4 rows = rowsC;
+          if (qB != 0xFFFFFFFFu) rowsC = __ldg(&a.bounds[qB]);
           const uint32_t wv = wvC;
           const double cur_pv = pvC;
           const uint4 cur = __ldcg(reinterpret_cast<const uint4 *>(words + p0));

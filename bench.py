@@ -709,9 +709,11 @@ def run_ours(args):
         flips = float(replicas) * world * sweeps * n_model * steps
         groups = (replicas + 31) // 32
         # what the kernel has to stream per sweep and group of 32 replicas (its rows are shared by the 32 replicas of a
-        # warp): the relabelled CSR (12 B per coupling, the diagonal is not stored), row starts and fields (16 B per spin),
-        # the 32-replica spin words read and written back (8 B per spin); neighbour words count as cache hits
-        required = groups * sweeps * (12.0 * plan.nnz + 24.0 * plan.n_padded) * steps
+        # warp): the relabelled CSR (12 B per coupling, the diagonal is not stored), per 4-position task one first-entry
+        # pointer and one row-boundary word (8 + 16 B = 6 B per spin), the 32-replica spin words read and written back
+        # (8 B per spin), the fields (8 B per spin) only when there are any; neighbour words count as cache hits
+        per_spin = 14.0 + (8.0 if np.any(ham.field) else 0.0)
+        required = groups * sweeps * (12.0 * plan.nnz + per_spin * plan.n_padded) * steps
         survey = replicas * sweeps * (12.0 * plan.nnz + 16.0 * n_model + 8.0) * steps  # one stream per replica
         traffic, traffic_note = measured_traffic(traffic_key) if (traffic_key and world == 1) else (None, "no ncu capture for this configuration")
         out = {
@@ -724,8 +726,8 @@ def run_ours(args):
                          "survey_formula": {"achieved": survey / (a_ms * 1e-3) / 1e9, "frac": survey / (a_ms * 1e-3) / 1e9 / peak,
                                             "note": "SURVEY.md 8d prices one CSR stream per REPLICA per sweep; the kernel reads a row once "
                                                     "per 32 replicas, so this figure can exceed 1 and is not a roofline fraction"},
-                         "note": "bytes = groups of 32 replicas x sweeps x (12 B per stored coupling + 24 B per spin): the stream the "
-                                 "row-sharing kernel cannot avoid; the kernel is bound by instruction issue (DESIGN.md 4.3)"},
+                         "note": "bytes = groups of 32 replicas x sweeps x (12 B per stored coupling + %d B per spin): the stream the "
+                                 "row-sharing kernel cannot avoid; the kernel is bound by instruction issue (DESIGN.md 4.3)" % per_spin},
             "gpu_launches": int(lib().asp_kernel_launch_count()) - launches_a0,
         }
         if e0 is not None:
