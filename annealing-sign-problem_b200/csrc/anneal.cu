@@ -356,7 +356,8 @@ constexpr int kStageSlots = 33;  // 32 staged entries + one: the row loop reads 
 template <bool kField>  // kField = false: every field is zero, nothing of it is read
 __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm) sa_sweep_kernel(const SaArgs a) {
   __shared__ StagedEntry s_stage[kSaWarps][kStageSlots];
-  const uint32_t lane = threadIdx.x & 31;
+  uint32_t lane = threadIdx.x & 31;
+  asm volatile("" : "+r"(lane));  // opaque: kept in a register instead of being re-read from the thread index in the task loop
   // broadcast from lane 0: tells the compiler that the warp index -- and with it every task loop below -- is warp-uniform
   const uint32_t warp_in_cta = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const uint32_t team = blockIdx.x / a.team_size;
@@ -370,6 +371,7 @@ __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm) sa_sweep_kernel(cons
 
   for (uint32_t g = team; g < a.groups; g += a.num_teams) {
     uint32_t *words = a.words + static_cast<uint64_t>(g) * a.n_padded;
+    asm volatile("" : "+l"(words));  // opaque: the group's base pointer is not re-derived for every load of the task loop
     uint32_t *best = a.best_words + static_cast<uint64_t>(g) * a.n_padded;
     const uint32_t replica = g * 32 + lane;                  // local slot
     const uint32_t stream_id = a.replica_offset + replica;   // global replica: RNG stream
