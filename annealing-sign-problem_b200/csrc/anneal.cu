@@ -710,7 +710,11 @@ __global__ void __launch_bounds__(256) sa_unpermute_kernel(uint64_t n, uint64_t 
 
 using namespace asp;
 
+static int g_sa_team_cap = 0;  // asp_debug_set_sa_team_ctas
+
 extern "C" {
+
+void asp_debug_set_sa_team_ctas(int max_ctas_per_team) { g_sa_team_cap = max_ctas_per_team > 0 ? max_ctas_per_team : 0; }
 
 void asp_sa_plan_destroy(asp_sa_plan *plan) {
   if (!plan) return;
@@ -925,6 +929,7 @@ int asp_sa_anneal(asp_sa_plan *plan, uint32_t num_replicas, uint32_t replica_off
     for (uint32_t c = 0; c < plan->num_classes; ++c) biggest = std::max(biggest, plan->class_ptr[c + 1] - plan->class_ptr[c]);
     const uint32_t useful = static_cast<uint32_t>((biggest / 4 + kSaWarps - 1) / kSaWarps);
     a.team_size = std::max(1u, std::min(a.team_size, useful));
+    if (g_sa_team_cap > 0) a.team_size = std::min(a.team_size, static_cast<uint32_t>(g_sa_team_cap));
   }
   a.num_sweeps = num_sweeps;
   a.replica_offset = replica_offset;

@@ -163,6 +163,7 @@ void asp_debug_set_extract_tuning(int filter_bits_delta, int table_bits_delta, i
  * CUDA events on its own stream; the second call returns the device time of the LAST such launch
  * (milliseconds; synchronises on it; -1 if none). */
 void asp_debug_set_apply_mode(int mode); /* asp_operator_apply_dev: 1 = always the general kernels, 2 = lane-per-row fill instead of warp-per-row */
+void asp_debug_set_sa_team_ctas(int max_ctas_per_team); /* asp_sa_anneal: cap the CTAs that share a replica group (0 = no cap); tests use it to reach the ticketed task hand-out on small models */
 void asp_debug_time_extract_kernel(int enable);
 float asp_debug_last_extract_kernel_ms(void);
 /* Same for the launch `back` launches before the last one (0 = last; the last 64 timed launches are kept). */

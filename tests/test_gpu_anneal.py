@@ -103,6 +103,32 @@ def test_sweep_kernel_is_bit_identical_to_the_oracle(oracle_capi, n, density, wi
         np.testing.assert_allclose(energies.cpu().numpy(), ref_e, rtol=0, atol=1e-10)
 
 
+def test_ticketed_task_hand_out_is_bit_identical_to_the_oracle(oracle_capi):
+    """Big classes hand their tasks out through a ticket counter (chunks of 8 tasks, whichever warp comes first); with the
+    team capped at one CTA a 6000-spin model has such classes.  Which warp runs a task must not matter."""
+    from annealing_sign_problem_b200._lib import lib
+
+    n, R, S = 6000, 40, 6
+    csr, h = random_model(n, 0.0006, seed=5, with_field=True)
+    ham = asp.sa.Hamiltonian(csr, h)
+    plan = asp.sa.AnnealPlan(ham)
+    ex, pos = check_plan(plan, csr, h)
+    assert np.diff(ex["class_ptr"]).max() // 4 >= 4 * 8 * 8  # tasks of the biggest class >= 4 chunks per warp of one CTA
+    betas = asp.sa.default_betas(ham, S)
+    escale = asp.sa.energy_scale(ham)
+    lib().asp_debug_set_sa_team_ctas(1)
+    try:
+        for seed in SEEDS[:3]:
+            bits, energies = plan.anneal_device(R, betas, seed, escale=escale)
+            ref_bits, _ = oracle_best(ex, pos, n, oracle_capi, R, betas, seed, escale)
+            assert np.array_equal(bits.cpu().numpy().view(np.uint64), ref_bits), "seed %d" % seed
+    finally:
+        lib().asp_debug_set_sa_team_ctas(0)
+    bits_free, _ = plan.anneal_device(R, betas, SEEDS[0], escale=escale)  # the uncapped launch deals the same tasks out by stride
+    ref_bits, _ = oracle_best(ex, pos, n, oracle_capi, R, betas, SEEDS[0], escale)
+    assert np.array_equal(bits_free.cpu().numpy().view(np.uint64), ref_bits)
+
+
 def test_x0_start_and_only_best_selection(oracle_capi):
     n = 500
     csr, h = random_model(n, 0.03, seed=9)
