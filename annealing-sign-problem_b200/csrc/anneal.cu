@@ -20,6 +20,9 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "plan.cuh"
@@ -77,6 +80,57 @@ __global__ void __launch_bounds__(256) colour_round_kernel(uint32_t n, const int
       return;
     }
   }
+}
+
+// ---- positions: stable sort of the spins by colour, on the device ------------------------
+// One stable split per bit of the colour (flags -> exclusive scan -> scatter), lowest bit first; then the spins of a
+// colour are a run of the permutation in ascending index order, exactly the oracle's counting sort.
+__global__ void __launch_bounds__(256) colour_max_kernel(uint32_t n, const int32_t *__restrict__ colour, unsigned int *__restrict__ out) {
+  const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+  unsigned int c = i < n ? static_cast<unsigned int>(colour[i]) : 0u;
+  c = __reduce_max_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0) atomicMax(out, c);
+}
+
+__global__ void __launch_bounds__(256) split_flag_kernel(uint32_t n, const int32_t *__restrict__ perm, const int32_t *__restrict__ colour, int bit,
+                                                         int64_t *__restrict__ flag) {
+  const uint32_t k = blockIdx.x * 256u + threadIdx.x;
+  if (k >= n) return;
+  const int32_t i = perm ? perm[k] : static_cast<int32_t>(k);
+  flag[k] = ((colour[i] >> bit) & 1) ? 0 : 1;
+}
+
+__global__ void __launch_bounds__(256) split_scatter_kernel(uint32_t n, const int32_t *__restrict__ perm, const int32_t *__restrict__ colour, int bit,
+                                                            const int64_t *__restrict__ zeros_before, int32_t *__restrict__ perm_out) {
+  const uint32_t k = blockIdx.x * 256u + threadIdx.x;
+  if (k >= n) return;
+  const int32_t i = perm ? perm[k] : static_cast<int32_t>(k);
+  const int64_t z = zeros_before[k], total_zeros = zeros_before[n];
+  const int64_t dst = ((colour[i] >> bit) & 1) ? total_zeros + (static_cast<int64_t>(k) - z) : z;
+  perm_out[dst] = i;
+}
+
+// start[c] = first slot of colour c in the sorted permutation (every colour 0..max is used: a spin takes the
+// smallest colour its neighbours leave free); start[classes] = n
+__global__ void __launch_bounds__(256) class_start_kernel(uint32_t n, uint32_t classes, const int32_t *__restrict__ perm, const int32_t *__restrict__ colour,
+                                                          int64_t *__restrict__ start) {
+  const uint32_t k = blockIdx.x * 256u + threadIdx.x;
+  if (k >= n) return;
+  const int32_t c = colour[perm ? perm[k] : static_cast<int32_t>(k)];
+  if (k == 0 || colour[perm ? perm[k - 1] : static_cast<int32_t>(k - 1)] != c) start[c] = k;
+  if (k == n - 1) start[classes] = n;
+}
+
+__global__ void __launch_bounds__(256) place_kernel(uint32_t n, const int32_t *__restrict__ perm, const int32_t *__restrict__ colour,
+                                                    const int64_t *__restrict__ start, const int64_t *__restrict__ class_ptr, int32_t *__restrict__ order,
+                                                    int32_t *__restrict__ position) {
+  const uint32_t k = blockIdx.x * 256u + threadIdx.x;
+  if (k >= n) return;
+  const int32_t i = perm ? perm[k] : static_cast<int32_t>(k);
+  const int32_t c = colour[i];
+  const int64_t p = class_ptr[c] + (static_cast<int64_t>(k) - start[c]);
+  order[p] = i;
+  position[i] = static_cast<int32_t>(p);
 }
 
 // ---- relabelled CSR -----------------------------------------------------------------
@@ -633,11 +687,16 @@ __global__ void __launch_bounds__(256) energy_sliced_final_kernel(const double *
 __global__ void __launch_bounds__(256) max_de_kernel(uint64_t n_padded, const int64_t *__restrict__ indptr, const double *__restrict__ data,
                                                      const double *__restrict__ field, unsigned long long *__restrict__ out) {
   const uint64_t p = static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x;
-  if (p >= n_padded) return;
-  double sum = 0.0;
-  for (int64_t k = indptr[p]; k < indptr[p + 1]; ++k) sum += fabs(data[k]);
-  const double bound = 4.0 * sum + 2.0 * fabs(field[p]);
-  atomicMax(out, static_cast<unsigned long long>(__double_as_longlong(bound)));
+  double bound = 0.0;
+  if (p < n_padded) {
+    double sum = 0.0;
+    for (int64_t k = indptr[p]; k < indptr[p + 1]; ++k) sum += fabs(data[k]);
+    bound = 4.0 * sum + 2.0 * fabs(field[p]);
+  }
+  unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(bound));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) bits = max(bits, __shfl_xor_sync(0xffffffffu, bits, o));  // one atomic per warp
+  if ((threadIdx.x & 31) == 0) atomicMax(out, bits);
 }
 
 // sum of the diagonal of the ORIGINAL model (dropped from the relabelled CSR): block partials
@@ -718,6 +777,7 @@ void asp_debug_set_sa_team_ctas(int max_ctas_per_team) { g_sa_team_cap = max_cta
 
 void asp_sa_plan_destroy(asp_sa_plan *plan) {
   if (!plan) return;
+  // the buffers come from the stream-ordered pool; cudaFree waits for the device and hands them back to it
   for (void *p : {static_cast<void *>(plan->d_order), static_cast<void *>(plan->d_position), static_cast<void *>(plan->d_indptr),
                   static_cast<void *>(plan->d_indices), static_cast<void *>(plan->d_data), static_cast<void *>(plan->d_field),
                   static_cast<void *>(plan->d_class_ptr), static_cast<void *>(plan->d_bounds)})
@@ -745,12 +805,24 @@ int asp_sa_plan_create(asp_sa_plan **out, uint64_t n, int64_t const *d_indptr, i
     }
   } guard{plan};
 
-  // 1. colour the coupling graph on the device
+  const bool timing = getenv("ASP_PLAN_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!timing) return;
+    cudaStreamSynchronize(s);
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "plan: %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
+  // Temporaries come from the stream-ordered pool (asp::keep_pool_memory keeps it warm): cudaMalloc / cudaFree of
+  // buffers this size cost tens to hundreds of milliseconds each.
+  // 1. colour the coupling graph on the device; the count of uncoloured spins is read back every fourth round
+  //    (a round after the last one changes nothing)
   int32_t *d_colour[2] = {nullptr, nullptr};
   unsigned long long *d_remaining = nullptr;
-  ASP_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&d_colour[0]), n * sizeof(int32_t)));
-  ASP_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&d_colour[1]), n * sizeof(int32_t)));
-  ASP_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&d_remaining), sizeof(unsigned long long)));
+  ASP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_colour[0]), n * sizeof(int32_t), s));
+  ASP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_colour[1]), n * sizeof(int32_t), s));
+  ASP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_remaining), sizeof(unsigned long long), s));
   ASP_CUDA_CHECK(cudaMemsetAsync(d_colour[0], 0xFF, n * sizeof(int32_t), s));
   const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
   int cur = 0;
@@ -759,56 +831,78 @@ int asp_sa_plan_create(asp_sa_plan **out, uint64_t n, int64_t const *d_indptr, i
     colour_round_kernel<<<blocks, 256, 0, s>>>(static_cast<uint32_t>(n), d_indptr, d_indices, d_colour[cur], d_colour[cur ^ 1], d_remaining);
     ASP_LAUNCH_CHECK();
     cur ^= 1;
+    if (round % 4 != 3) continue;
     unsigned long long remaining = 0;
     ASP_CUDA_CHECK(cudaMemcpyAsync(&remaining, d_remaining, sizeof(remaining), cudaMemcpyDeviceToHost, s));
     ASP_CUDA_CHECK(cudaStreamSynchronize(s));
     if (remaining == 0) break;
     if (round > 100000) {
-      cudaFree(d_colour[0]);
-      cudaFree(d_colour[1]);
-      cudaFree(d_remaining);
       set_error("colouring did not converge");
       return ASP_ERR_CUDA;
     }
   }
-  // 2. stable counting sort by colour on the host (O(n) bookkeeping): positions
-  std::vector<int32_t> colour(n);
-  ASP_CUDA_CHECK(cudaMemcpy(colour.data(), d_colour[cur], n * sizeof(int32_t), cudaMemcpyDeviceToHost));
-  cudaFree(d_colour[0]);
-  cudaFree(d_colour[1]);
-  cudaFree(d_remaining);
-  int32_t max_colour = 0;
-  for (int32_t c : colour) max_colour = std::max(max_colour, c);
-  const uint32_t classes = static_cast<uint32_t>(max_colour) + 1;
-  std::vector<int64_t> size(classes, 0);
-  for (int32_t c : colour) ++size[c];
+  const int32_t *d_col = d_colour[cur];
+  lap("colouring");
+  // 2. stable sort of the spins by colour on the device -> positions (classes padded to multiples of 4)
+  unsigned int max_colour = 0;
+  {
+    unsigned int *d_max = reinterpret_cast<unsigned int *>(d_remaining);
+    ASP_CUDA_CHECK(cudaMemsetAsync(d_max, 0, sizeof(unsigned int), s));
+    colour_max_kernel<<<blocks, 256, 0, s>>>(static_cast<uint32_t>(n), d_col, d_max);
+    ASP_LAUNCH_CHECK();
+    ASP_CUDA_CHECK(cudaMemcpyAsync(&max_colour, d_max, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+    ASP_CUDA_CHECK(cudaStreamSynchronize(s));
+  }
+  const uint32_t classes = max_colour + 1;
+  int32_t *d_perm[2] = {nullptr, nullptr};
+  int64_t *d_flag = nullptr, *d_zeros = nullptr, *d_start = nullptr;
+  void *d_scan = nullptr;
+  ASP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_perm[0]), n * sizeof(int32_t), s));
+  ASP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_perm[1]), n * sizeof(int32_t), s));
+  ASP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_flag), n * sizeof(int64_t), s));
+  ASP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_zeros), (n + 1) * sizeof(int64_t), s));
+  ASP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_start), (classes + 1) * sizeof(int64_t), s));
+  ASP_CUDA_CHECK(cudaMallocAsync(&d_scan, scan_tmp_bytes(n), s));
+  const int32_t *perm = nullptr;  // identity
+  int side = 0;
+  for (int bit = 0; (max_colour >> bit) != 0; ++bit) {
+    split_flag_kernel<<<blocks, 256, 0, s>>>(static_cast<uint32_t>(n), perm, d_col, bit, d_flag);
+    ASP_LAUNCH_CHECK();
+    int rc_scan = scan_exclusive_i64(d_flag, d_zeros, n, d_scan, s);
+    if (rc_scan != ASP_OK) return rc_scan;
+    split_scatter_kernel<<<blocks, 256, 0, s>>>(static_cast<uint32_t>(n), perm, d_col, bit, d_zeros, d_perm[side]);
+    ASP_LAUNCH_CHECK();
+    perm = d_perm[side];
+    side ^= 1;
+  }
+  class_start_kernel<<<blocks, 256, 0, s>>>(static_cast<uint32_t>(n), classes, perm, d_col, d_start);
+  ASP_LAUNCH_CHECK();
+  std::vector<int64_t> start(classes + 1);
+  ASP_CUDA_CHECK(cudaMemcpyAsync(start.data(), d_start, (classes + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  ASP_CUDA_CHECK(cudaStreamSynchronize(s));
   plan->class_ptr.assign(classes + 1, 0);
-  for (uint32_t c = 0; c < classes; ++c) plan->class_ptr[c + 1] = plan->class_ptr[c] + (size[c] + 3) / 4 * 4;
+  for (uint32_t c = 0; c < classes; ++c) plan->class_ptr[c + 1] = plan->class_ptr[c] + (start[c + 1] - start[c] + 3) / 4 * 4;
   plan->num_classes = classes;
   plan->n_padded = static_cast<uint64_t>(plan->class_ptr[classes]);
-  std::vector<int32_t> order(plan->n_padded, -1), position(n);
-  {
-    std::vector<int64_t> cursor(plan->class_ptr.begin(), plan->class_ptr.end() - 1);
-    for (uint64_t i = 0; i < n; ++i) {
-      const int64_t p = cursor[colour[i]]++;
-      order[p] = static_cast<int32_t>(i);
-      position[i] = static_cast<int32_t>(p);
-    }
-  }
   const uint64_t np = plan->n_padded;
-  ASP_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&plan->d_order), np * sizeof(int32_t)));
-  ASP_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&plan->d_position), n * sizeof(int32_t)));
-  ASP_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&plan->d_class_ptr), (classes + 1) * sizeof(int64_t)));
-  ASP_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&plan->d_indptr), (np + 1) * sizeof(int64_t)));
-  ASP_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&plan->d_field), np * sizeof(double)));
-  ASP_CUDA_CHECK(cudaMemcpyAsync(plan->d_order, order.data(), np * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-  ASP_CUDA_CHECK(cudaMemcpyAsync(plan->d_position, position.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  ASP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&plan->d_order), np * sizeof(int32_t), s));
+  ASP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&plan->d_position), n * sizeof(int32_t), s));
+  ASP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&plan->d_class_ptr), (classes + 1) * sizeof(int64_t), s));
+  ASP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&plan->d_indptr), (np + 1) * sizeof(int64_t), s));
+  ASP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&plan->d_field), np * sizeof(double), s));
   ASP_CUDA_CHECK(cudaMemcpyAsync(plan->d_class_ptr, plan->class_ptr.data(), (classes + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  ASP_CUDA_CHECK(cudaMemsetAsync(plan->d_order, 0xFF, np * sizeof(int32_t), s));
+  place_kernel<<<blocks, 256, 0, s>>>(static_cast<uint32_t>(n), perm, d_col, d_start, plan->d_class_ptr, plan->d_order, plan->d_position);
+  ASP_LAUNCH_CHECK();
+  for (void *p : {static_cast<void *>(d_colour[0]), static_cast<void *>(d_colour[1]), static_cast<void *>(d_remaining), static_cast<void *>(d_perm[0]),
+                  static_cast<void *>(d_perm[1]), static_cast<void *>(d_flag), static_cast<void *>(d_zeros), static_cast<void *>(d_start), d_scan})
+    ASP_CUDA_CHECK(cudaFreeAsync(p, s));
+  lap("positions");
   // 3. relabelled CSR without the diagonal (the diagonal never enters dE)
   int64_t *d_len = nullptr;
   void *d_tmp = nullptr;
-  ASP_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&d_len), np * sizeof(int64_t)));
-  ASP_CUDA_CHECK(cudaMalloc(&d_tmp, scan_tmp_bytes(np)));
+  ASP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_len), np * sizeof(int64_t), s));
+  ASP_CUDA_CHECK(cudaMallocAsync(&d_tmp, scan_tmp_bytes(np), s));
   const unsigned pblocks = static_cast<unsigned>((np + 255) / 256);
   relabel_count_kernel<<<pblocks, 256, 0, s>>>(np, plan->d_order, d_indptr, d_indices, d_len);
   ASP_LAUNCH_CHECK();
@@ -817,18 +911,19 @@ int asp_sa_plan_create(asp_sa_plan **out, uint64_t n, int64_t const *d_indptr, i
   int64_t nnz = 0;
   ASP_CUDA_CHECK(cudaMemcpyAsync(&nnz, plan->d_indptr + np, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
   ASP_CUDA_CHECK(cudaStreamSynchronize(s));
-  cudaFree(d_len);
-  cudaFree(d_tmp);
+  ASP_CUDA_CHECK(cudaFreeAsync(d_len, s));
+  ASP_CUDA_CHECK(cudaFreeAsync(d_tmp, s));
   plan->nnz = static_cast<uint64_t>(nnz);
-  ASP_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&plan->d_indices), std::max<int64_t>(nnz, 1) * sizeof(int32_t)));
-  ASP_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&plan->d_data), std::max<int64_t>(nnz, 1) * sizeof(double)));
+  ASP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&plan->d_indices), std::max<int64_t>(nnz, 1) * sizeof(int32_t), s));
+  ASP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&plan->d_data), std::max<int64_t>(nnz, 1) * sizeof(double), s));
   relabel_fill_kernel<<<pblocks, 256, 0, s>>>(np, plan->d_order, plan->d_position, d_indptr, d_indices, d_data, d_field,
                                               plan->d_indptr, plan->d_indices, plan->d_data, plan->d_field);
   ASP_LAUNCH_CHECK();
+  lap("relabelled CSR");
   {  // constant part of the energy: the diagonal, summed in a fixed order
     const unsigned dblocks = static_cast<unsigned>((n + 255) / 256);
     double *d_part = nullptr;
-    ASP_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&d_part), (dblocks + 1) * sizeof(double)));
+    ASP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&d_part), (dblocks + 1) * sizeof(double), s));
     diag_partial_kernel<<<dblocks, 256, 0, s>>>(n, d_indptr, d_indices, d_data, d_part);
     ASP_LAUNCH_CHECK();
     diag_final_kernel<<<1, 256, 0, s>>>(d_part, dblocks, d_part + dblocks);
@@ -846,15 +941,16 @@ int asp_sa_plan_create(asp_sa_plan **out, uint64_t n, int64_t const *d_indptr, i
       any_field_kernel<<<pblocks, 256, 0, s>>>(np, plan->d_field, reinterpret_cast<uint32_t *>(d_part));
       ASP_LAUNCH_CHECK();
     }
-    ASP_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&plan->d_bounds), (np / 4) * sizeof(int4)));
+    ASP_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&plan->d_bounds), (np / 4) * sizeof(int4), s));
     task_bounds_kernel<<<static_cast<unsigned>((np / 4 + 255) / 256), 256, 0, s>>>(np / 4, plan->d_indptr, plan->d_bounds);
     ASP_LAUNCH_CHECK();
     ASP_CUDA_CHECK(cudaMemcpyAsync(&any_field, d_part, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     ASP_CUDA_CHECK(cudaStreamSynchronize(s));
     plan->has_field = any_field != 0;
-    cudaFree(d_part);
+    ASP_CUDA_CHECK(cudaFreeAsync(d_part, s));
   }
   ASP_CUDA_CHECK(cudaStreamSynchronize(s));
+  lap("diagonal, bounds, task words");
   guard.p = nullptr;
   *out = plan;
   return ASP_OK;
