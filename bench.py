@@ -216,6 +216,18 @@ def cpu_anneal_once(capi, inputs, sweeps):
     return reps * sweeps * n / dt, cores, reps
 
 
+def cpu_greedy_once(capi, inputs):
+    """Oracle greedy solver (our restatement of the rules the reference preserves at common.py:298-438) on the sample model."""
+    spins, psi, other_spins, other_coeffs, other_counts, other_psi = inputs
+    counts = np.ones(spins.shape[0], dtype=np.int64)
+    rows, cols, vals, _ = capi.build_matrix(spins, counts, psi, other_spins, other_coeffs, other_counts, other_psi, impl="port64")
+    n = spins.shape[0]
+    indptr, indices, data = capi.canonical_csr(n, rows, cols, vals)
+    t0 = time.perf_counter()
+    capi.greedy(indptr, indices, data, None)
+    return n, time.perf_counter() - t0
+
+
 def cpu_live_path_once(inputs):
     """The reference's LIVE extraction path (common.py:131-208: batched_apply -> searchsorted -> couplings -> scipy
     0.5 (M + M^T) -> COO) in the oracle's numpy/scipy restatement, neighbour generation included -- the second CPU
@@ -760,6 +772,26 @@ def run_ours(args):
         anneal = measure_anneal(ham, args.replicas, strided_betas(ham, args.sweeps), args.steps, args.warmup,
                                 traffic_key="sa_sweep_kernel" if (args.states == 10_000_000 and args.replicas == 64 and args.sweeps == 16) else None)
         anneal["config"]["schedule"] = "%d sweeps: every 8th rung of the %d-sweep default ladder (hot to frozen)" % (args.sweeps, 8 * args.sweeps)
+        if world == 1:
+            # what the reference's 32- and 36-spin runs call instead of the annealer (common.py:249-250): the greedy solver
+            # on the same model (asp_greedy_solve: plan + maximum spanning forest + descent; SURVEY 8f N1, parity unpinned)
+            t0 = time.perf_counter()
+            g_plan = asp.sa.AnnealPlan(ham)
+            torch.cuda.synchronize()
+            g_plan_ms = 1e3 * (time.perf_counter() - t0)
+            g_plan.greedy_device()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(3):
+                g_bits, g_energy, g_rounds, g_sweeps = g_plan.greedy_device()
+            g1.record()
+            torch.cuda.synchronize()
+            g_ms = g0.elapsed_time(g1) / 3
+            anneal["greedy"] = {"metric": "greedy_spins_per_sec", "value": n_model / (g_ms * 1e-3), "unit": "spins/s", "ms_per_solve": g_ms,
+                                "plan_ms": g_plan_ms, "merge_rounds": g_rounds, "descent_sweeps": g_sweeps, "energy": float(g_energy),
+                                "energy_of_the_anneal": anneal["config"]["best_energy"],
+                                "api": "asp_greedy_solve on the plan of the same model (configuration and energy on the device)"}
+            del g_plan, g_bits
         del ham
     del indptr, indices, data
 
@@ -904,6 +936,12 @@ def run_ours(args):
                "candidates_per_sec": inputs[2].shape[0] / dt,
                "anneal": {"value": flips_s, "unit": "proposals/s", "cores": cores, "kind": "port",
                           "sample": "oracle/anneal_port.c, %d replicas x 4 sweeps on the %d-spin sample model" % (reps, inputs[0].shape[0])}}
+        try:  # the greedy solver's CPU restatement on the same sample model
+            g_n, g_dt = cpu_greedy_once(capi, inputs)
+            cpu["greedy"] = {"value": g_n / g_dt, "unit": "spins/s", "cores": 1, "kind": "port",
+                             "sample": "oracle/greedy_port.c (Kruskal with a signed union-find + descent) on the %d-spin sample model" % g_n}
+        except Exception as exc:  # noqa: BLE001
+            cpu["greedy"] = {"unavailable": repr(exc)[:200]}
         try:  # an extra figure: it must never cost the headline
             nnz_l, dt_l = cpu_live_path_once(inputs)
             cpu["live_path"] = {"value": nnz_l / dt_l, "unit": "couplings/s", "cores": 1, "kind": "port",
