@@ -256,23 +256,36 @@ __device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
   return (static_cast<uint64_t>(hi_min) << 32) | lo_min;
 }
 
-__global__ void __launch_bounds__(kOrbitThreads) apply_fill_orbit_kernel(const ApplyArgs a, const uint8_t *__restrict__ perm_dst, int number_spins) {
+__global__ void __launch_bounds__(kOrbitThreads, 3) apply_fill_orbit_kernel(const ApplyArgs a, const uint8_t *__restrict__ perm_dst, int number_spins) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Move *s_moves = reinterpret_cast<Move *>(smem_raw);
   DiagBond *s_diag = reinterpret_cast<DiagBond *>(s_moves + a.n_moves);
   BitPerm *s_perms = reinterpret_cast<BitPerm *>(s_diag + a.n_diag);
   uint2 *s_image = reinterpret_cast<uint2 *>(s_perms + a.sym.num_perms);  // [bit][element]: g(1 << bit) as {low word, high word}
+  const int stride = (a.sym.num_perms + 31) & ~31;
+  const int order = static_cast<int>(a.sym.group_order);
+  // sqrt(stabiliser / |G|) for every possible stabiliser size, and the two flipped bits of every move: a candidate then
+  // costs one table read instead of a double-precision square root and two find-first-set chains on all 32 lanes
+  double *s_norm = reinterpret_cast<double *>(s_image + static_cast<size_t>(number_spins + 1) * stride);  // [order + 1]
+  uchar2 *s_bits = reinterpret_cast<uchar2 *>(s_norm + order + 1);                                    // [n_moves]
+  for (int k = threadIdx.x; k <= order; k += blockDim.x) s_norm[k] = sqrt(fmax(static_cast<double>(k), 0.0) / a.sym.group_order);
+  for (int k = threadIdx.x; k < a.n_moves; k += blockDim.x) {
+    const uint64_t flip = a.moves[k].flip, rest = flip & (flip - 1);
+    s_bits[k] = make_uchar2(static_cast<unsigned char>(__ffsll(static_cast<long long>(flip)) - 1),
+                            rest ? static_cast<unsigned char>(__ffsll(static_cast<long long>(rest)) - 1) : static_cast<unsigned char>(255));
+  }
   for (int k = threadIdx.x; k < a.n_moves; k += blockDim.x) s_moves[k] = a.moves[k];
   for (int k = threadIdx.x; k < a.n_diag; k += blockDim.x) s_diag[k] = a.diag[k];
   for (int k = threadIdx.x; k < a.sym.num_perms; k += blockDim.x) s_perms[k] = a.sym.perms[k];
   // image of every single bit under every group element, laid out [bit][element]: the lanes of a warp (consecutive
   // elements) read consecutive 8-byte words
-  const int stride = (a.sym.num_perms + 31) & ~31;
-  for (int k = threadIdx.x; k < number_spins * stride; k += blockDim.x) {
+  for (int k = threadIdx.x; k < (number_spins + 1) * stride; k += blockDim.x) {  // row number_spins: all zero ("no bit")
     const int bit = k / stride, e = k % stride;
-    const uint64_t image = e < a.sym.num_perms ? 1ull << perm_dst[e * 64 + bit] : 0ull;
+    const uint64_t image = (bit < number_spins && e < a.sym.num_perms) ? 1ull << perm_dst[e * 64 + bit] : 0ull;
     s_image[k] = make_uint2(static_cast<uint32_t>(image), static_cast<uint32_t>(image >> 32));
   }
+  const uint32_t zero_row = static_cast<uint32_t>(number_spins);
+  const bool full_rounds = (a.sym.num_perms & 31) == 0;
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31;
   const int rounds = (a.sym.num_perms + 31) / 32;  // group elements per lane actually present (<= kOrbitK)
@@ -300,66 +313,75 @@ __global__ void __launch_bounds__(kOrbitThreads) apply_fill_orbit_kernel(const A
     }
     // orbit of the candidate s ^ flip (flip = bits b0, b1; 255 = none): representative and stabiliser size.
     // min(y, ~y) = fold(y), and [y == c] + [~y == c] = [fold(y) == fold(c)] (y and ~y differ in the top bit).
+    // A state (< 2^52) is carried as the bit pattern of the double 2^52 + y: minimum and equality are then ONE
+    // instruction each (DMNMX, DSETP) instead of two-word integer compare-and-select chains, and positive doubles order
+    // like their bit patterns, so the warp minimum can stay on the integer halves.
+    const uint32_t top_shift = 31u - ((number_spins - 1) & 31);
+    const bool top_in_hi = number_spins > 32;
+    const uint32_t mask_lo = static_cast<uint32_t>(a.sym.state_mask), mask_hi = static_cast<uint32_t>(a.sym.state_mask >> 32);
+    const uint32_t inv_all = inversion ? 0xFFFFFFFFu : 0u;
+    constexpr uint32_t kBiasHi = 0x43300000u;  // high word of 2^52
     auto orbit = [&](uint64_t c, uint32_t b0, uint32_t b1, uint64_t &rep, uint32_t &stab) {
       const uint64_t c_folded = fold(c);
-      uint64_t best = ~0ull;
+      const double c_d = __hiloint2double(static_cast<int>(static_cast<uint32_t>(c_folded >> 32) | kBiasHi), static_cast<int>(static_cast<uint32_t>(c_folded)));
+      double best = __hiloint2double(0x43400000, 0);  // 2^53: above every state
       uint32_t fixed = 0;
       if (lane == 0) {  // the identity
-        best = c_folded;
+        best = c_d;
         fixed = 1;
       }
-      const uint2 *const image0 = s_image + (b0 == 255u ? 0u : b0) * stride + lane, *const image1 = s_image + (b1 == 255u ? 0u : b1) * stride + lane;
+      const uint2 *const image0 = s_image + (b0 == 255u ? zero_row : b0) * stride + lane, *const image1 = s_image + (b1 == 255u ? zero_row : b1) * stride + lane;
+      auto element = [&](int k) {
+        const uint2 f0 = image0[32 * k], f1 = image1[32 * k];
+        uint32_t lo = static_cast<uint32_t>(gs[k]) ^ f0.x ^ f1.x, hi = static_cast<uint32_t>(gs[k] >> 32) ^ f0.y ^ f1.y;
+        // fold: under inversion a state with the top bit set is replaced by its complement
+        const uint32_t m = static_cast<uint32_t>(static_cast<int32_t>((top_in_hi ? hi : lo) << top_shift) >> 31) & inv_all;
+        lo ^= m & mask_lo;
+        hi ^= m & mask_hi;
+        const double y = __hiloint2double(static_cast<int>(hi | kBiasHi), static_cast<int>(lo));
+        fixed += y == c_d;
+        best = y < best ? y : best;  // (no NaNs here: a plain compare-and-select, fmin would add its NaN fix-up)
+      };
+      if (full_rounds) {  // every lane has an element in every round (|G| - 1 a multiple of 32, or padded below): no lane tests
 #pragma unroll
-      for (int k = 0; k < kOrbitK; ++k) {
-        if (k >= rounds) break;  // (uniform) no group elements beyond
-        const int e = static_cast<int>(lane) + 32 * k;
-        if (e < a.sym.num_perms) {
-          uint32_t lo = static_cast<uint32_t>(gs[k]), hi = static_cast<uint32_t>(gs[k] >> 32);
-          if (b0 != 255u) {
-            const uint2 f = image0[32 * k];
-            lo ^= f.x;
-            hi ^= f.y;
-          }
-          if (b1 != 255u) {
-            const uint2 f = image1[32 * k];
-            lo ^= f.x;
-            hi ^= f.y;
-          }
-          const uint64_t y = fold((static_cast<uint64_t>(hi) << 32) | lo);
-          fixed += y == c_folded;
-          best = min(best, y);
+        for (int k = 0; k < kOrbitK; ++k) {
+          if (k >= rounds) break;  // (uniform) no group elements beyond
+          element(k);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < kOrbitK; ++k) {
+          if (k >= rounds) break;
+          if (static_cast<int>(lane) + 32 * k < a.sym.num_perms) element(k);
         }
       }
-      rep = warp_min_u64(best);
+      const uint32_t bhi = static_cast<uint32_t>(__double2hiint(best)), blo = static_cast<uint32_t>(__double2loint(best));
+      const uint32_t hi_min = __reduce_min_sync(0xffffffffu, bhi);
+      const uint32_t lo_min = __reduce_min_sync(0xffffffffu, bhi == hi_min ? blo : 0xFFFFFFFFu);
+      rep = (static_cast<uint64_t>(hi_min & ~kBiasHi & 0x000FFFFFu) << 32) | lo_min;
       stab = __reduce_add_sync(0xffffffffu, fixed);
     };
     uint64_t rep_s;
     uint32_t stab_s;
     orbit(s, 255u, 255u, rep_s, stab_s);
-    const double norm_s = sqrt(fmax(static_cast<double>(stab_s), 0.0) / a.sym.group_order);
+    const double norm_s = s_norm[stab_s];
     int64_t out = a.offsets[r];
     auto emit = [&](uint64_t c, double coef, uint32_t b0, uint32_t b1) {
       uint64_t rep;
       uint32_t stab_c;
       orbit(c, b0, b1, rep, stab_c);
       if (lane == 0) {
-        const double norm_c = sqrt(fmax(static_cast<double>(stab_c), 0.0) / a.sym.group_order);
+        const double norm_c = s_norm[stab_c];  // the same sqrt(stab / |G|) the general kernels evaluate: bitwise equal outputs
         a.other_spins[out] = rep;
         a.other_coeffs[out] = coef * ((1.0 * norm_c) / norm_s);
       }
       ++out;
     };
-    auto flip_bits = [](uint64_t flip, uint32_t &b0, uint32_t &b1) {
-      b0 = static_cast<uint32_t>(__ffsll(static_cast<long long>(flip))) - 1u;
-      const uint64_t rest = flip & (flip - 1);
-      b1 = rest ? static_cast<uint32_t>(__ffsll(static_cast<long long>(rest))) - 1u : 255u;
-    };
     for (int m = 0; m < a.n_down; ++m) {
       const Move mv = s_moves[m];
       if ((s & mv.mask) != mv.need) continue;  // the same row on every lane: a uniform branch
-      uint32_t b0, b1;
-      flip_bits(mv.flip, b0, b1);
-      emit(s ^ mv.flip, mv.coef, b0, b1);
+      const uchar2 b = s_bits[m];
+      emit(s ^ mv.flip, mv.coef, b.x, b.y);
     }
     {
       double d = 0.0;
@@ -372,9 +394,8 @@ __global__ void __launch_bounds__(kOrbitThreads) apply_fill_orbit_kernel(const A
     for (int m = a.n_down; m < a.n_moves; ++m) {
       const Move mv = s_moves[m];
       if ((s & mv.mask) != mv.need) continue;
-      uint32_t b0, b1;
-      flip_bits(mv.flip, b0, b1);
-      emit(s ^ mv.flip, mv.coef, b0, b1);
+      const uchar2 b = s_bits[m];
+      emit(s ^ mv.flip, mv.coef, b.x, b.y);
     }
   }
 }
@@ -540,10 +561,12 @@ int asp_operator_apply_dev(asp_operator const *op, uint64_t num_rows, uint64_t c
   a.other_spins = d_other_spins;
   a.other_coeffs = d_other_coeffs;
   // moves that flip one or two bits (every two-site term) and a group of at most 32 * kOrbitK elements: one warp per row
-  bool warp_per_row = positive && g_apply_mode != 2 && op->d_perm_dst != nullptr && op->perms.size() <= 32u * kOrbitK;
+  bool warp_per_row = positive && g_apply_mode != 2 && op->d_perm_dst != nullptr && op->perms.size() <= 32u * kOrbitK &&
+                      op->number_spins <= 52;  // the orbit kernel carries a state as the double 2^52 + state
   for (const Move &mv : op->moves) warp_per_row = warp_per_row && __builtin_popcountll(mv.flip) <= 2;
   if (warp_per_row) {
-    const size_t osmem = smem + ((op->perms.size() + 31) / 32 * 32) * static_cast<size_t>(op->number_spins) * sizeof(uint2);
+    const size_t osmem = smem + ((op->perms.size() + 31) / 32 * 32) * static_cast<size_t>(op->number_spins + 1) * sizeof(uint2) +
+                         (static_cast<size_t>(a.sym.group_order) + 1) * sizeof(double) + ((op->moves.size() * 2 + 15) & ~size_t(15));
     ASP_REQUIRE(osmem <= 200 * 1024, "operator too large for shared memory");
     ASP_CUDA_CHECK(cudaFuncSetAttribute(apply_fill_orbit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(osmem)));
     int per_sm = 0;
