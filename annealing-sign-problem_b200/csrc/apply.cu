@@ -371,18 +371,39 @@ __global__ void __launch_bounds__(kOrbitThreads, 3) apply_fill_orbit_kernel(cons
       uint32_t stab_c;
       orbit(c, b0, b1, rep, stab_c);
       if (lane == 0) {
-        const double norm_c = s_norm[stab_c];  // the same sqrt(stab / |G|) the general kernels evaluate: bitwise equal outputs
+        // the same sqrt(stab / |G|) the general kernels evaluate; equal stabilisers (the usual case) give x / x = 1 exactly
+        const double ratio = stab_c == stab_s ? 1.0 : (1.0 * s_norm[stab_c]) / norm_s;
         a.other_spins[out] = rep;
-        a.other_coeffs[out] = coef * ((1.0 * norm_c) / norm_s);
+        a.other_coeffs[out] = coef * ratio;
       }
       ++out;
     };
-    for (int m = 0; m < a.n_down; ++m) {
-      const Move mv = s_moves[m];
-      if ((s & mv.mask) != mv.need) continue;  // the same row on every lane: a uniform branch
-      const uchar2 b = s_bits[m];
-      emit(s ^ mv.flip, mv.coef, b.x, b.y);
-    }
+    // which moves apply: lane l tests moves l, l + 32, ... and a ballot makes the answer a warp-uniform bit mask,
+    // so the candidate loops below visit applicable moves only (a row has ~37 of 144)
+    auto applicable = [&](int base) -> uint32_t {
+      const int m = base + static_cast<int>(lane);
+      bool on = false;
+      if (m < a.n_moves) {
+        const Move mv = s_moves[m];
+        on = (s & mv.mask) == mv.need;
+      }
+      return __ballot_sync(0xffffffffu, on);
+    };
+    auto emit_moves = [&](int first, int last) {  // moves [first, last) in order
+      for (int base = first & ~31; base < last; base += 32) {
+        uint32_t bits = applicable(base);
+        if (base < first) bits &= ~0u << (first - base);
+        if (base + 32 > last) bits &= (last - base) >= 32 ? ~0u : ((1u << (last - base)) - 1u);
+        while (bits) {
+          const int m = base + __ffs(static_cast<int>(bits)) - 1;
+          bits &= bits - 1;
+          const Move mv = s_moves[m];
+          const uchar2 b = s_bits[m];
+          emit(s ^ mv.flip, mv.coef, b.x, b.y);
+        }
+      }
+    };
+    emit_moves(0, a.n_down);
     {
       double d = 0.0;
       for (int k = 0; k < a.n_diag; ++k) {
@@ -391,12 +412,7 @@ __global__ void __launch_bounds__(kOrbitThreads, 3) apply_fill_orbit_kernel(cons
       }
       emit(s, d, 255u, 255u);
     }
-    for (int m = a.n_down; m < a.n_moves; ++m) {
-      const Move mv = s_moves[m];
-      if ((s & mv.mask) != mv.need) continue;
-      const uchar2 b = s_bits[m];
-      emit(s ^ mv.flip, mv.coef, b.x, b.y);
-    }
+    emit_moves(a.n_down, a.n_moves);
   }
 }
 
