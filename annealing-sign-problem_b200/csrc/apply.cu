@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(kOrbitThreads, 3) apply_fill_orbit_kernel(cons
     s_image[k] = make_uint2(static_cast<uint32_t>(image), static_cast<uint32_t>(image >> 32));
   }
   const uint32_t zero_row = static_cast<uint32_t>(number_spins);
-  const bool full_rounds = (a.sym.num_perms & 31) == 0;
+
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31;
   const int rounds = (a.sym.num_perms + 31) / 32;  // group elements per lane actually present (<= kOrbitK)
@@ -320,6 +320,7 @@ __global__ void __launch_bounds__(kOrbitThreads, 3) apply_fill_orbit_kernel(cons
     const bool top_in_hi = number_spins > 32;
     const uint32_t mask_lo = static_cast<uint32_t>(a.sym.state_mask), mask_hi = static_cast<uint32_t>(a.sym.state_mask >> 32);
     const uint32_t inv_all = inversion ? 0xFFFFFFFFu : 0u;
+    const bool in_last_round = static_cast<int>(lane) + 32 * (rounds - 1) < a.sym.num_perms;
     constexpr uint32_t kBiasHi = 0x43300000u;  // high word of 2^52
     auto orbit = [&](uint64_t c, uint32_t b0, uint32_t b1, uint64_t &rep, uint32_t &stab) {
       const uint64_t c_folded = fold(c);
@@ -342,18 +343,12 @@ __global__ void __launch_bounds__(kOrbitThreads, 3) apply_fill_orbit_kernel(cons
         fixed += y == c_d;
         best = y < best ? y : best;  // (no NaNs here: a plain compare-and-select, fmin would add its NaN fix-up)
       };
-      if (full_rounds) {  // every lane has an element in every round (|G| - 1 a multiple of 32, or padded below): no lane tests
+      // only the last round can have lanes without an element (|G| - 1 is rarely a multiple of 32): the test is on the
+      // round (uniform), not on every lane of every round
 #pragma unroll
-        for (int k = 0; k < kOrbitK; ++k) {
-          if (k >= rounds) break;  // (uniform) no group elements beyond
-          element(k);
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < kOrbitK; ++k) {
-          if (k >= rounds) break;
-          if (static_cast<int>(lane) + 32 * k < a.sym.num_perms) element(k);
-        }
+      for (int k = 0; k < kOrbitK; ++k) {
+        if (k >= rounds) break;  // (uniform) no group elements beyond
+        if (k < rounds - 1 || in_last_round) element(k);
       }
       const uint32_t bhi = static_cast<uint32_t>(__double2hiint(best)), blo = static_cast<uint32_t>(__double2loint(best));
       const uint32_t hi_min = __reduce_min_sync(0xffffffffu, bhi);

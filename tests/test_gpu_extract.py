@@ -351,7 +351,8 @@ def test_batched_apply_device_matches_oracle_including_symmetry_groups():
 def test_symmetrised_apply_fast_kernels_equal_the_general_ones_bitwise():
     """All characters +1: counts without visiting orbits + the warp-per-row orbit kernel (apply_fill_orbit_kernel)
     against the lane-per-row walk (apply_fill_positive_kernel) and the general move-by-move kernels."""
-    for system, m in [("heisenberg_kagome_36", 20000), ("heisenberg_pyrochlore_2x2x2", 5000), ("heisenberg_kagome_18", 24310)]:
+    for system, m in [("heisenberg_kagome_36", 20000), ("heisenberg_pyrochlore_2x2x2", 5000), ("heisenberg_kagome_18", 24310),
+                      ("j1j2_square_4x4", 3000), ("heisenberg_kagome_16", 2000)]:  # the last two: 16 spins, the top bit in the low word
         op = asp.load_hamiltonian(asp.ls.system_path(system))
         rows = op.basis.states if system == "heisenberg_kagome_18" else None
         if rows is None:
