@@ -256,6 +256,7 @@ __device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
   return (static_cast<uint64_t>(hi_min) << 32) | lo_min;
 }
 
+template <bool kTopInHi>  // more than 32 spins: the top bit of a state is in its high word
 __global__ void __launch_bounds__(kOrbitThreads, 3) apply_fill_orbit_kernel(const ApplyArgs a, const uint8_t *__restrict__ perm_dst, int number_spins) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Move *s_moves = reinterpret_cast<Move *>(smem_raw);
@@ -300,7 +301,9 @@ __global__ void __launch_bounds__(kOrbitThreads, 3) apply_fill_orbit_kernel(cons
 #pragma unroll
     for (int k = 0; k < kOrbitK; ++k) {
       const int e = static_cast<int>(lane) + 32 * k;
-      gs[k] = 0;
+      // a lane without an element in the last round carries 2^51: above every state, unchanged by the (all-zero) images
+      // and by the fold, so it never is the minimum and never equals the candidate -- no lane tests in the loops below
+      gs[k] = 1ull << 51;
       if (k < rounds && e < a.sym.num_perms) {
         const BitPerm &p = s_perms[e];
         uint64_t x = s;
@@ -317,10 +320,8 @@ __global__ void __launch_bounds__(kOrbitThreads, 3) apply_fill_orbit_kernel(cons
     // instruction each (DMNMX, DSETP) instead of two-word integer compare-and-select chains, and positive doubles order
     // like their bit patterns, so the warp minimum can stay on the integer halves.
     const uint32_t top_shift = 31u - ((number_spins - 1) & 31);
-    const bool top_in_hi = number_spins > 32;
     const uint32_t mask_lo = static_cast<uint32_t>(a.sym.state_mask), mask_hi = static_cast<uint32_t>(a.sym.state_mask >> 32);
     const uint32_t inv_all = inversion ? 0xFFFFFFFFu : 0u;
-    const bool in_last_round = static_cast<int>(lane) + 32 * (rounds - 1) < a.sym.num_perms;
     constexpr uint32_t kBiasHi = 0x43300000u;  // high word of 2^52
     auto orbit = [&](uint64_t c, uint32_t b0, uint32_t b1, uint64_t &rep, uint32_t &stab) {
       const uint64_t c_folded = fold(c);
@@ -336,19 +337,17 @@ __global__ void __launch_bounds__(kOrbitThreads, 3) apply_fill_orbit_kernel(cons
         const uint2 f0 = image0[32 * k], f1 = image1[32 * k];
         uint32_t lo = static_cast<uint32_t>(gs[k]) ^ f0.x ^ f1.x, hi = static_cast<uint32_t>(gs[k] >> 32) ^ f0.y ^ f1.y;
         // fold: under inversion a state with the top bit set is replaced by its complement
-        const uint32_t m = static_cast<uint32_t>(static_cast<int32_t>((top_in_hi ? hi : lo) << top_shift) >> 31) & inv_all;
+        const uint32_t m = static_cast<uint32_t>(static_cast<int32_t>((kTopInHi ? hi : lo) << top_shift) >> 31) & inv_all;
         lo ^= m & mask_lo;
         hi ^= m & mask_hi;
         const double y = __hiloint2double(static_cast<int>(hi | kBiasHi), static_cast<int>(lo));
         fixed += y == c_d;
         best = y < best ? y : best;  // (no NaNs here: a plain compare-and-select, fmin would add its NaN fix-up)
       };
-      // only the last round can have lanes without an element (|G| - 1 is rarely a multiple of 32): the test is on the
-      // round (uniform), not on every lane of every round
 #pragma unroll
       for (int k = 0; k < kOrbitK; ++k) {
         if (k >= rounds) break;  // (uniform) no group elements beyond
-        if (k < rounds - 1 || in_last_round) element(k);
+        element(k);
       }
       const uint32_t bhi = static_cast<uint32_t>(__double2hiint(best)), blo = static_cast<uint32_t>(__double2loint(best));
       const uint32_t hi_min = __reduce_min_sync(0xffffffffu, bhi);
@@ -573,18 +572,19 @@ int asp_operator_apply_dev(asp_operator const *op, uint64_t num_rows, uint64_t c
   a.other_coeffs = d_other_coeffs;
   // moves that flip one or two bits (every two-site term) and a group of at most 32 * kOrbitK elements: one warp per row
   bool warp_per_row = positive && g_apply_mode != 2 && op->d_perm_dst != nullptr && op->perms.size() <= 32u * kOrbitK &&
-                      op->number_spins <= 52;  // the orbit kernel carries a state as the double 2^52 + state
+                      op->number_spins <= 51;  // the orbit kernel carries a state as the double 2^52 + state, 2^51 marks "no element"
   for (const Move &mv : op->moves) warp_per_row = warp_per_row && __builtin_popcountll(mv.flip) <= 2;
   if (warp_per_row) {
     const size_t osmem = smem + ((op->perms.size() + 31) / 32 * 32) * static_cast<size_t>(op->number_spins + 1) * sizeof(uint2) +
                          (static_cast<size_t>(a.sym.group_order) + 1) * sizeof(double) + ((op->moves.size() * 2 + 15) & ~size_t(15));
     ASP_REQUIRE(osmem <= 200 * 1024, "operator too large for shared memory");
-    ASP_CUDA_CHECK(cudaFuncSetAttribute(apply_fill_orbit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(osmem)));
+    void (*const orbit_kernel)(const ApplyArgs, const uint8_t *, int) = op->number_spins > 32 ? apply_fill_orbit_kernel<true> : apply_fill_orbit_kernel<false>;
+    ASP_CUDA_CHECK(cudaFuncSetAttribute(orbit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(osmem)));
     int per_sm = 0;
-    ASP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, apply_fill_orbit_kernel, kOrbitThreads, osmem));
+    ASP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, orbit_kernel, kOrbitThreads, osmem));
     const uint64_t want = (num_rows + kOrbitThreads / 32 - 1) / (kOrbitThreads / 32);
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(want, static_cast<uint64_t>(kNumSMs) * std::max(per_sm, 1)));
-    apply_fill_orbit_kernel<<<grid, kOrbitThreads, osmem, s>>>(a, op->d_perm_dst, static_cast<int>(op->number_spins));
+    orbit_kernel<<<grid, kOrbitThreads, osmem, s>>>(a, op->d_perm_dst, static_cast<int>(op->number_spins));
   } else if (positive) {
     ASP_CUDA_CHECK(cudaFuncSetAttribute(apply_fill_positive_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     apply_fill_positive_kernel<<<blocks, kApplyThreads, smem, s>>>(a);
