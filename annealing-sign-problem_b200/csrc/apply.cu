@@ -73,6 +73,9 @@ struct ApplyArgs {
   int n_moves, n_down;
   const DiagBond *diag;
   int n_diag;
+  const DiagGroup *groups;  // closed form of the diagonal (operator.cuh), n_groups < 0: not available
+  int n_groups, diag_scale;
+  long long diag_c0;
   SymmetryView sym;
   bool symmetrised;
   int64_t *counts;         // pass 1 out / unused
@@ -400,9 +403,20 @@ __global__ void __launch_bounds__(kOrbitThreads, 3) apply_fill_orbit_kernel(cons
     emit_moves(0, a.n_down);
     {
       double d = 0.0;
-      for (int k = 0; k < a.n_diag; ++k) {
-        const DiagBond db = s_diag[k];
-        d += db.d[((s >> db.i) & 1) * 2 + ((s >> db.j) & 1)];
+      if (a.n_groups >= 0) {
+        // every diagonal entry a small dyadic rational: the sum in exact integer arithmetic (a few popcounts) is bit for
+        // bit the bond-by-bond f64 sum of the general kernels (the same closed form extract_csr_kernel uses)
+        long long acc = a.diag_c0;
+        for (int g = 0; g < a.n_groups; ++g) {
+          const DiagGroup grp = a.groups[g];
+          acc += static_cast<long long>(grp.weight) * __popcll(s & (s >> grp.shift) & grp.sites);
+        }
+        d = scalbn(static_cast<double>(acc), -a.diag_scale);
+      } else {
+        for (int k = 0; k < a.n_diag; ++k) {
+          const DiagBond db = s_diag[k];
+          d += db.d[((s >> db.i) & 1) * 2 + ((s >> db.j) & 1)];
+        }
       }
       emit(s, d, 255u, 255u);
     }
@@ -527,6 +541,10 @@ int asp_operator_apply_dev(asp_operator const *op, uint64_t num_rows, uint64_t c
   a.n_down = static_cast<int>(op->n_down);
   a.diag = op->d_diag;
   a.n_diag = static_cast<int>(op->diag.size());
+  a.groups = op->d_diag_groups;
+  a.n_groups = (op->diag_scale >= 0 && op->d_diag_groups) ? static_cast<int>(op->diag_groups.size()) : -1;
+  a.diag_scale = op->diag_scale;
+  a.diag_c0 = op->diag_c0;
   a.symmetrised = op->symmetrised();
   a.sym.perms = op->d_perms;
   a.sym.characters = op->d_characters;
