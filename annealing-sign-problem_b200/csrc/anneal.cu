@@ -410,8 +410,7 @@ constexpr int kStageSlots = 33;  // 32 staged entries + one: the row loop reads 
 template <bool kField>  // kField = false: every field is zero, nothing of it is read
 __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm) sa_sweep_kernel(const SaArgs a) {
   __shared__ StagedEntry s_stage[kSaWarps][kStageSlots];
-  uint32_t lane = threadIdx.x & 31;
-  asm volatile("" : "+r"(lane));  // opaque: kept in a register instead of being re-read from the thread index in the task loop
+  const uint32_t lane = threadIdx.x & 31;
   // broadcast from lane 0: tells the compiler that the warp index -- and with it every task loop below -- is warp-uniform
   const uint32_t warp_in_cta = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const uint32_t team = blockIdx.x / a.team_size;
