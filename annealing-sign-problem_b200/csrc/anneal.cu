@@ -393,8 +393,7 @@ __device__ __forceinline__ double staged_entry(const uint4 e, uint32_t up) {
   return __hiloint2double(static_cast<int>(e.y ^ (~(e.z << up) & 0x80000000u)), static_cast<int>(e.x));
 }
 
-__device__ __forceinline__ double staged_row_sum(const StagedEntry *stage, int32_t lo, int32_t hi, uint32_t up) {
-  double acc = 0.0;
+__device__ __forceinline__ double staged_row_sum(const StagedEntry *stage, int32_t lo, int32_t hi, uint32_t up, double acc = 0.0) {
   const uint4 *p = reinterpret_cast<const uint4 *>(stage) + lo, *const last = reinterpret_cast<const uint4 *>(stage) + (hi - 1);
 #pragma unroll 1
   for (; p <= last; p += 2) {
@@ -552,13 +551,38 @@ __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm) sa_sweep_kernel(cons
             acc[2] = staged_row_sum(stage, rows.y, rows.z, up);
             acc[3] = staged_row_sum(stage, rows.z, rows.w, up);
           } else {
-            TaskRows tr;
-            tr.b[0] = 0;
-            tr.b[1] = rows.x;
-            tr.b[2] = rows.y;
-            tr.b[3] = rows.z;
-            tr.b[4] = rows.w;
-            accumulate_rows(tr, __ldg(&a.indptr[static_cast<uint64_t>(q_now) * 4]), cur_pv, wv, a.indices, a.data, words, stage, lane, acc);
+            // longer rows (SK-type and dense models): the span goes through the stage in chunks of 32 entries; the
+            // (value, column, spin word) of the NEXT chunk are on their way while this one is summed, and a row that
+            // crosses a chunk boundary carries its partial sum on (same order of additions)
+            const int64_t e_begin = __ldg(&a.indptr[static_cast<uint64_t>(q_now) * 4]);
+            acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
+            double pv_c = cur_pv;
+            uint32_t wv_c = wv;
+            for (int32_t cb = 0;; cb += 32) {
+              double pv_n = 0.0;
+              uint32_t wv_n = 0u;
+              const int32_t mine = cb + 32 + static_cast<int32_t>(lane);
+              if (mine < rows.w) {
+                pv_n = __ldg(&a.data[e_begin + mine]);
+                wv_n = __ldcg(&words[__ldg(&a.indices[e_begin + mine])]);
+              }
+              __syncwarp();
+              StagedEntry se;
+              se.val = pv_c;
+              se.word = wv_c;
+              se.pad = 0;
+              stage[lane] = se;
+              __syncwarp();
+              const int32_t b[5] = {0, rows.x, rows.y, rows.z, rows.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int32_t lo = max(b[j], cb) - cb, hi = min(b[j + 1], cb + 32) - cb;
+                if (lo < hi) acc[j] = staged_row_sum(stage, lo, hi, up, acc[j]);
+              }
+              if (cb + 32 >= rows.w) break;
+              pv_c = pv_n;
+              wv_c = wv_n;
+            }
           }
           const uint32_t cur_w[4] = {cur.x, cur.y, cur.z, cur.w};
           // dE = -s (4 sum + 2 h): 4 acc is exact, so one fma rounds like the oracle's mul, mul, add;
