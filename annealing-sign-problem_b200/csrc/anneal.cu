@@ -279,6 +279,7 @@ struct SaArgs {
   const int4 *bounds;    // [n_padded / 4] row boundaries of each warp-task, relative to its first entry
   PhiloxKeys round_keys; // key schedule of `seed`
   unsigned int *tickets; // [num_teams][num_classes] chunk tickets, zeroed by the host
+  uint32_t stage_slots;  // staged entries per warp: kStageSlots, or kStageSlotsWide when a task of the model spans more than 32 entries
 };
 
 constexpr int kSaThreads = 256;
@@ -382,6 +383,13 @@ __global__ void __launch_bounds__(256) task_bounds_kernel(uint64_t tasks, const 
                         static_cast<int>(indptr[q * 4 + 4] - b0));
 }
 
+// how many tasks span more than one staged chunk (32 entries)
+__global__ void __launch_bounds__(256) long_tasks_kernel(uint64_t tasks, const int4 *__restrict__ bounds, unsigned long long *__restrict__ out) {
+  const uint64_t q = static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x;
+  const unsigned int n = __popc(__ballot_sync(0xffffffffu, q < tasks && bounds[q].w > 32));
+  if ((threadIdx.x & 31) == 0 && n) atomicAdd(out, static_cast<unsigned long long>(n));
+}
+
 __global__ void __launch_bounds__(256) any_field_kernel(uint64_t n_padded, const double *__restrict__ field, uint32_t *__restrict__ out) {
   const uint64_t p = static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x;
   if (p < n_padded && field[p] != 0.0) *out = 1u;
@@ -404,11 +412,58 @@ __device__ __forceinline__ double staged_row_sum(const StagedEntry *stage, int32
   return acc;
 }
 
-constexpr int kStageSlots = 33;  // 32 staged entries + one: the row loop reads two entries per trip
+// Rows of 9..40 couplings (SK-type models, small full-basis models): the whole span of a task fits the wide stage.  The
+// first 32 entries came with the pipeline; the other chunks are loaded here, ALL loads before the first use (values and
+// columns, then the gathered spin words), so the task pays two memory round trips, not two per chunk; then the four rows
+// are summed straight from the stage.  Not inlined: the register allocation of the short-row path stays as it is.
+struct Sum4 {
+  double v[4];
+};
+__device__ __noinline__ Sum4 wide_task_sums(const double *__restrict__ data, const int32_t *__restrict__ indices, const uint32_t *words, StagedEntry *stage,
+                                            int64_t e_begin, int4 rows, double first_pv, uint32_t first_wv, uint32_t lane) {
+  const uint32_t up = 31u - lane;
+  double pvx[4];
+  int32_t pix[4];
+  uint32_t wvx[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int32_t mine = 32 + 32 * c + static_cast<int32_t>(lane);
+    pvx[c] = 0.0;
+    pix[c] = -1;
+    if (mine < rows.w) {
+      pvx[c] = __ldg(&data[e_begin + mine]);
+      pix[c] = __ldg(&indices[e_begin + mine]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) wvx[c] = pix[c] >= 0 ? __ldcg(&words[pix[c]]) : 0u;
+  __syncwarp();
+  StagedEntry se;
+  se.val = first_pv;
+  se.word = first_wv;
+  se.pad = 0;
+  stage[lane] = se;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    se.val = pvx[c];
+    se.word = wvx[c];
+    stage[32 + 32 * c + lane] = se;
+  }
+  __syncwarp();
+  Sum4 out;
+  out.v[0] = staged_row_sum(stage, 0, rows.x, up);
+  out.v[1] = staged_row_sum(stage, rows.x, rows.y, up);
+  out.v[2] = staged_row_sum(stage, rows.y, rows.z, up);
+  out.v[3] = staged_row_sum(stage, rows.z, rows.w, up);
+  return out;
+}
+
+constexpr int kStageSlots = 34;        // 32 staged entries + two: the row loop reads two entries per trip
+constexpr int kStageSlotsWide = 162;   // 32 + 4 x 32 + two: models with a task span above 32 entries (SaArgs::stage_slots)
 
 template <bool kField>  // kField = false: every field is zero, nothing of it is read
 __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm) sa_sweep_kernel(const SaArgs a) {
-  __shared__ StagedEntry s_stage[kSaWarps][kStageSlots];
+  extern __shared__ __align__(16) unsigned char sa_smem[];  // [kSaWarps][a.stage_slots] staged entries
   const uint32_t lane = threadIdx.x & 31;
   // broadcast from lane 0: tells the compiler that the warp index -- and with it every task loop below -- is warp-uniform
   const uint32_t warp_in_cta = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -419,7 +474,7 @@ __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm) sa_sweep_kernel(cons
   const uint32_t my_warp = member * kSaWarps + warp_in_cta;
   const uint32_t up = 31u - lane, lane_bit = 1u << lane;
   TeamBarrier bar{a.barriers + team, 0ull, a.team_size};
-  StagedEntry *stage = s_stage[warp_in_cta];
+  StagedEntry *stage = reinterpret_cast<StagedEntry *>(sa_smem) + static_cast<size_t>(warp_in_cta) * a.stage_slots;
 
   for (uint32_t g = team; g < a.groups; g += a.num_teams) {
     uint32_t *words = a.words + static_cast<uint64_t>(g) * a.n_padded;
@@ -550,8 +605,14 @@ __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm) sa_sweep_kernel(cons
             acc[1] = staged_row_sum(stage, rows.x, rows.y, up);
             acc[2] = staged_row_sum(stage, rows.y, rows.z, up);
             acc[3] = staged_row_sum(stage, rows.z, rows.w, up);
+          } else if (rows.w <= 160 && a.stage_slots >= static_cast<uint32_t>(kStageSlotsWide)) {
+            const Sum4 sums = wide_task_sums(a.data, a.indices, words, stage, __ldg(&a.indptr[static_cast<uint64_t>(q_now) * 4]), rows, cur_pv, wv, lane);
+            acc[0] = sums.v[0];
+            acc[1] = sums.v[1];
+            acc[2] = sums.v[2];
+            acc[3] = sums.v[3];
           } else {
-            // longer rows (SK-type and dense models): the span goes through the stage in chunks of 32 entries; the
+            // longer rows still (dense models): the span goes through the stage in chunks of 32 entries; the
             // (value, column, spin word) of the NEXT chunk are on their way while this one is summed, and a row that
             // crosses a chunk boundary carries its partial sum on (same order of additions)
             const int64_t e_begin = __ldg(&a.indptr[static_cast<uint64_t>(q_now) * 4]);
@@ -969,7 +1030,15 @@ int asp_sa_plan_create(asp_sa_plan **out, uint64_t n, int64_t const *d_indptr, i
     ASP_LAUNCH_CHECK();
     ASP_CUDA_CHECK(cudaMemcpyAsync(&any_field, d_part, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     ASP_CUDA_CHECK(cudaStreamSynchronize(s));
+    unsigned long long long_tasks = 0;
+    unsigned long long *d_long = reinterpret_cast<unsigned long long *>(d_part);
+    ASP_CUDA_CHECK(cudaMemsetAsync(d_long, 0, sizeof(unsigned long long), s));
+    long_tasks_kernel<<<static_cast<unsigned>((np / 4 + 255) / 256), 256, 0, s>>>(np / 4, plan->d_bounds, d_long);
+    ASP_LAUNCH_CHECK();
+    ASP_CUDA_CHECK(cudaMemcpyAsync(&long_tasks, d_long, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    ASP_CUDA_CHECK(cudaStreamSynchronize(s));
     plan->has_field = any_field != 0;
+    plan->long_tasks = long_tasks;
     ASP_CUDA_CHECK(cudaFreeAsync(d_part, s));
   }
   ASP_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -1021,7 +1090,10 @@ int asp_sa_anneal(asp_sa_plan *plan, uint32_t num_replicas, uint32_t replica_off
   ASP_CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
   ASP_REQUIRE(coop != 0, "device does not support cooperative launches");
   void *const sweep = plan->has_field ? reinterpret_cast<void *>(sa_sweep_kernel<true>) : reinterpret_cast<void *>(sa_sweep_kernel<false>);
-  ASP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<void (*)(SaArgs)>(sweep), kSaThreads, 0));
+  // the wide stage (20 KB of shared memory per CTA, taken from L1) pays when long tasks are common, not for a stray one
+  const uint32_t stage_slots = plan->long_tasks * 64 > plan->n_padded / 4 ? kStageSlotsWide : kStageSlots;
+  const size_t sweep_smem = static_cast<size_t>(kSaWarps) * stage_slots * sizeof(StagedEntry);
+  ASP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<void (*)(SaArgs)>(sweep), kSaThreads, sweep_smem));
   ASP_REQUIRE(per_sm >= 1, "sweep kernel does not fit on an SM");
   const uint32_t max_ctas = static_cast<uint32_t>(sms * per_sm);
 
@@ -1033,6 +1105,7 @@ int asp_sa_anneal(asp_sa_plan *plan, uint32_t num_replicas, uint32_t replica_off
   a.field = plan->d_field;
   a.class_ptr = plan->d_class_ptr;
   a.bounds = plan->d_bounds;
+  a.stage_slots = stage_slots;
   a.num_classes = plan->num_classes;
   a.groups = groups;
   if (groups >= max_ctas) {
@@ -1086,7 +1159,7 @@ int asp_sa_anneal(asp_sa_plan *plan, uint32_t num_replicas, uint32_t replica_off
   if (num_sweeps > 0) {
     void *params[] = {&a};
     const unsigned grid = a.num_teams * a.team_size;
-    ASP_CUDA_CHECK(cudaLaunchCooperativeKernel(sweep, dim3(grid), dim3(kSaThreads), params, 0, s));
+    ASP_CUDA_CHECK(cudaLaunchCooperativeKernel(sweep, dim3(grid), dim3(kSaThreads), params, sweep_smem, s));
     g_launches.fetch_add(1, std::memory_order_relaxed);
   }
   {

@@ -25,6 +25,7 @@ struct asp_sa_plan {
   int64_t *d_class_ptr = nullptr; // [num_classes + 1]
   int4 *d_bounds = nullptr;       // [n_padded / 4] row boundaries of the sweep kernel's 4-position tasks (relative to the first entry)
   bool has_field = false;         // any h_p != 0
+  uint64_t long_tasks = 0;        // 4-position tasks with more than 32 CSR entries (one staged chunk)
   std::vector<int64_t> class_ptr;
   double diag_sum = 0.0;          // sum_i J_ii of the original model (constant part of the energy)
   double max_de = 0.0;            // max_p (4 sum_j |J_pj| + 2 |h_p|): bound on any single-flip energy change
