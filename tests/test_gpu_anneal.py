@@ -86,6 +86,7 @@ def oracle_best(ex, pos, n, capi, R, betas, seed, escale, x0=None):
 
 @pytest.mark.parametrize("n,density,with_field,R,S", [
     (300, 0.05, False, 64, 40), (777, 0.02, True, 33, 25), (2000, 0.004, False, 96, 12), (50, 0.5, True, 7, 60),
+    (120, 0.6, True, 40, 10),  # ~70 couplings per row: a task spans more than the wide stage (chunk-by-chunk path)
 ])
 def test_sweep_kernel_is_bit_identical_to_the_oracle(oracle_capi, n, density, with_field, R, S):
     csr, h = random_model(n, density, seed=n)
