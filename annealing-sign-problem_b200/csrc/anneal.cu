@@ -458,10 +458,86 @@ __device__ __noinline__ Sum4 wide_task_sums(const double *__restrict__ data, con
   return out;
 }
 
+// One class phase with ONE POSITION per warp-task -- for classes so small that the team has a warp for (nearly) every
+// position: four times the warps of the 4-position tasks work at once and a task is a quarter as long, which is what
+// counts when a phase is a single task deep (small models, few replicas: the time between two barriers is the latency
+// of one task).  All the loads of a row are issued before the first use.  Same arithmetic per position, the same variate
+// (component p % 4 of the Philox block of task p / 4), so the chain is unchanged.  Rows longer than the stage holds go
+// through it piece by piece.  Not inlined: the register allocation of the main task loop stays as it is.
+__device__ __noinline__ long long fine_class_phase(const int64_t *__restrict__ indptr, const int4 *__restrict__ bounds, const double *__restrict__ data,
+                                                   const int32_t *__restrict__ indices, const double *__restrict__ field, uint32_t *words,
+                                                   StagedEntry *stage, uint32_t stage_slots, uint32_t p_begin, uint32_t p_end, uint32_t my_warp,
+                                                   uint32_t team_warps, uint32_t lane, uint32_t t, uint32_t stream_id, double beta, double escale,
+                                                   uint2 key) {
+  const uint32_t up = 31u - lane, lane_bit = 1u << lane;
+  const int32_t room = static_cast<int32_t>(stage_slots) - 2;  // entries the stage holds: 32 or 160
+  long long rel_delta = 0;
+  for (uint32_t p = p_begin + my_warp; p < p_end; p += team_warps) {
+    const uint32_t q = p >> 2, j = p & 3u;
+    const int64_t e_task = __ldg(&indptr[static_cast<uint64_t>(q) * 4]);
+    const int4 bd = __ldg(&bounds[q]);
+    const uint32_t cur_w = __ldcg(&words[p]);
+    const double f2 = field ? __dmul_rn(2.0, __ldg(&field[p])) : 0.0;
+    const int32_t lo = j == 0 ? 0 : (j == 1 ? bd.x : (j == 2 ? bd.y : bd.z)), hi = j == 0 ? bd.x : (j == 1 ? bd.y : (j == 2 ? bd.z : bd.w));
+    const int64_t e_row = e_task + lo;
+    const int32_t len = hi - lo;
+    double acc = 0.0;
+    for (int32_t base = 0; base < len || base == 0; base += room) {
+      const int32_t piece = min(len - base, room);
+      double pvx[5];
+      int32_t pix[5];
+      uint32_t wvx[5];
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        const int32_t mine = 32 * c + static_cast<int32_t>(lane);
+        pvx[c] = 0.0;
+        pix[c] = -1;
+        if (mine < piece) {
+          pvx[c] = __ldg(&data[e_row + base + mine]);
+          pix[c] = __ldg(&indices[e_row + base + mine]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 5; ++c) wvx[c] = pix[c] >= 0 ? __ldcg(&words[pix[c]]) : 0u;
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        if (32 * c < room) {  // (uniform) the narrow stage holds one chunk
+          StagedEntry se;
+          se.val = pvx[c];
+          se.word = wvx[c];
+          se.pad = 0;
+          stage[32 * c + lane] = se;
+        }
+      }
+      __syncwarp();
+      acc = staged_row_sum(stage, 0, piece, up, acc);
+      if (len == 0) break;
+    }
+    const double gsum = __fma_rn(4.0, acc, f2);
+    const uint32_t neg = (cur_w << up) & 0x80000000u;  // spin up: dE = -gsum
+    const double dE = __hiloint2double(__double2hiint(gsum) ^ static_cast<int>(neg), __double2loint(gsum));
+    const double x = __dmul_rn(beta, dE);
+    const uint32_t uphill = __ballot_sync(0xffffffffu, dE > 0.0 && x < kRejectAbove);
+    uint32_t accepted = __ballot_sync(0xffffffffu, !(dE > 0.0));
+    if (uphill) {
+      const uint4 rnd = philox4x32_10(make_uint4(q, t, stream_id, 0u), key);
+      const uint32_t r = j == 0 ? rnd.x : (j == 1 ? rnd.y : (j == 2 ? rnd.z : rnd.w));
+      accepted |= __ballot_sync(0xffffffffu, accept_uphill(x, r)) & uphill;
+    }
+    if (accepted & lane_bit) rel_delta += round_to_ll(__dmul_rn(dE, escale));
+    if (lane == 0) __stcg(&words[p], cur_w ^ accepted);
+  }
+  return rel_delta;
+}
+
 constexpr int kStageSlots = 34;        // 32 staged entries + two: the row loop reads two entries per trip
 constexpr int kStageSlotsWide = 162;   // 32 + 4 x 32 + two: models with a task span above 32 entries (SaArgs::stage_slots)
 
-template <bool kField>  // kField = false: every field is zero, nothing of it is read
+// kField = false: every field is zero, nothing of it is read.  kFine = true: a model so small that the team has a warp for
+// (nearly) every position of its biggest class -- every class phase is fine_class_phase (one position per task); the host
+// picks the instantiation, so the 4-position task loop below is compiled without the call.
+template <bool kField, bool kFine>
 __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm) sa_sweep_kernel(const SaArgs a) {
   extern __shared__ __align__(16) unsigned char sa_smem[];  // [kSaWarps][a.stage_slots] staged entries
   const uint32_t lane = threadIdx.x & 31;
@@ -496,6 +572,13 @@ __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm) sa_sweep_kernel(cons
         // replica).  The ticket for the NEXT chunk is drawn when a chunk begins (lane 0; read by shuffle when
         // needed).  Small classes (fewer than four chunks per warp) are dealt out task by task with a fixed
         // stride instead -- every warp gets work, and no atomic sits on the path between two barriers.
+        if constexpr (kFine) {
+          rel_delta += fine_class_phase(a.indptr, a.bounds, a.data, a.indices, kField ? a.field : nullptr, words, stage, a.stage_slots, q_begin * 4u,
+                                        q_end * 4u, my_warp, team_warps, lane, t, stream_id, beta, a.escale,
+                                        make_uint2(static_cast<uint32_t>(a.seed), static_cast<uint32_t>(a.seed >> 32)));
+          bar.sync();
+          continue;
+        }
         unsigned int *const ticket_counter = a.tickets + static_cast<uint64_t>(team) * a.num_classes + c;
         const bool dealt = (q_end - q_begin) < 4u * kSaChunk * team_warps;
         const uint32_t chunk = dealt ? 1u : kSaChunk;
@@ -1089,11 +1172,19 @@ int asp_sa_anneal(asp_sa_plan *plan, uint32_t num_replicas, uint32_t replica_off
   ASP_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   ASP_CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
   ASP_REQUIRE(coop != 0, "device does not support cooperative launches");
-  void *const sweep = plan->has_field ? reinterpret_cast<void *>(sa_sweep_kernel<true>) : reinterpret_cast<void *>(sa_sweep_kernel<false>);
+  // (chosen below, once the team size is known)
+  void *sweep = nullptr;
   // the wide stage (20 KB of shared memory per CTA, taken from L1) pays when long tasks are common, not for a stray one
   const uint32_t stage_slots = plan->long_tasks * 64 > plan->n_padded / 4 ? kStageSlotsWide : kStageSlots;
   const size_t sweep_smem = static_cast<size_t>(kSaWarps) * stage_slots * sizeof(StagedEntry);
-  ASP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<void (*)(SaArgs)>(sweep), kSaThreads, sweep_smem));
+  {
+    void (*const quad)(SaArgs) = plan->has_field ? sa_sweep_kernel<true, false> : sa_sweep_kernel<false, false>;
+    void (*const fine)(SaArgs) = plan->has_field ? sa_sweep_kernel<true, true> : sa_sweep_kernel<false, true>;
+    int per_sm_fine = 0;
+    ASP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, quad, kSaThreads, sweep_smem));
+    ASP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_fine, fine, kSaThreads, sweep_smem));
+    per_sm = std::min(per_sm, per_sm_fine);
+  }
   ASP_REQUIRE(per_sm >= 1, "sweep kernel does not fit on an SM");
   const uint32_t max_ctas = static_cast<uint32_t>(sms * per_sm);
 
@@ -1115,14 +1206,26 @@ int asp_sa_anneal(asp_sa_plan *plan, uint32_t num_replicas, uint32_t replica_off
     a.team_size = max_ctas / groups;
     a.num_teams = groups;
   }
-  // a team larger than the work of the biggest class only adds barrier latency
+  // A team larger than the work of the biggest class only adds barrier latency.  When the team can have a warp for
+  // (nearly) every POSITION of the biggest class, the whole model runs one position per task (the fine kernel); otherwise
+  // the team is sized for one 4-position task per warp.
+  bool fine_model = false;
   {
     int64_t biggest = 4;
     for (uint32_t c = 0; c < plan->num_classes; ++c) biggest = std::max(biggest, plan->class_ptr[c + 1] - plan->class_ptr[c]);
-    const uint32_t useful = static_cast<uint32_t>((biggest / 4 + kSaWarps - 1) / kSaWarps);
-    a.team_size = std::max(1u, std::min(a.team_size, useful));
-    if (g_sa_team_cap > 0) a.team_size = std::min(a.team_size, static_cast<uint32_t>(g_sa_team_cap));
+    uint32_t team_fine = std::max(1u, std::min(a.team_size, static_cast<uint32_t>((biggest + kSaWarps - 1) / kSaWarps)));
+    if (g_sa_team_cap > 0) team_fine = std::min(team_fine, static_cast<uint32_t>(g_sa_team_cap));
+    fine_model = biggest <= 2ll * team_fine * kSaWarps;
+    if (fine_model) {
+      a.team_size = team_fine;
+    } else {
+      const uint32_t useful = static_cast<uint32_t>((biggest / 4 + kSaWarps - 1) / kSaWarps);
+      a.team_size = std::max(1u, std::min(a.team_size, useful));
+      if (g_sa_team_cap > 0) a.team_size = std::min(a.team_size, static_cast<uint32_t>(g_sa_team_cap));
+    }
   }
+  sweep = plan->has_field ? (fine_model ? reinterpret_cast<void *>(sa_sweep_kernel<true, true>) : reinterpret_cast<void *>(sa_sweep_kernel<true, false>))
+                          : (fine_model ? reinterpret_cast<void *>(sa_sweep_kernel<false, true>) : reinterpret_cast<void *>(sa_sweep_kernel<false, false>));
   a.num_sweeps = num_sweeps;
   a.replica_offset = replica_offset;
   a.seed = seed;
