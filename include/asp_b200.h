@@ -243,6 +243,9 @@ int asp_accuracy_overlap(uint64_t n, uint32_t num_replicas, uint64_t const *d_pr
  *    at row adjacency only) -- the caller's job, like the reference's preconditions; the Python
  *    mirror checks it.  The plan BORROWS d_indptr / d_indices / d_data / d_field (the greedy
  *    solver and the energy pass read the original model): they must outlive the plan.
+ *    Everything is built on the device in `stream` (the plan's own buffers come from the
+ *    device's stream-ordered memory pool); the call returns when the plan is complete, and
+ *    asp_sa_plan_destroy waits for the device before it hands the buffers back.
  * ---------------------------------------------------------------------------------- */
 int asp_sa_plan_create(asp_sa_plan **out, uint64_t n, int64_t const *d_indptr,
                        int32_t const *d_indices, double const *d_data, double const *d_field,
