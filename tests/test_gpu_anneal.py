@@ -138,6 +138,39 @@ def test_ticketed_task_hand_out_is_bit_identical_to_the_oracle(oracle_capi):
     assert np.array_equal(bits_free.cpu().numpy().view(np.uint64), ref_bits)
 
 
+def test_a_few_long_rows_in_a_sparse_model(oracle_capi):
+    """A sparse model (narrow stage: long tasks are rare) with three hub spins of 90, 200 and 40 couplings: the hubs' rows go
+    through the stage piece by piece, in both task shapes (a warp per position / 4-position tasks with the team capped)."""
+    from annealing_sign_problem_b200._lib import lib
+
+    n, R, S = 4000, 40, 8
+    rng = np.random.default_rng(11)
+    a = scipy.sparse.random(n, n, density=0.0008, random_state=rng, data_rvs=rng.standard_normal).tolil()
+    for hub, degree in ((17, 90), (2500, 200), (3999, 40)):
+        for j in rng.choice(n, size=degree, replace=False):
+            if j != hub:
+                a[hub, j] = rng.standard_normal()
+    a = a.tocsr()
+    csr = (a + a.T).tocsr()
+    csr.sort_indices()
+    h = np.zeros(n)
+    ham = asp.sa.Hamiltonian(csr, h)
+    plan = asp.sa.AnnealPlan(ham)
+    ex, pos = check_plan(plan, csr, h)
+    assert np.diff(ex["indptr"]).max() > 160
+    betas = asp.sa.default_betas(ham, S)
+    escale = asp.sa.energy_scale(ham)
+    for seed in SEEDS[:2]:
+        ref_bits, _ = oracle_best(ex, pos, n, oracle_capi, R, betas, seed, escale)
+        for cap in (0, 1):
+            lib().asp_debug_set_sa_team_ctas(cap)
+            try:
+                bits, _ = plan.anneal_device(R, betas, seed, escale=escale)
+            finally:
+                lib().asp_debug_set_sa_team_ctas(0)
+            assert np.array_equal(bits.cpu().numpy().view(np.uint64), ref_bits), "seed %d, team cap %d" % (seed, cap)
+
+
 def test_x0_start_and_only_best_selection(oracle_capi):
     n = 500
     csr, h = random_model(n, 0.03, seed=9)
